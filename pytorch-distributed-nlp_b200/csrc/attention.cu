@@ -1,0 +1,531 @@
+// Fused multi-head self-attention, forward and backward, on tcgen05 tensor cores (head_dim 64, seq % 128 == 0).
+//
+// Replaces the eager attention of BertSelfAttention (SP/transformers/models/bert/modeling_bert.py:115-140:
+// matmul -> *scale -> +mask -> softmax -> dropout -> matmul, and the transpose/contiguous head merge at :138,:206)
+// plus its autograd backward.  The [B,12,S,S] probability tensor never exists in HBM: the
+// backward recomputes it from Q, K and the saved log-sum-exp.
+//
+// One CTA = 128 threads = 128 query (fwd) or key (bwd) rows = the 128 TMEM lanes; thread r owns row r.
+// Tiles move HBM->smem by TMA straight out of the packed [tokens, 3*hidden] QKV activation (128B swizzle);
+// the same smem tile serves as a K-major operand for one product and as an MN-major operand for another
+// (e.g. dO is A of dP = dO V^T and B of dV = P^T dO), so nothing is ever transposed in memory.
+#include "common.cuh"
+#include "../../include/b2_ddp_bert.h"
+
+namespace b2 {
+
+constexpr int ATT_THREADS = 128;
+constexpr int TILE_BYTES = 128 * 64 * 2;  // one [128 x 64] bf16 tile = 16 KB
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+constexpr float kMaskBias = -3.4028234663852886e38f;  // torch.finfo(float32).min, what HF adds for masked keys
+
+// [128 rows x 128 cols] bf16 tile as two 64-column sub-tiles of 128-byte swizzled rows.  Read as a K-major operand
+// (rows = M, cols = K) or as an MN-major operand (rows = K, cols = M) depending on the descriptor.
+__device__ __forceinline__ void st_tile_chunk(uint8_t* tile, int row, int chunk /*0..15, 8 elements each*/, uint4 v) {
+  const int sub = chunk >> 3, ch = chunk & 7;
+  *reinterpret_cast<uint4*>(tile + sub * TILE_BYTES + row * 128 + ((ch ^ (row & 7)) << 4)) = v;
+}
+
+struct AttnParams {
+  int batch, seq, heads, hidden;  // hidden = heads * 64
+  float scale;                    // 1/sqrt(64)
+  float dropout_p; const unsigned long long* rng; unsigned rng_site;
+  const long long* mask;          // [batch, seq] or null
+  __nv_bfloat16* ctx;             // fwd out [tokens, hidden]
+  float* lse;                     // [batch, heads, seq] natural log
+  // backward
+  const __nv_bfloat16* ctx_in; const __nv_bfloat16* d_ctx;
+  __nv_bfloat16* d_qkv; float* dq_accum;
+};
+
+// ------------------------------------------------------------------------------------------------------------
+// forward: grid (seq/128, heads, batch)
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(ATT_THREADS) attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv,
+                                                                   const AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = smem + TILE_BYTES;
+  uint8_t* sV = smem + 2 * TILE_BYTES;
+  uint8_t* sP = smem + 3 * TILE_BYTES;  // 2 tiles
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 5 * TILE_BYTES);
+  uint64_t* bar_load = &bars[0];
+  uint64_t* bar_s = &bars[1];
+  uint64_t* bar_o = &bars[2];
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(&bars[4]);
+  float* s_bias = reinterpret_cast<float*>(smem + 5 * TILE_BYTES + 64);  // [seq]
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int qb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int nkv = p.seq / 128;
+
+  if (tid == 0) {
+    tma_prefetch_desc(&tmap_qkv);
+    mbar_init(bar_load, 1);
+    mbar_init(bar_s, 1);
+    mbar_init(bar_o, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_holder, 256);
+  for (int c = tid; c < p.seq; c += ATT_THREADS)
+    s_bias[c] = (p.mask != nullptr && p.mask[(size_t)b * p.seq + c] == 0) ? kMaskBias : 0.f;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_holder;
+  const uint32_t tmem_s = tmem, tmem_o = tmem + 128;
+  const uint32_t lane_base = ((uint32_t)(warp * 32)) << 16;
+
+  const int row0 = b * p.seq;           // first token row of this sequence
+  const int q_row = qb * 128 + tid;     // query index inside the sequence
+  const int col_q = h * 64, col_k = p.hidden + h * 64, col_v = 2 * p.hidden + h * 64;
+  const DropCtx drop = make_drop_ctx(p.rng, p.rng_site, p.dropout_p);
+  const float c2 = p.scale * kLog2e;
+
+  float o_acc[64];
+#pragma unroll
+  for (int i = 0; i < 64; ++i) o_acc[i] = 0.f;
+  float m_run = -INFINITY, l_run = 0.f;
+  uint32_t ph_load = 0, ph_s = 0, ph_o = 0;
+
+  constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, false, false);
+  constexpr uint32_t idesc_o = make_idesc_bf16(128, 64, false, true);
+
+  for (int j = 0; j < nkv; ++j) {
+    if (tid == 0) {
+      mbar_expect_tx(bar_load, (j == 0 ? 3 : 2) * TILE_BYTES);
+      if (j == 0) tma_load_2d(sQ, &tmap_qkv, bar_load, col_q, row0 + qb * 128);
+      tma_load_2d(sK, &tmap_qkv, bar_load, col_k, row0 + j * 128);
+      tma_load_2d(sV, &tmap_qkv, bar_load, col_v, row0 + j * 128);
+      mbar_wait(bar_load, ph_load);
+      tc_fence_after();
+      const uint32_t aq = smem_u32(sQ), ak = smem_u32(sK);
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        umma_bf16(tmem_s, make_smem_desc(aq + k * 32, 16, 1024), make_smem_desc(ak + k * 32, 16, 1024), idesc_s,
+                  k > 0 ? 1u : 0u);
+      umma_commit(bar_s);
+    }
+    ph_load ^= 1;
+    __syncwarp();
+    mbar_wait(bar_s, ph_s);
+    ph_s ^= 1;
+    tc_fence_after();
+
+    // pass 1: row maximum of the scaled + masked scores (log2 domain)
+    float m_new = m_run;
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      uint32_t v[32];
+      tmem_ld32(tmem_s + lane_base + c * 32, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        m_new = fmaxf(m_new, __uint_as_float(v[i]) * c2 + s_bias[j * 128 + c * 32 + i]);
+    }
+    const float alpha = exp2f(m_run - m_new);  // first block: exp2(-inf) = 0
+    float l_blk = 0.f;
+    // pass 2: probabilities -> (dropout) -> bf16 P tile in smem
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      uint32_t v[32];
+      tmem_ld32(tmem_s + lane_base + c * 32, v);
+      tmem_ld_wait();
+      float pr[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        pr[i] = exp2f(__uint_as_float(v[i]) * c2 + s_bias[j * 128 + c * 32 + i] - m_new);
+        l_blk += pr[i];
+      }
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const unsigned long long idx =
+            (((unsigned long long)(b * p.heads + h) * p.seq + q_row) * p.seq) + j * 128 + c * 32 + g * 8;
+        const uint32_t keep = dropout_keep8(drop, idx);
+        float q8[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) q8[i] = ((keep >> i) & 1u) ? pr[g * 8 + i] * drop.scale : 0.f;
+        uint4 o;
+        o.x = pack_bf16(q8[0], q8[1]); o.y = pack_bf16(q8[2], q8[3]);
+        o.z = pack_bf16(q8[4], q8[5]); o.w = pack_bf16(q8[6], q8[7]);
+        st_tile_chunk(sP, tid, c * 4 + g, o);
+      }
+    }
+    l_run = l_run * alpha + l_blk;
+    m_run = m_new;
+
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      const uint32_t ap = smem_u32(sP), av = smem_u32(sV);
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        umma_bf16(tmem_o, make_smem_desc(ap + (k >> 2) * TILE_BYTES + (k & 3) * 32, 16, 1024),
+                  make_smem_desc(av + k * 2048, 16, 1024), idesc_o, k > 0 ? 1u : 0u);
+      umma_commit(bar_o);
+    }
+    __syncwarp();
+    mbar_wait(bar_o, ph_o);
+    ph_o ^= 1;
+    tc_fence_after();
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      uint32_t v[32];
+      tmem_ld32(tmem_o + lane_base + c * 32, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) o_acc[c * 32 + i] = o_acc[c * 32 + i] * alpha + __uint_as_float(v[i]);
+    }
+    // all TMEM reads of this iteration must retire before thread 0 issues the next QK^T / PV
+    tc_fence_before();
+    __syncthreads();
+  }
+
+  const float inv_l = 1.0f / l_run;
+  __nv_bfloat16* out = p.ctx + (size_t)(row0 + q_row) * p.hidden + h * 64;
+#pragma unroll
+  for (int i = 0; i < 64; i += 8) {
+    uint4 o;
+    o.x = pack_bf16(o_acc[i] * inv_l, o_acc[i + 1] * inv_l);
+    o.y = pack_bf16(o_acc[i + 2] * inv_l, o_acc[i + 3] * inv_l);
+    o.z = pack_bf16(o_acc[i + 4] * inv_l, o_acc[i + 5] * inv_l);
+    o.w = pack_bf16(o_acc[i + 6] * inv_l, o_acc[i + 7] * inv_l);
+    stg16(out + i, o);
+  }
+  if (p.lse != nullptr) p.lse[((size_t)b * p.heads + h) * p.seq + q_row] = (m_run + log2f(l_run)) * kLn2;
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 256);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// backward: grid (seq/128 kv blocks, heads, batch); loops over query blocks
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(ATT_THREADS) attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv,
+                                                                   const __grid_constant__ CUtensorMap tmap_do,
+                                                                   const AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sK = smem;
+  uint8_t* sV = smem + TILE_BYTES;
+  uint8_t* sQ = smem + 2 * TILE_BYTES;
+  uint8_t* sdO = smem + 3 * TILE_BYTES;
+  uint8_t* sP = smem + 4 * TILE_BYTES;   // 2 tiles
+  uint8_t* sdS = smem + 6 * TILE_BYTES;  // 2 tiles
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 8 * TILE_BYTES);
+  uint64_t* bar_kv = &bars[0];
+  uint64_t* bar_q = &bars[1];
+  uint64_t* bar_s = &bars[2];
+  uint64_t* bar_mma = &bars[3];
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(&bars[4]);
+  float* s_bias = reinterpret_cast<float*>(smem + 8 * TILE_BYTES + 64);  // [128] keys of this block
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int jb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int nq = p.seq / 128;
+
+  if (tid == 0) {
+    tma_prefetch_desc(&tmap_qkv);
+    tma_prefetch_desc(&tmap_do);
+    mbar_init(bar_kv, 1);
+    mbar_init(bar_q, 1);
+    mbar_init(bar_s, 1);
+    mbar_init(bar_mma, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_holder, 512);
+  s_bias[tid] = (p.mask != nullptr && p.mask[(size_t)b * p.seq + jb * 128 + tid] == 0) ? kMaskBias : 0.f;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_holder;
+  const uint32_t tm_s = tmem, tm_dp = tmem + 128, tm_dv = tmem + 256, tm_dk = tmem + 320, tm_dq = tmem + 384;
+  const uint32_t lane_base = ((uint32_t)(warp * 32)) << 16;
+
+  const int row0 = b * p.seq;
+  const int col_q = h * 64, col_k = p.hidden + h * 64, col_v = 2 * p.hidden + h * 64;
+  const DropCtx drop = make_drop_ctx(p.rng, p.rng_site, p.dropout_p);
+  const float c2 = p.scale * kLog2e;
+
+  if (tid == 0) {
+    mbar_expect_tx(bar_kv, 2 * TILE_BYTES);
+    tma_load_2d(sK, &tmap_qkv, bar_kv, col_k, row0 + jb * 128);
+    tma_load_2d(sV, &tmap_qkv, bar_kv, col_v, row0 + jb * 128);
+  }
+
+  constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, false, false);   // S, dP
+  constexpr uint32_t idesc_t = make_idesc_bf16(128, 64, true, true);      // dV, dK (A = P^T / dS^T)
+  constexpr uint32_t idesc_q = make_idesc_bf16(128, 64, false, true);     // dQ
+  uint32_t ph_q = 0, ph_s = 0, ph_mma = 0;
+
+  for (int i = 0; i < nq; ++i) {
+    const int q_row = i * 128 + tid;  // this thread's query row in the sequence
+    if (tid == 0) {
+      mbar_expect_tx(bar_q, 2 * TILE_BYTES);
+      tma_load_2d(sQ, &tmap_qkv, bar_q, col_q, row0 + i * 128);
+      tma_load_2d(sdO, &tmap_do, bar_q, h * 64, row0 + i * 128);
+      if (i == 0) mbar_wait(bar_kv, 0);
+      mbar_wait(bar_q, ph_q);
+      tc_fence_after();
+      const uint32_t aq = smem_u32(sQ), ak = smem_u32(sK), ado = smem_u32(sdO), av = smem_u32(sV);
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        umma_bf16(tm_s, make_smem_desc(aq + k * 32, 16, 1024), make_smem_desc(ak + k * 32, 16, 1024), idesc_s,
+                  k > 0 ? 1u : 0u);
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        umma_bf16(tm_dp, make_smem_desc(ado + k * 32, 16, 1024), make_smem_desc(av + k * 32, 16, 1024), idesc_s,
+                  k > 0 ? 1u : 0u);
+      umma_commit(bar_s);
+    }
+    ph_q ^= 1;
+    __syncwarp();
+
+    // delta = rowsum(dO * O) and the row's log-sum-exp, straight from HBM while the MMAs run
+    float delta = 0.f;
+    {
+      const __nv_bfloat16* o_row = p.ctx_in + (size_t)(row0 + q_row) * p.hidden + h * 64;
+      const __nv_bfloat16* do_row = p.d_ctx + (size_t)(row0 + q_row) * p.hidden + h * 64;
+#pragma unroll
+      for (int k = 0; k < 64; k += 8) {
+        const uint4 a = ldg16(o_row + k), g = ldg16(do_row + k);
+        delta += bf16_lo(a.x) * bf16_lo(g.x) + bf16_hi(a.x) * bf16_hi(g.x) + bf16_lo(a.y) * bf16_lo(g.y) +
+                 bf16_hi(a.y) * bf16_hi(g.y) + bf16_lo(a.z) * bf16_lo(g.z) + bf16_hi(a.z) * bf16_hi(g.z) +
+                 bf16_lo(a.w) * bf16_lo(g.w) + bf16_hi(a.w) * bf16_hi(g.w);
+      }
+    }
+    const float lse2 = p.lse[((size_t)b * p.heads + h) * p.seq + q_row] * kLog2e;
+
+    mbar_wait(bar_s, ph_s);
+    ph_s ^= 1;
+    tc_fence_after();
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      uint32_t vs[32], vd[32];
+      tmem_ld32(tm_s + lane_base + c * 32, vs);
+      tmem_ld32(tm_dp + lane_base + c * 32, vd);
+      tmem_ld_wait();
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const unsigned long long idx =
+            (((unsigned long long)(b * p.heads + h) * p.seq + q_row) * p.seq) + jb * 128 + c * 32 + g * 8;
+        const uint32_t keep = dropout_keep8(drop, idx);
+        float pd[8], ds[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int cc = g * 8 + e;
+          const float pr = exp2f(__uint_as_float(vs[cc]) * c2 + s_bias[c * 32 + cc] - lse2);
+          const bool kp = (keep >> e) & 1u;
+          pd[e] = kp ? pr * drop.scale : 0.f;
+          const float dp = kp ? __uint_as_float(vd[cc]) * drop.scale : 0.f;
+          ds[e] = pr * (dp - delta) * p.scale;
+        }
+        uint4 o;
+        o.x = pack_bf16(pd[0], pd[1]); o.y = pack_bf16(pd[2], pd[3]);
+        o.z = pack_bf16(pd[4], pd[5]); o.w = pack_bf16(pd[6], pd[7]);
+        st_tile_chunk(sP, tid, c * 4 + g, o);
+        o.x = pack_bf16(ds[0], ds[1]); o.y = pack_bf16(ds[2], ds[3]);
+        o.z = pack_bf16(ds[4], ds[5]); o.w = pack_bf16(ds[6], ds[7]);
+        st_tile_chunk(sdS, tid, c * 4 + g, o);
+      }
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      const uint32_t ap = smem_u32(sP), ads = smem_u32(sdS), ado = smem_u32(sdO), aq = smem_u32(sQ),
+                     ak = smem_u32(sK);
+      // dV[key, d] += sum_q P[q, key] dO[q, d]      (A = P as MN-major: rows = q = K index)
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        umma_bf16(tm_dv, make_smem_desc(ap + k * 2048, TILE_BYTES, 1024), make_smem_desc(ado + k * 2048, 16, 1024),
+                  idesc_t, (i > 0 || k > 0) ? 1u : 0u);
+      // dK[key, d] += sum_q dS[q, key] Q[q, d]
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        umma_bf16(tm_dk, make_smem_desc(ads + k * 2048, TILE_BYTES, 1024), make_smem_desc(aq + k * 2048, 16, 1024),
+                  idesc_t, (i > 0 || k > 0) ? 1u : 0u);
+      // dQ[q, d] = sum_key dS[q, key] K[key, d]     (A = dS as K-major)
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        umma_bf16(tm_dq, make_smem_desc(ads + (k >> 2) * TILE_BYTES + (k & 3) * 32, 16, 1024),
+                  make_smem_desc(ak + k * 2048, 16, 1024), idesc_q, k > 0 ? 1u : 0u);
+      umma_commit(bar_mma);
+    }
+    __syncwarp();
+    mbar_wait(bar_mma, ph_mma);
+    ph_mma ^= 1;
+    tc_fence_after();
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      uint32_t v[32];
+      tmem_ld32(tm_dq + lane_base + c * 32, v);
+      tmem_ld_wait();
+      if (p.dq_accum == nullptr) {
+        __nv_bfloat16* dst = p.d_qkv + (size_t)(row0 + q_row) * (3 * p.hidden) + col_q + c * 32;
+#pragma unroll
+        for (int e = 0; e < 32; e += 8) {
+          uint4 o;
+          o.x = pack_bf16(__uint_as_float(v[e]), __uint_as_float(v[e + 1]));
+          o.y = pack_bf16(__uint_as_float(v[e + 2]), __uint_as_float(v[e + 3]));
+          o.z = pack_bf16(__uint_as_float(v[e + 4]), __uint_as_float(v[e + 5]));
+          o.w = pack_bf16(__uint_as_float(v[e + 6]), __uint_as_float(v[e + 7]));
+          stg16(dst + e, o);
+        }
+      } else {
+        float* dst = p.dq_accum + (size_t)(row0 + q_row) * p.hidden + h * 64 + c * 32;
+#pragma unroll
+        for (int e = 0; e < 32; ++e) atomicAdd(dst + e, __uint_as_float(v[e]));
+      }
+    }
+    tc_fence_before();
+    __syncthreads();
+  }
+
+  // dK, dV for this thread's key row
+  {
+    const int k_row = jb * 128 + tid;
+    __nv_bfloat16* dk = p.d_qkv + (size_t)(row0 + k_row) * (3 * p.hidden) + col_k;
+    __nv_bfloat16* dv = p.d_qkv + (size_t)(row0 + k_row) * (3 * p.hidden) + col_v;
+    tc_fence_after();
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      uint32_t v[32], w[32];
+      tmem_ld32(tm_dk + lane_base + c * 32, v);
+      tmem_ld32(tm_dv + lane_base + c * 32, w);
+      tmem_ld_wait();
+#pragma unroll
+      for (int e = 0; e < 32; e += 8) {
+        uint4 o;
+        o.x = pack_bf16(__uint_as_float(v[e]), __uint_as_float(v[e + 1]));
+        o.y = pack_bf16(__uint_as_float(v[e + 2]), __uint_as_float(v[e + 3]));
+        o.z = pack_bf16(__uint_as_float(v[e + 4]), __uint_as_float(v[e + 5]));
+        o.w = pack_bf16(__uint_as_float(v[e + 6]), __uint_as_float(v[e + 7]));
+        stg16(dk + c * 32 + e, o);
+        o.x = pack_bf16(__uint_as_float(w[e]), __uint_as_float(w[e + 1]));
+        o.y = pack_bf16(__uint_as_float(w[e + 2]), __uint_as_float(w[e + 3]));
+        o.z = pack_bf16(__uint_as_float(w[e + 4]), __uint_as_float(w[e + 5]));
+        o.w = pack_bf16(__uint_as_float(w[e + 6]), __uint_as_float(w[e + 7]));
+        stg16(dv + c * 32 + e, o);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+// fp32 dQ accumulator [tokens, hidden] -> the Q column block of d_qkv (bf16 [tokens, 3*hidden])
+__global__ void dq_convert_kernel(const float* __restrict__ acc, __nv_bfloat16* __restrict__ d_qkv, long long tokens,
+                                  int hidden) {
+  const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i >= tokens * hidden) return;
+  const long long t = i / hidden;
+  const int c = (int)(i % hidden);
+  const float4 v = *reinterpret_cast<const float4*>(acc + i);
+  uint2 o;
+  o.x = pack_bf16(v.x, v.y);
+  o.y = pack_bf16(v.z, v.w);
+  *reinterpret_cast<uint2*>(d_qkv + t * 3 * hidden + c) = o;
+}
+
+constexpr int kFwdSmem = 5 * TILE_BYTES + 64 + 512 * 4 + 1024;
+constexpr int kBwdSmem = 8 * TILE_BYTES + 64 + 128 * 4 + 1024;
+
+static int32_t check_attn_shapes(const char* who, int64_t batch, int64_t seq, int64_t heads, int64_t head_dim) {
+  B2_REQUIRE(batch > 0 && seq > 0 && heads > 0, "%s: empty problem (batch=%lld seq=%lld heads=%lld)", who,
+             (long long)batch, (long long)seq, (long long)heads);
+  B2_REQUIRE(head_dim == 64, "%s: head_dim=%lld (only 64 is on the path)", who, (long long)head_dim);
+  B2_REQUIRE(seq % 128 == 0 && seq <= 512, "%s: seq=%lld must be a multiple of 128, at most 512", who,
+             (long long)seq);
+  B2_REQUIRE(batch <= 65535 && heads <= 65535, "%s: batch/heads exceed grid limits", who);
+  return 0;
+}
+
+}  // namespace b2
+
+using namespace b2;
+
+extern "C" int32_t b2_attention_fwd(const void* qkv, const int64_t* attention_mask, int64_t batch, int64_t seq,
+                                    int64_t heads, int64_t head_dim, float dropout_p, const void* rng_state,
+                                    uint32_t rng_site, void* ctx, float* lse, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  B2_REQUIRE(qkv && ctx, "attention_fwd: null pointer");
+  int32_t st = check_attn_shapes("attention_fwd", batch, seq, heads, head_dim);
+  if (st) return st;
+  B2_REQUIRE(!(dropout_p > 0.f) || rng_state, "attention_fwd: dropout needs rng_state");
+  const int64_t hidden = heads * 64, tokens = batch * seq;
+  CUtensorMap tm;
+  st = get_tensor_map_2d(&tm, qkv, (uint64_t)tokens, (uint64_t)(3 * hidden), (uint64_t)(3 * hidden * 2), 128, 64);
+  if (st) return st;
+  AttnParams p{};
+  p.batch = (int)batch; p.seq = (int)seq; p.heads = (int)heads; p.hidden = (int)hidden;
+  p.scale = 0.125f;
+  p.dropout_p = dropout_p; p.rng = (const unsigned long long*)rng_state; p.rng_site = rng_site;
+  p.mask = (const long long*)attention_mask;
+  p.ctx = (__nv_bfloat16*)ctx; p.lse = lse;
+  static bool attr = false;
+  if (!attr) {
+    B2_CUDA(cudaFuncSetAttribute(attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmem));
+    attr = true;
+  }
+  dim3 grid((unsigned)(seq / 128), (unsigned)heads, (unsigned)batch);
+  attention_fwd_kernel<<<grid, ATT_THREADS, kFwdSmem, stream>>>(tm, p);
+  B2_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int32_t b2_attention_bwd(const void* qkv, const int64_t* attention_mask, const void* ctx, const void* d_ctx,
+                                    const float* lse, int64_t batch, int64_t seq, int64_t heads, int64_t head_dim,
+                                    float dropout_p, const void* rng_state, uint32_t rng_site, void* d_qkv,
+                                    float* dq_accum, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  B2_REQUIRE(qkv && ctx && d_ctx && lse && d_qkv, "attention_bwd: null pointer");
+  int32_t st = check_attn_shapes("attention_bwd", batch, seq, heads, head_dim);
+  if (st) return st;
+  B2_REQUIRE(!(dropout_p > 0.f) || rng_state, "attention_bwd: dropout needs rng_state");
+  B2_REQUIRE(seq == 128 || dq_accum != nullptr, "attention_bwd: seq > 128 needs the fp32 dq_accum buffer");
+  const int64_t hidden = heads * 64, tokens = batch * seq;
+  CUtensorMap tm_qkv, tm_do;
+  st = get_tensor_map_2d(&tm_qkv, qkv, (uint64_t)tokens, (uint64_t)(3 * hidden), (uint64_t)(3 * hidden * 2), 128, 64);
+  if (st) return st;
+  st = get_tensor_map_2d(&tm_do, d_ctx, (uint64_t)tokens, (uint64_t)hidden, (uint64_t)(hidden * 2), 128, 64);
+  if (st) return st;
+  AttnParams p{};
+  p.batch = (int)batch; p.seq = (int)seq; p.heads = (int)heads; p.hidden = (int)hidden;
+  p.scale = 0.125f;
+  p.dropout_p = dropout_p; p.rng = (const unsigned long long*)rng_state; p.rng_site = rng_site;
+  p.mask = (const long long*)attention_mask;
+  p.lse = const_cast<float*>(lse);
+  p.ctx_in = (const __nv_bfloat16*)ctx; p.d_ctx = (const __nv_bfloat16*)d_ctx;
+  p.d_qkv = (__nv_bfloat16*)d_qkv;
+  p.dq_accum = seq > 128 ? dq_accum : nullptr;
+  if (p.dq_accum) B2_CUDA(cudaMemsetAsync(p.dq_accum, 0, (size_t)tokens * hidden * 4, stream));
+  static bool attr = false;
+  if (!attr) {
+    B2_CUDA(cudaFuncSetAttribute(attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem));
+    attr = true;
+  }
+  dim3 grid((unsigned)(seq / 128), (unsigned)heads, (unsigned)batch);
+  attention_bwd_kernel<<<grid, ATT_THREADS, kBwdSmem, stream>>>(tm_qkv, tm_do, p);
+  B2_CUDA(cudaGetLastError());
+  if (p.dq_accum) {
+    const long long n4 = tokens * hidden / 4;
+    dq_convert_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, stream>>>(p.dq_accum, (__nv_bfloat16*)d_qkv, tokens,
+                                                                        (int)hidden);
+    B2_CUDA(cudaGetLastError());
+  }
+  return 0;
+}

@@ -1,0 +1,217 @@
+// BertEmbeddings forward / backward (SP/transformers/models/bert/modeling_bert.py:72-112).
+// forward : word + position + token-type gather, add, LayerNorm, dropout, one warp per token, one pass over HBM.
+// backward: LayerNorm backward, then deterministic scatter-adds:
+//   word rows      one "owner" CTA per touched vocabulary row (lowest token index wins an atomicMin) sums all of
+//                  that row's occurrences in token order -> no float atomics, bit-reproducible;
+//   position rows  row s = sum over the batch of dx[b, s, :];
+//   type rows      filtered column sums.
+#include "common.cuh"
+#include "layernorm.cuh"
+#include "../../include/b2_ddp_bert.h"
+
+#include <climits>
+
+namespace b2 {
+
+template <int VPL>
+__global__ void __launch_bounds__(128) embed_fwd_kernel(
+    const long long* __restrict__ input_ids, const long long* __restrict__ token_type_ids, int tokens, int seq,
+    const __nv_bfloat16* __restrict__ word, const __nv_bfloat16* __restrict__ pos,
+    const __nv_bfloat16* __restrict__ type, const __nv_bfloat16* __restrict__ gamma,
+    const __nv_bfloat16* __restrict__ beta, int vocab, int type_vocab, float eps, float dropout_p,
+    const unsigned long long* rng, unsigned rng_site, __nv_bfloat16* __restrict__ y,
+    __nv_bfloat16* __restrict__ pre_ln, float* __restrict__ mean_out, float* __restrict__ rstd_out,
+    int* __restrict__ ids32, int* __restrict__ tt32) {
+  constexpr int H = VPL * 256;
+  const int t = blockIdx.x * 4 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (t >= tokens) return;
+  long long id = input_ids[t];
+  long long tt = token_type_ids ? token_type_ids[t] : 0;
+  // out-of-range ids would be a host bug; clamp so a bad batch cannot fault the GPU (host validates too)
+  id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
+  tt = tt < 0 ? 0 : (tt >= type_vocab ? type_vocab - 1 : tt);
+  const int s = t % seq;
+  float v[VPL * 8], a[VPL * 8];
+  load_row<VPL>(word + (size_t)id * H, lane, v);
+  load_row<VPL>(pos + (size_t)s * H, lane, a);
+#pragma unroll
+  for (int i = 0; i < VPL * 8; ++i) v[i] += a[i];
+  load_row<VPL>(type + (size_t)tt * H, lane, a);
+#pragma unroll
+  for (int i = 0; i < VPL * 8; ++i) v[i] += a[i];
+  store_row<VPL>(pre_ln + (size_t)t * H, lane, v);
+  float mean, rstd;
+  row_stats<VPL>(v, eps, mean, rstd);
+  normalize<VPL>(v, mean, rstd, gamma, beta, lane);
+  const DropCtx drop = make_drop_ctx(rng, rng_site, dropout_p);
+  if (drop.thresh != 0) {
+#pragma unroll
+    for (int vv = 0; vv < VPL; ++vv) {
+      const uint32_t keep = dropout_keep8(drop, (unsigned long long)t * H + (vv * 32 + lane) * 8);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[vv * 8 + i] = ((keep >> i) & 1u) ? v[vv * 8 + i] * drop.scale : 0.f;
+    }
+  }
+  store_row<VPL>(y + (size_t)t * H, lane, v);
+  if (lane == 0) {
+    mean_out[t] = mean;
+    rstd_out[t] = rstd;
+    ids32[t] = (int)id;
+    tt32[t] = (int)tt;
+  }
+}
+
+__global__ void embed_owner_kernel(const int* __restrict__ ids32, int tokens, int pad_id,
+                                   int* __restrict__ owner) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < tokens && ids32[t] != pad_id) atomicMin(&owner[ids32[t]], t);
+}
+
+// one CTA per token; only the owner of a vocabulary row does work.  Threads = H/8 (one 16-byte vector each).
+__global__ void embed_word_scatter_kernel(const __nv_bfloat16* __restrict__ dx, const int* __restrict__ ids32,
+                                          int tokens, int H, int pad_id, int* __restrict__ owner,
+                                          __nv_bfloat16* __restrict__ d_word) {
+  const int t = blockIdx.x;
+  const int id = ids32[t];
+  // nn.Embedding(padding_idx=pad_token_id): the pad row never receives gradient (stays at the caller's zero fill)
+  if (id == pad_id || owner[id] != t) return;
+  const int nvec = H / 8;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  // occurrences of `id` can only be at token indices >= t (t is the minimum)
+  for (int base = t; base < tokens; base += blockDim.x) {
+    const int tp = base + threadIdx.x;
+    const bool hit = (tp < tokens) && (ids32[tp] == id);
+    // every warp needs the hits of the whole block: exchange through smem
+    __shared__ unsigned hits[32];
+    const unsigned b = __ballot_sync(0xffffffffu, hit);
+    if ((threadIdx.x & 31) == 0) hits[threadIdx.x >> 5] = b;
+    __syncthreads();
+    const int nw = blockDim.x >> 5;
+    for (int w = 0; w < nw; ++w) {
+      unsigned m = hits[w];
+      while (m) {
+        const int bit = __ffs(m) - 1;
+        m &= m - 1;
+        const int src = base + w * 32 + bit;
+        if ((int)threadIdx.x < nvec) {
+          const uint4 v = ldg16(dx + (size_t)src * H + threadIdx.x * 8);
+          acc[0] += bf16_lo(v.x); acc[1] += bf16_hi(v.x); acc[2] += bf16_lo(v.y); acc[3] += bf16_hi(v.y);
+          acc[4] += bf16_lo(v.z); acc[5] += bf16_hi(v.z); acc[6] += bf16_lo(v.w); acc[7] += bf16_hi(v.w);
+        }
+      }
+    }
+    __syncthreads();
+  }
+  if ((int)threadIdx.x < nvec) {
+    uint4 o;
+    o.x = pack_bf16(acc[0], acc[1]); o.y = pack_bf16(acc[2], acc[3]);
+    o.z = pack_bf16(acc[4], acc[5]); o.w = pack_bf16(acc[6], acc[7]);
+    stg16(d_word + (size_t)id * H + threadIdx.x * 8, o);
+  }
+  if (threadIdx.x == 0) owner[id] = INT_MAX;  // leave the table armed for the next step
+}
+
+// d_pos[s] = sum_b dx[b*seq + s]  (rows >= seq get zero).  grid = max_pos rows, threads = H/8
+__global__ void embed_pos_kernel(const __nv_bfloat16* __restrict__ dx, int batch, int seq, int H,
+                                 __nv_bfloat16* __restrict__ d_pos) {
+  const int s = blockIdx.x;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (s < seq) {
+    for (int b = 0; b < batch; ++b) {
+      const uint4 v = ldg16(dx + ((size_t)b * seq + s) * H + threadIdx.x * 8);
+      acc[0] += bf16_lo(v.x); acc[1] += bf16_hi(v.x); acc[2] += bf16_lo(v.y); acc[3] += bf16_hi(v.y);
+      acc[4] += bf16_lo(v.z); acc[5] += bf16_hi(v.z); acc[6] += bf16_lo(v.w); acc[7] += bf16_hi(v.w);
+    }
+  }
+  uint4 o;
+  o.x = pack_bf16(acc[0], acc[1]); o.y = pack_bf16(acc[2], acc[3]);
+  o.z = pack_bf16(acc[4], acc[5]); o.w = pack_bf16(acc[6], acc[7]);
+  stg16(d_pos + (size_t)s * H + threadIdx.x * 8, o);
+}
+
+__global__ void fill_int_kernel(int* p, int n, int v) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+}  // namespace b2
+
+using namespace b2;
+
+extern "C" int32_t b2_embed_fwd(const int64_t* input_ids, const int64_t* token_type_ids, int64_t batch, int64_t seq,
+                                const void* word_emb, const void* pos_emb, const void* type_emb, const void* gamma,
+                                const void* beta, int64_t hidden, int64_t vocab, int64_t type_vocab, float eps,
+                                float dropout_p, const void* rng_state, uint32_t rng_site, void* y, void* pre_ln,
+                                float* mean, float* rstd, int32_t* ids32, int32_t* tt32, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  B2_REQUIRE(input_ids && word_emb && pos_emb && type_emb && gamma && beta && y && pre_ln && mean && rstd && ids32 &&
+                 tt32,
+             "embed_fwd: null pointer");
+  B2_REQUIRE(batch > 0 && seq > 0, "embed_fwd: empty batch (batch=%lld seq=%lld)", (long long)batch, (long long)seq);
+  B2_REQUIRE(hidden % 256 == 0 && hidden >= 256 && hidden <= 1024, "embed_fwd: hidden=%lld unsupported",
+             (long long)hidden);
+  B2_REQUIRE(!(dropout_p > 0.f) || rng_state, "embed_fwd: dropout needs rng_state");
+  const int tokens = (int)(batch * seq);
+  const unsigned grid = (unsigned)((tokens + 3) / 4);
+#define B2_EMB(VPL_)                                                                                              \
+  case VPL_:                                                                                                      \
+    embed_fwd_kernel<VPL_><<<grid, 128, 0, stream>>>(                                                             \
+        (const long long*)input_ids, (const long long*)token_type_ids, tokens, (int)seq,                          \
+        (const __nv_bfloat16*)word_emb, (const __nv_bfloat16*)pos_emb, (const __nv_bfloat16*)type_emb,            \
+        (const __nv_bfloat16*)gamma, (const __nv_bfloat16*)beta, (int)vocab, (int)type_vocab, eps, dropout_p,     \
+        (const unsigned long long*)rng_state, rng_site, (__nv_bfloat16*)y, (__nv_bfloat16*)pre_ln, mean, rstd,    \
+        ids32, tt32);                                                                                             \
+    break;
+  switch ((int)(hidden / 256)) { B2_EMB(1) B2_EMB(2) B2_EMB(3) B2_EMB(4) }
+#undef B2_EMB
+  B2_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int32_t b2_embed_bwd(const void* dy, const void* pre_ln, const float* mean, const float* rstd,
+                                const void* gamma, const int32_t* ids32, const int32_t* tt32, int64_t batch,
+                                int64_t seq, int64_t hidden, int64_t vocab, int64_t type_vocab, int64_t pad_token_id,
+                                float dropout_p, const void* rng_state, uint32_t rng_site, void* d_word, void* d_pos,
+                                void* d_type,
+                                void* d_gamma, void* d_beta, void* scratch_dx, float* scratch_partials,
+                                int64_t scratch_partials_bytes, int32_t* owner, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  B2_REQUIRE(dy && pre_ln && mean && rstd && gamma && ids32 && tt32 && d_word && d_pos && d_type && d_gamma &&
+                 d_beta && scratch_dx && scratch_partials && owner,
+             "embed_bwd: null pointer");
+  B2_REQUIRE(batch > 0 && seq > 0, "embed_bwd: empty batch");
+  B2_REQUIRE(hidden % 256 == 0 && hidden <= 1024, "embed_bwd: hidden=%lld unsupported", (long long)hidden);
+  const int tokens = (int)(batch * seq);
+  // 1. LayerNorm backward (dropout sits on the LN output here -> mode 1); dx lands in scratch_dx
+  int32_t st = launch_layernorm_bwd(dy, nullptr, pre_ln, mean, rstd, gamma, tokens, hidden, dropout_p, rng_state,
+                                    rng_site, 1, scratch_dx, nullptr, d_gamma, d_beta, nullptr, scratch_partials,
+                                    scratch_partials_bytes, stream);
+  if (st) return st;
+  // 2. word rows (d_word pre-zeroed by the caller)
+  embed_owner_kernel<<<(tokens + 255) / 256, 256, 0, stream>>>(ids32, tokens, (int)pad_token_id, owner);
+  B2_CUDA(cudaGetLastError());
+  embed_word_scatter_kernel<<<tokens, 128, 0, stream>>>((const __nv_bfloat16*)scratch_dx, ids32, tokens, (int)hidden,
+                                                        (int)pad_token_id, owner, (__nv_bfloat16*)d_word);
+  B2_CUDA(cudaGetLastError());
+  // 3. position rows: the table has `max_pos` rows but only the first `seq` receive gradient; the caller passes
+  //    d_pos sized [seq rows used]; rows beyond are zeroed by the caller's bucket memset
+  embed_pos_kernel<<<(unsigned)seq, (unsigned)(hidden / 8), 0, stream>>>((const __nv_bfloat16*)scratch_dx, (int)batch,
+                                                                         (int)seq, (int)hidden, (__nv_bfloat16*)d_pos);
+  B2_CUDA(cudaGetLastError());
+  // 4. token-type rows
+  for (int ty = 0; ty < (int)type_vocab; ++ty) {
+    st = launch_colsum(scratch_dx, tokens, hidden, hidden, tt32, ty, (__nv_bfloat16*)d_type + (size_t)ty * hidden,
+                       scratch_partials, scratch_partials_bytes, stream);
+    if (st) return st;
+  }
+  return 0;
+}
+
+// arms the owner table (INT_MAX) once; the scatter kernel re-arms what it touched
+extern "C" int32_t b2_embed_owner_init(int32_t* owner, int64_t vocab, void* stream_) {
+  B2_REQUIRE(owner && vocab > 0, "embed_owner_init: bad args");
+  fill_int_kernel<<<(unsigned)((vocab + 255) / 256), 256, 0, (cudaStream_t)stream_>>>(owner, (int)vocab, INT_MAX);
+  B2_CUDA(cudaGetLastError());
+  return 0;
+}

@@ -1,0 +1,434 @@
+// bf16 GEMM on the 5th-gen tensor cores: D[M,N] = op(A) * op(B) (+ fused epilogue), fp32 accumulate in TMEM.
+//
+// Replaces the cuBLAS `addmm` calls issued by HF BertSelfAttention / BertSelfOutput / BertIntermediate /
+// BertOutput (transformers modeling_bert.py:179-181, :295, :340, :353) and their autograd dgrad / wgrad
+// twins.
+//
+// Structure (persistent, warp specialised, one CTA per SM):
+//   warp 0      TMA producer      global -> 128B-swizzled smem ring (full/empty mbarriers)
+//   warp 1      MMA issuer        one lane issues tcgen05.mma (128 x BN x 16), commits to mbarriers
+//   warp 2      TMEM allocator    2 accumulator stages so tile i+1's MMAs overlap tile i's epilogue
+//   warps 4-11  epilogue          tcgen05.ld -> bias / GELU / dropout / residual -> bf16 global stores
+// Operand layouts are expressed only through the TMA box + UMMA descriptor (no transposes in HBM):
+//   NT  A[M,K] K-major,  B[N,K] K-major   (forward:  y = x W^T)
+//   NN  A[M,K] K-major,  B[K,N] MN-major  (dgrad:    dx = dy W)
+//   TN  A[K,M] MN-major, B[K,N] MN-major  (wgrad:    dW = dy^T x), optional split-K over the token axis
+#include "common.cuh"
+#include "../../include/b2_ddp_bert.h"
+
+namespace b2 {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int UMMA_K = 16;
+constexpr int NUM_EPI_WARPS = 8;
+constexpr int GEMM_THREADS = (4 + NUM_EPI_WARPS) * 32;
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int kStages = (BN == 256) ? 4 : (BN == 192 ? 5 : 6);
+  static constexpr int kABytes = BM * BK * 2;
+  static constexpr int kBBytes = BN * BK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kAccStride = (BN <= 128) ? 128 : 256;  // TMEM columns between the 2 accumulators
+  static constexpr int kTmemCols = 2 * kAccStride;            // 256 or 512 (power of two)
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+struct GemmKernelParams {
+  int M, N, K;
+  int tiles_m, tiles_n, splits, kblocks_per_split, kblocks_total;
+  int epilogue;
+  __nv_bfloat16* D; long long ldd;
+  const __nv_bfloat16* bias;
+  const __nv_bfloat16* aux_in; long long ld_aux_in;
+  __nv_bfloat16* aux_out; long long ld_aux_out;
+  float* partial;  // split-K fp32 partials [splits][M][N]
+  float dropout_p; const unsigned long long* rng; unsigned rng_site;
+};
+
+template <int BN, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                 const GemmKernelParams p) {
+  using Cfg = GemmCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint64_t* empty_bar = full_bar + Cfg::kStages;
+  uint64_t* tmem_full = empty_bar + Cfg::kStages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < Cfg::kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full[s], 1);
+      mbar_init(&tmem_empty[s], NUM_EPI_WARPS);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_holder, Cfg::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  const int num_work = p.tiles_m * p.tiles_n * p.splits;
+
+  if (warp == 0) {
+    // ------------------------------ TMA producer ------------------------------
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+        const int tile = w / p.splits, split = w % p.splits;
+        const int m0 = (tile / p.tiles_n) * BM, n0 = (tile % p.tiles_n) * BN;
+        const int kb0 = split * p.kblocks_per_split;
+        const int kb1 = min(kb0 + p.kblocks_per_split, p.kblocks_total);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+          uint8_t* sa = smem + stage * Cfg::kStageBytes;
+          uint8_t* sb = sa + Cfg::kABytes;
+          const int k0 = kb * BK;
+          if (!A_MN) {
+            tma_load_2d(sa, &tmap_a, &full_bar[stage], k0, m0);            // box {64 k, 128 rows}
+          } else {
+#pragma unroll
+            for (int j = 0; j < BM / 64; ++j)                                // box {64 m, 64 k-rows}
+              tma_load_2d(sa + j * (BK * 128), &tmap_a, &full_bar[stage], m0 + 64 * j, k0);
+          }
+          if (!B_MN) {
+            tma_load_2d(sb, &tmap_b, &full_bar[stage], k0, n0);            // box {64 k, BN rows}
+          } else {
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j)
+              tma_load_2d(sb + j * (BK * 128), &tmap_b, &full_bar[stage], n0 + 64 * j, k0);
+          }
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------ MMA issuer ------------------------------
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(BM, BN, A_MN, B_MN);
+      constexpr uint32_t a_lbo = A_MN ? BK * 128 : 16, b_lbo = B_MN ? BK * 128 : 16;
+      constexpr uint32_t a_kstep = A_MN ? UMMA_K * 128 : UMMA_K * 2;
+      constexpr uint32_t b_kstep = B_MN ? UMMA_K * 128 : UMMA_K * 2;
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+        const int split = w % p.splits;
+        const int kb0 = split * p.kblocks_per_split;
+        const int kb1 = min(kb0 + p.kblocks_per_split, p.kblocks_total);
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * Cfg::kAccStride;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
+          const uint32_t sb = sa + Cfg::kABytes;
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            const uint64_t da = make_smem_desc(sa + k * a_kstep, a_lbo, 1024);
+            const uint64_t db = make_smem_desc(sb + k * b_kstep, b_lbo, 1024);
+            umma_bf16(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs have read it
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tmem_full[acc]);      // accumulator complete -> epilogue
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------ epilogue ------------------------------
+    const int ew = warp - 4;
+    const int quarter = warp & 3;            // TMEM lane quarter this warp may touch
+    const int colhalf = ew >> 2;             // which half of the BN columns
+    constexpr int kColsPerWarp = BN / 2;
+    constexpr int kChunks = kColsPerWarp / 32;
+    const DropCtx drop = make_drop_ctx(p.rng, p.rng_site, p.dropout_p);
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+      const int tile = w / p.splits, split = w % p.splits;
+      const int m0 = (tile / p.tiles_n) * BM, n0 = (tile % p.tiles_n) * BN;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const int m = m0 + quarter * 32 + lane;
+      const bool row_ok = m < p.M;
+#pragma unroll 1
+      for (int c = 0; c < kChunks; ++c) {
+        const int n = n0 + colhalf * kColsPerWarp + c * 32;
+        uint32_t v[32];
+        tmem_ld32(tmem_base + acc * Cfg::kAccStride + ((uint32_t)(quarter * 32) << 16) +
+                      (uint32_t)(colhalf * kColsPerWarp + c * 32), v);
+        tmem_ld_wait();
+        if (n < p.N && row_ok) {
+        if (p.epilogue == B2_EPI_PARTIAL_F32) {
+          float* dst = p.partial + ((size_t)split * p.M + m) * p.N + n;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<float4*>(dst + j) =
+                make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                            __uint_as_float(v[j + 3]));
+        } else {
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+        if (p.bias != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            const uint4 b = ldg16(p.bias + n + j);
+            f[j + 0] += bf16_lo(b.x); f[j + 1] += bf16_hi(b.x);
+            f[j + 2] += bf16_lo(b.y); f[j + 3] += bf16_hi(b.y);
+            f[j + 4] += bf16_lo(b.z); f[j + 5] += bf16_hi(b.z);
+            f[j + 6] += bf16_lo(b.w); f[j + 7] += bf16_hi(b.w);
+          }
+        }
+        if (p.epilogue == B2_EPI_BIAS_GELU) {
+          // keep the pre-activation (bf16) for the backward pass, emit gelu(pre-activation)
+          __nv_bfloat16* u = p.aux_out + (size_t)m * p.ld_aux_out + n;
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            uint4 o;
+            o.x = pack_bf16(f[j], f[j + 1]); o.y = pack_bf16(f[j + 2], f[j + 3]);
+            o.z = pack_bf16(f[j + 4], f[j + 5]); o.w = pack_bf16(f[j + 6], f[j + 7]);
+            stg16(u + j, o);
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = gelu_erf(bf16_round(f[j]));
+        } else if (p.epilogue == B2_EPI_BIAS_DROPOUT_RESIDUAL) {
+          const __nv_bfloat16* r = p.aux_in + (size_t)m * p.ld_aux_in + n;
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            const uint32_t keep = dropout_keep8(drop, (unsigned long long)m * p.N + n + j);
+            const uint4 rr = ldg16(r + j);
+            const float res[8] = {bf16_lo(rr.x), bf16_hi(rr.x), bf16_lo(rr.y), bf16_hi(rr.y),
+                                  bf16_lo(rr.z), bf16_hi(rr.z), bf16_lo(rr.w), bf16_hi(rr.w)};
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              f[j + i] = (((keep >> i) & 1u) ? f[j + i] * drop.scale : 0.f) + res[i];
+          }
+        } else if (p.epilogue == B2_EPI_RESIDUAL) {
+          const __nv_bfloat16* r = p.aux_in + (size_t)m * p.ld_aux_in + n;
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            const uint4 rr = ldg16(r + j);
+            f[j + 0] += bf16_lo(rr.x); f[j + 1] += bf16_hi(rr.x);
+            f[j + 2] += bf16_lo(rr.y); f[j + 3] += bf16_hi(rr.y);
+            f[j + 4] += bf16_lo(rr.z); f[j + 5] += bf16_hi(rr.z);
+            f[j + 6] += bf16_lo(rr.w); f[j + 7] += bf16_hi(rr.w);
+          }
+        } else if (p.epilogue == B2_EPI_GELU_BWD) {
+          const __nv_bfloat16* u = p.aux_in + (size_t)m * p.ld_aux_in + n;
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            const uint4 uu = ldg16(u + j);
+            f[j + 0] *= gelu_erf_grad(bf16_lo(uu.x)); f[j + 1] *= gelu_erf_grad(bf16_hi(uu.x));
+            f[j + 2] *= gelu_erf_grad(bf16_lo(uu.y)); f[j + 3] *= gelu_erf_grad(bf16_hi(uu.y));
+            f[j + 4] *= gelu_erf_grad(bf16_lo(uu.z)); f[j + 5] *= gelu_erf_grad(bf16_hi(uu.z));
+            f[j + 6] *= gelu_erf_grad(bf16_lo(uu.w)); f[j + 7] *= gelu_erf_grad(bf16_hi(uu.w));
+          }
+        }
+        __nv_bfloat16* d = p.D + (size_t)m * p.ldd + n;
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+          uint4 o;
+          o.x = pack_bf16(f[j], f[j + 1]); o.y = pack_bf16(f[j + 2], f[j + 3]);
+          o.z = pack_bf16(f[j + 4], f[j + 5]); o.w = pack_bf16(f[j + 6], f[j + 7]);
+          stg16(d + j, o);
+        }
+        }  // bf16 epilogues
+        }  // in range
+        __syncwarp();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+// sums split-K partials [splits][M][N] fp32 -> bf16 D
+__global__ void splitk_reduce_kernel(const float* __restrict__ partial, __nv_bfloat16* __restrict__ D,
+                                     long long ldd, int M, int N, int splits) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // one float4 (4 columns) each
+  const long long total = (long long)M * N / 4;
+  if (idx >= total) return;
+  const long long e = idx * 4;
+  const int m = (int)(e / N), n = (int)(e % N);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int s = 0; s < splits; ++s) {
+    const float4 v = *reinterpret_cast<const float4*>(partial + (size_t)s * M * N + e);
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  }
+  uint2 o;
+  o.x = pack_bf16(acc.x, acc.y);
+  o.y = pack_bf16(acc.z, acc.w);
+  *reinterpret_cast<uint2*>(D + (size_t)m * ldd + n) = o;
+}
+
+static int g_num_sms = 0;
+static int num_sms() {
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  return g_num_sms;
+}
+
+template <int BN, bool A_MN, bool B_MN>
+static int32_t launch_gemm(const b2_gemm_args_t& a, int splits, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  CUtensorMap ta, tb;
+  int32_t st;
+  if (!A_MN) st = get_tensor_map_2d(&ta, a.A, (uint64_t)a.M, (uint64_t)a.K, (uint64_t)a.lda * 2, BM, 64);
+  else       st = get_tensor_map_2d(&ta, a.A, (uint64_t)a.K, (uint64_t)a.M, (uint64_t)a.lda * 2, BK, 64);
+  if (st) return st;
+  if (!B_MN) st = get_tensor_map_2d(&tb, a.B, (uint64_t)a.N, (uint64_t)a.K, (uint64_t)a.ldb * 2, BN, 64);
+  else       st = get_tensor_map_2d(&tb, a.B, (uint64_t)a.K, (uint64_t)a.N, (uint64_t)a.ldb * 2, BK, 64);
+  if (st) return st;
+
+  GemmKernelParams p;
+  p.M = (int)a.M; p.N = (int)a.N; p.K = (int)a.K;
+  p.tiles_m = (p.M + BM - 1) / BM;
+  p.tiles_n = (p.N + BN - 1) / BN;
+  p.kblocks_total = (p.K + BK - 1) / BK;
+  p.splits = splits;
+  p.kblocks_per_split = (p.kblocks_total + splits - 1) / splits;
+  p.epilogue = splits > 1 ? B2_EPI_PARTIAL_F32 : a.epilogue;
+  p.D = (__nv_bfloat16*)a.D; p.ldd = a.ldd;
+  p.bias = (const __nv_bfloat16*)a.bias;
+  p.aux_in = (const __nv_bfloat16*)a.aux_in; p.ld_aux_in = a.ld_aux_in;
+  p.aux_out = (__nv_bfloat16*)a.aux_out; p.ld_aux_out = a.ld_aux_out;
+  p.partial = (float*)a.workspace;
+  p.dropout_p = a.dropout_p; p.rng = (const unsigned long long*)a.rng_state; p.rng_site = a.rng_site;
+
+  auto kern = gemm_bf16_kernel<BN, A_MN, B_MN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  const int work = p.tiles_m * p.tiles_n * p.splits;
+  const int grid = work < num_sms() ? work : num_sms();
+  kern<<<grid, GEMM_THREADS, Cfg::kSmemBytes, stream>>>(ta, tb, p);
+  B2_CUDA(cudaGetLastError());
+  if (splits > 1) {
+    const long long total = (long long)p.M * p.N / 4;
+    splitk_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(
+        (const float*)a.workspace, (__nv_bfloat16*)a.D, a.ldd, p.M, p.N, splits);
+    B2_CUDA(cudaGetLastError());
+  }
+  return 0;
+}
+
+// Tile-width / split-K choice: maximise the fraction of SM-slots busy over whole waves.
+static void choose_config(const b2_gemm_args_t& a, int* bn_out, int* splits_out) {
+  const int sms = num_sms();
+  const int tiles_m = (int)((a.M + BM - 1) / BM);
+  const int kblocks = (int)((a.K + BK - 1) / BK);
+  const bool can_split = (a.epilogue == B2_EPI_NONE) && a.workspace != nullptr && a.bias == nullptr;
+  double best = -1.0; int best_bn = 128, best_s = 1;
+  const int bns[3] = {256, 192, 128};
+  for (int bi = 0; bi < 3; ++bi) {
+    const int bn = bns[bi];
+    if (a.N % bn != 0 && !(bn == 128)) continue;
+    const int tiles = tiles_m * (int)((a.N + bn - 1) / bn);
+    const int max_s = can_split ? 8 : 1;
+    for (int s = 1; s <= max_s; s *= 2) {
+      if (s > 1 && (kblocks / s < 8)) break;
+      if (s > 1 && (size_t)s * a.M * a.N * 4 > (size_t)a.workspace_bytes) break;
+      const int work = tiles * s;
+      const int waves = (work + sms - 1) / sms;
+      double eff = (double)work / ((double)waves * sms);
+      // per-tile fixed costs (prologue/epilogue) favour wider tiles and fewer splits a little
+      eff *= (bn == 256 ? 1.0 : bn == 192 ? 0.97 : 0.93);
+      if (s > 1) eff *= 0.92;
+      if (eff > best) { best = eff; best_bn = bn; best_s = s; }
+    }
+  }
+  *bn_out = best_bn; *splits_out = best_s;
+}
+
+}  // namespace b2
+
+using namespace b2;
+
+extern "C" int32_t b2_gemm_bf16(const b2_gemm_args_t* a, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  B2_REQUIRE(a != nullptr, "b2_gemm_bf16: null args");
+  B2_REQUIRE(a->M > 0 && a->N > 0 && a->K > 0, "b2_gemm_bf16: empty problem M=%lld N=%lld K=%lld",
+             (long long)a->M, (long long)a->N, (long long)a->K);
+  B2_REQUIRE(a->A && a->B && a->D, "b2_gemm_bf16: null operand pointer");
+  B2_REQUIRE(a->N % 32 == 0, "b2_gemm_bf16: N=%lld must be a multiple of 32", (long long)a->N);
+  B2_REQUIRE(a->K % 8 == 0 && a->lda % 8 == 0 && a->ldb % 8 == 0 && a->ldd % 8 == 0,
+             "b2_gemm_bf16: K and leading dimensions must be multiples of 8 elements (16 B)");
+  B2_REQUIRE(((uintptr_t)a->A % 16 == 0) && ((uintptr_t)a->B % 16 == 0) && ((uintptr_t)a->D % 16 == 0),
+             "b2_gemm_bf16: operands must be 16-byte aligned");
+  B2_REQUIRE(a->epilogue >= B2_EPI_NONE && a->epilogue <= B2_EPI_GELU_BWD, "b2_gemm_bf16: bad epilogue %d",
+             a->epilogue);
+  if (a->epilogue == B2_EPI_BIAS || a->epilogue == B2_EPI_BIAS_GELU || a->epilogue == B2_EPI_BIAS_DROPOUT_RESIDUAL)
+    B2_REQUIRE(a->bias != nullptr, "b2_gemm_bf16: epilogue %d needs a bias", a->epilogue);
+  if (a->epilogue == B2_EPI_BIAS_DROPOUT_RESIDUAL || a->epilogue == B2_EPI_RESIDUAL ||
+      a->epilogue == B2_EPI_GELU_BWD)
+    B2_REQUIRE(a->aux_in != nullptr && a->ld_aux_in % 8 == 0, "b2_gemm_bf16: epilogue %d needs aux_in",
+               a->epilogue);
+  if (a->epilogue == B2_EPI_BIAS_GELU)
+    B2_REQUIRE(a->aux_out != nullptr && a->ld_aux_out % 8 == 0, "b2_gemm_bf16: BIAS_GELU needs aux_out");
+  if (a->epilogue == B2_EPI_BIAS_DROPOUT_RESIDUAL && a->dropout_p > 0.f)
+    B2_REQUIRE(a->rng_state != nullptr, "b2_gemm_bf16: dropout needs rng_state");
+  B2_REQUIRE(a->dropout_p >= 0.f && a->dropout_p < 1.f, "b2_gemm_bf16: dropout_p out of range");
+
+  int bn = 128, splits = 1;
+  choose_config(*a, &bn, &splits);
+  if (a->force_bn == 128 || a->force_bn == 192 || a->force_bn == 256) {
+    B2_REQUIRE(a->N % a->force_bn == 0 || a->force_bn == 128, "b2_gemm_bf16: force_bn does not divide N");
+    bn = a->force_bn;
+  }
+  if (a->force_splits >= 1) {
+    B2_REQUIRE(a->force_splits == 1 ||
+                   (a->epilogue == B2_EPI_NONE && a->workspace &&
+                    (size_t)a->force_splits * a->M * a->N * 4 <= (size_t)a->workspace_bytes),
+               "b2_gemm_bf16: split-K needs EPI_NONE and a large enough workspace");
+    splits = a->force_splits;
+  }
+  const bool a_mn = a->a_major == B2_MAJOR_MN, b_mn = a->b_major == B2_MAJOR_MN;
+  B2_REQUIRE(!(a_mn && !b_mn), "b2_gemm_bf16: layout TT (A MN-major, B K-major) is not on the path");
+
+#define B2_DISPATCH(BN_)                                                                \
+  if (bn == BN_) {                                                                      \
+    if (!a_mn && !b_mn) return launch_gemm<BN_, false, false>(*a, splits, stream);      \
+    if (!a_mn && b_mn) return launch_gemm<BN_, false, true>(*a, splits, stream);        \
+    return launch_gemm<BN_, true, true>(*a, splits, stream);                            \
+  }
+  B2_DISPATCH(128)
+  B2_DISPATCH(192)
+  B2_DISPATCH(256)
+#undef B2_DISPATCH
+  set_error("b2_gemm_bf16: no kernel for BN=%d", bn);
+  return -2;
+}

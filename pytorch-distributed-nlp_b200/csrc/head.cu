@@ -1,0 +1,232 @@
+// Classification head: BertPooler (tanh(h[:,0] Wp^T + bp), modeling_bert.py:462-468), classifier dropout + Linear
+// (:1123-1124) and the mean cross-entropy the reference's Trainer applies (multi-gpu-distributed-cls.py:169,343),
+// forward and backward.  Work is tiny (batch x hidden): warp-per-output dot products, fp32 math, launch-latency
+// bound by construction.
+#include "common.cuh"
+#include "../../include/b2_ddp_bert.h"
+
+namespace b2 {
+
+// dot of two bf16 vectors of length H (H % 256 == 0) spread over a warp
+__device__ __forceinline__ float warp_dot_bf16(const __nv_bfloat16* __restrict__ a,
+                                               const __nv_bfloat16* __restrict__ b, int H, int lane) {
+  float s = 0.f;
+  for (int c = lane * 8; c < H; c += 256) {
+    const uint4 x = ldg16(a + c), y = ldg16(b + c);
+    s += bf16_lo(x.x) * bf16_lo(y.x) + bf16_hi(x.x) * bf16_hi(y.x) + bf16_lo(x.y) * bf16_lo(y.y) +
+         bf16_hi(x.y) * bf16_hi(y.y) + bf16_lo(x.z) * bf16_lo(y.z) + bf16_hi(x.z) * bf16_hi(y.z) +
+         bf16_lo(x.w) * bf16_lo(y.w) + bf16_hi(x.w) * bf16_hi(y.w);
+  }
+  return warp_sum(s);
+}
+
+// pooled[b, j] = tanh(h[b*seq, :] . Wp[j, :] + bp[j]); one warp per j, looping over the batch
+__global__ void __launch_bounds__(256) pooler_fwd_kernel(const __nv_bfloat16* __restrict__ h, int batch, int seq,
+                                                        int H, const __nv_bfloat16* __restrict__ Wp,
+                                                        const __nv_bfloat16* __restrict__ bp,
+                                                        __nv_bfloat16* __restrict__ pooled) {
+  const int j = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (j >= H) return;
+  const float bias = __bfloat162float(bp[j]);
+  for (int b = 0; b < batch; ++b) {
+    const float s = warp_dot_bf16(h + (size_t)b * seq * H, Wp + (size_t)j * H, H, lane);
+    if (lane == 0) pooled[(size_t)b * H + j] = __float2bfloat16_rn(tanhf(s + bias));
+  }
+}
+
+// logits[b, c] = dropout(pooled[b, :]) . Wc[c, :] + bc[c]; one warp per (b, c)
+__global__ void __launch_bounds__(256) classifier_fwd_kernel(const __nv_bfloat16* __restrict__ pooled, int batch,
+                                                            int H, const __nv_bfloat16* __restrict__ Wc,
+                                                            const __nv_bfloat16* __restrict__ bc, int C,
+                                                            float dropout_p, const unsigned long long* rng,
+                                                            unsigned site, float* __restrict__ logits) {
+  const int o = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (o >= batch * C) return;
+  const int b = o / C, c = o % C;
+  const DropCtx drop = make_drop_ctx(rng, site, dropout_p);
+  float s = 0.f;
+  for (int k = lane * 8; k < H; k += 256) {
+    const uint4 x = ldg16(pooled + (size_t)b * H + k), w = ldg16(Wc + (size_t)c * H + k);
+    const uint32_t keep = dropout_keep8(drop, (unsigned long long)b * H + k);
+    const float xv[8] = {bf16_lo(x.x), bf16_hi(x.x), bf16_lo(x.y), bf16_hi(x.y),
+                         bf16_lo(x.z), bf16_hi(x.z), bf16_lo(x.w), bf16_hi(x.w)};
+    const float wv[8] = {bf16_lo(w.x), bf16_hi(w.x), bf16_lo(w.y), bf16_hi(w.y),
+                         bf16_lo(w.z), bf16_hi(w.z), bf16_lo(w.w), bf16_hi(w.w)};
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += (((keep >> i) & 1u) ? xv[i] * drop.scale : 0.f) * wv[i];
+  }
+  s = warp_sum(s);
+  if (lane == 0) logits[o] = s + __bfloat162float(bc[c]);
+}
+
+// mean CE over the batch + dlogits = (softmax - onehot) / batch.  One block, one thread per sample (strided).
+__global__ void __launch_bounds__(256) ce_fwd_bwd_kernel(const float* __restrict__ logits,
+                                                        const long long* __restrict__ labels, int batch, int C,
+                                                        float* __restrict__ loss, float* __restrict__ dlogits) {
+  __shared__ float red[256];
+  float local = 0.f;
+  for (int b = threadIdx.x; b < batch; b += blockDim.x) {
+    const float* z = logits + (size_t)b * C;
+    float mx = -INFINITY;
+    for (int c = 0; c < C; ++c) mx = fmaxf(mx, z[c]);
+    float se = 0.f;
+    for (int c = 0; c < C; ++c) se += expf(z[c] - mx);
+    const float lse = mx + logf(se);
+    long long y = labels[b];
+    y = y < 0 ? 0 : (y >= C ? C - 1 : y);
+    local += lse - z[y];
+    if (dlogits != nullptr) {
+      const float inv = 1.0f / (float)batch;
+      for (int c = 0; c < C; ++c)
+        dlogits[(size_t)b * C + c] = (expf(z[c] - lse) - (c == (int)y ? 1.f : 0.f)) * inv;
+    }
+  }
+  red[threadIdx.x] = local;
+  __syncthreads();
+  for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+    if ((int)threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *loss = red[0] / (float)batch;
+}
+
+// ---- backward ----
+// k1: per (b, j): dpd = sum_c dlogits[b,c] Wc[c,j]  -> d_pooled = mask*scale*dpd -> d_pre = d_pooled*(1-pooled^2)
+//     (fp32 scratch [batch, H]).  Also the classifier grads: d_cls_w[c,j] = sum_b dlogits[b,c]*drop(pooled[b,j]),
+//     d_cls_b[c] = sum_b dlogits[b,c].  One thread per column j; loops over batch and classes.
+__global__ void __launch_bounds__(256) head_bwd_k1(const float* __restrict__ dlogits,
+                                                  const __nv_bfloat16* __restrict__ pooled, int batch, int H,
+                                                  const __nv_bfloat16* __restrict__ Wc, int C, float dropout_p,
+                                                  const unsigned long long* rng, unsigned site,
+                                                  float* __restrict__ d_pre, __nv_bfloat16* __restrict__ d_cls_w,
+                                                  __nv_bfloat16* __restrict__ d_cls_b) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < C && blockIdx.x == 0) {  // class bias grads (C <= blockDim.x)
+    float s = 0.f;
+    for (int b = 0; b < batch; ++b) s += dlogits[(size_t)b * C + j];
+    d_cls_b[j] = __float2bfloat16_rn(s);
+  }
+  if (j >= H) return;
+  const DropCtx drop = make_drop_ctx(rng, site, dropout_p);
+  constexpr int MAXC = 64;
+  float dw[MAXC];
+  for (int c = 0; c < C; ++c) dw[c] = 0.f;
+  for (int b = 0; b < batch; ++b) {
+    const float p = __bfloat162float(pooled[(size_t)b * H + j]);
+    const uint32_t keep8 = dropout_keep8(drop, ((unsigned long long)b * H + j) & ~7ull);
+    const float m = ((keep8 >> (j & 7)) & 1u) ? drop.scale : 0.f;
+    float dpd = 0.f;
+    for (int c = 0; c < C; ++c) {
+      const float dl = dlogits[(size_t)b * C + c];
+      dpd += dl * __bfloat162float(Wc[(size_t)c * H + j]);
+      dw[c] += dl * (p * m);
+    }
+    d_pre[(size_t)b * H + j] = dpd * m * (1.f - p * p);
+  }
+  for (int c = 0; c < C; ++c) d_cls_w[(size_t)c * H + j] = __float2bfloat16_rn(dw[c]);
+}
+
+// k2: d_pool_w[j, k] = sum_b d_pre[b, j] * h0[b, k];  d_pool_b[j] = sum_b d_pre[b, j].
+//     grid = H rows (j), threads = H/8 (each 8 consecutive k)
+__global__ void head_bwd_k2(const float* __restrict__ d_pre, const __nv_bfloat16* __restrict__ h, int batch, int seq,
+                            int H, __nv_bfloat16* __restrict__ d_pool_w, __nv_bfloat16* __restrict__ d_pool_b) {
+  const int j = blockIdx.x;
+  const int k = threadIdx.x * 8;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  float sb = 0.f;
+  for (int b = 0; b < batch; ++b) {
+    const float d = d_pre[(size_t)b * H + j];
+    sb += d;
+    const uint4 x = ldg16(h + (size_t)b * seq * H + k);
+    acc[0] += d * bf16_lo(x.x); acc[1] += d * bf16_hi(x.x); acc[2] += d * bf16_lo(x.y); acc[3] += d * bf16_hi(x.y);
+    acc[4] += d * bf16_lo(x.z); acc[5] += d * bf16_hi(x.z); acc[6] += d * bf16_lo(x.w); acc[7] += d * bf16_hi(x.w);
+  }
+  uint4 o;
+  o.x = pack_bf16(acc[0], acc[1]); o.y = pack_bf16(acc[2], acc[3]);
+  o.z = pack_bf16(acc[4], acc[5]); o.w = pack_bf16(acc[6], acc[7]);
+  stg16(d_pool_w + (size_t)j * H + k, o);
+  if (threadIdx.x == 0) d_pool_b[j] = __float2bfloat16_rn(sb);
+}
+
+// k3: d_h0[b, k] = sum_j d_pre[b, j] * Wp[j, k]  -> written into row b*seq of d_hidden (other rows pre-zeroed)
+//     grid = batch, threads = H/8
+__global__ void head_bwd_k3(const float* __restrict__ d_pre, const __nv_bfloat16* __restrict__ Wp, int seq, int H,
+                            __nv_bfloat16* __restrict__ d_hidden) {
+  const int b = blockIdx.x;
+  const int k = threadIdx.x * 8;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int j = 0; j < H; ++j) {
+    const float d = d_pre[(size_t)b * H + j];
+    const uint4 w = ldg16(Wp + (size_t)j * H + k);
+    acc[0] += d * bf16_lo(w.x); acc[1] += d * bf16_hi(w.x); acc[2] += d * bf16_lo(w.y); acc[3] += d * bf16_hi(w.y);
+    acc[4] += d * bf16_lo(w.z); acc[5] += d * bf16_hi(w.z); acc[6] += d * bf16_lo(w.w); acc[7] += d * bf16_hi(w.w);
+  }
+  uint4 o;
+  o.x = pack_bf16(acc[0], acc[1]); o.y = pack_bf16(acc[2], acc[3]);
+  o.z = pack_bf16(acc[4], acc[5]); o.w = pack_bf16(acc[6], acc[7]);
+  stg16(d_hidden + (size_t)b * seq * H + k, o);
+}
+
+}  // namespace b2
+
+using namespace b2;
+
+extern "C" int32_t b2_head_fwd(const void* hidden_states, int64_t batch, int64_t seq, int64_t hidden,
+                               const void* pool_w, const void* pool_b, const void* cls_w, const void* cls_b,
+                               int64_t num_labels, float dropout_p, const void* rng_state, uint32_t rng_site,
+                               void* pooled, float* logits, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  B2_REQUIRE(hidden_states && pool_w && pool_b && cls_w && cls_b && pooled && logits, "head_fwd: null pointer");
+  B2_REQUIRE(batch > 0 && seq > 0 && num_labels > 0, "head_fwd: empty problem");
+  B2_REQUIRE(hidden % 256 == 0, "head_fwd: hidden=%lld must be a multiple of 256", (long long)hidden);
+  B2_REQUIRE(!(dropout_p > 0.f) || rng_state, "head_fwd: dropout needs rng_state");
+  pooler_fwd_kernel<<<(unsigned)((hidden + 7) / 8), 256, 0, stream>>>(
+      (const __nv_bfloat16*)hidden_states, (int)batch, (int)seq, (int)hidden, (const __nv_bfloat16*)pool_w,
+      (const __nv_bfloat16*)pool_b, (__nv_bfloat16*)pooled);
+  B2_CUDA(cudaGetLastError());
+  classifier_fwd_kernel<<<(unsigned)((batch * num_labels + 7) / 8), 256, 0, stream>>>(
+      (const __nv_bfloat16*)pooled, (int)batch, (int)hidden, (const __nv_bfloat16*)cls_w, (const __nv_bfloat16*)cls_b,
+      (int)num_labels, dropout_p, (const unsigned long long*)rng_state, rng_site, logits);
+  B2_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int32_t b2_ce_fwd_bwd(const float* logits, const int64_t* labels, int64_t batch, int64_t num_labels,
+                                 float* loss, float* dlogits, void* stream_) {
+  B2_REQUIRE(logits && labels && loss, "ce_fwd_bwd: null pointer");
+  B2_REQUIRE(batch > 0 && num_labels > 0, "ce_fwd_bwd: empty batch");
+  ce_fwd_bwd_kernel<<<1, 256, 0, (cudaStream_t)stream_>>>(logits, (const long long*)labels, (int)batch,
+                                                          (int)num_labels, loss, dlogits);
+  B2_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int32_t b2_head_bwd(const float* dlogits, const void* hidden_states, const void* pooled, int64_t batch,
+                               int64_t seq, int64_t hidden, const void* pool_w, const void* cls_w, int64_t num_labels,
+                               float dropout_p, const void* rng_state, uint32_t rng_site, void* d_pool_w,
+                               void* d_pool_b, void* d_cls_w, void* d_cls_b, void* d_hidden, float* scratch,
+                               void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  B2_REQUIRE(dlogits && hidden_states && pooled && pool_w && cls_w && d_pool_w && d_pool_b && d_cls_w && d_cls_b &&
+                 d_hidden && scratch,
+             "head_bwd: null pointer");
+  B2_REQUIRE(batch > 0 && seq > 0, "head_bwd: empty batch");
+  B2_REQUIRE(hidden % 256 == 0 && hidden / 8 <= 1024, "head_bwd: hidden=%lld unsupported", (long long)hidden);
+  B2_REQUIRE(num_labels <= 64, "head_bwd: num_labels=%lld > 64", (long long)num_labels);
+  B2_CUDA(cudaMemsetAsync(d_hidden, 0, (size_t)batch * seq * hidden * 2, stream));
+  head_bwd_k1<<<(unsigned)((hidden + 255) / 256), 256, 0, stream>>>(
+      dlogits, (const __nv_bfloat16*)pooled, (int)batch, (int)hidden, (const __nv_bfloat16*)cls_w, (int)num_labels,
+      dropout_p, (const unsigned long long*)rng_state, rng_site, scratch, (__nv_bfloat16*)d_cls_w,
+      (__nv_bfloat16*)d_cls_b);
+  B2_CUDA(cudaGetLastError());
+  head_bwd_k2<<<(unsigned)hidden, (unsigned)(hidden / 8), 0, stream>>>(
+      scratch, (const __nv_bfloat16*)hidden_states, (int)batch, (int)seq, (int)hidden, (__nv_bfloat16*)d_pool_w,
+      (__nv_bfloat16*)d_pool_b);
+  B2_CUDA(cudaGetLastError());
+  head_bwd_k3<<<(unsigned)batch, (unsigned)(hidden / 8), 0, stream>>>(scratch, (const __nv_bfloat16*)pool_w, (int)seq,
+                                                                      (int)hidden, (__nv_bfloat16*)d_hidden);
+  B2_CUDA(cudaGetLastError());
+  return 0;
+}

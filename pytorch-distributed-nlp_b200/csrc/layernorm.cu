@@ -1,0 +1,264 @@
+// LayerNorm forward / backward and column sums: HBM-bound, one warp per row, 16-byte vector accesses,
+// fp32 statistics.  Replaces ATen native_layer_norm (+backward) issued by BertSelfOutput / BertOutput
+// (SP/transformers/models/bert/modeling_bert.py:297, :355) and the bias-gradient reductions autograd runs
+// for the dense layers.
+#include "common.cuh"
+#include "layernorm.cuh"
+#include "../../include/b2_ddp_bert.h"
+
+namespace b2 {
+
+template <int VPL>
+__global__ void __launch_bounds__(128) layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ x,
+                                                           const __nv_bfloat16* __restrict__ gamma,
+                                                           const __nv_bfloat16* __restrict__ beta, int rows, float eps,
+                                                           __nv_bfloat16* __restrict__ y, float* __restrict__ mean_out,
+                                                           float* __restrict__ rstd_out) {
+  constexpr int H = VPL * 256;
+  const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  float v[VPL * 8];
+  load_row<VPL>(x + (size_t)row * H, lane, v);
+  float mean, rstd;
+  row_stats<VPL>(v, eps, mean, rstd);
+  normalize_store<VPL>(v, mean, rstd, gamma, beta, lane, y + (size_t)row * H);
+  if (lane == 0) {
+    mean_out[row] = mean;
+    rstd_out[row] = rstd;
+  }
+}
+
+// mode 0: dropout mask (if any) applies to the LN *input* branch -> emit dx_drop = dx*mask*scale (encoder LNs)
+// mode 1: dropout mask applies to the LN *output* (embeddings: y = dropout(LN(x))) -> dy is masked on load
+template <int VPL>
+__global__ void __launch_bounds__(256) layernorm_bwd_kernel(
+    const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ dy_add,
+    const __nv_bfloat16* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ rstd,
+    const __nv_bfloat16* __restrict__ gamma, int rows, float dropout_p, const unsigned long long* rng,
+    unsigned rng_site, int mode, __nv_bfloat16* __restrict__ dx, __nv_bfloat16* __restrict__ dx_drop,
+    float* __restrict__ partials /* [gridDim.x][3][H] */) {
+  constexpr int H = VPL * 256;
+  constexpr int WARPS = 8;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const DropCtx drop = make_drop_ctx(rng, rng_site, dropout_p);
+
+  float g[VPL * 8];
+  load_row<VPL>(gamma, lane, g);
+  float acc_g[VPL * 8], acc_b[VPL * 8], acc_d[VPL * 8];
+#pragma unroll
+  for (int i = 0; i < VPL * 8; ++i) acc_g[i] = acc_b[i] = acc_d[i] = 0.f;
+
+  for (int row = blockIdx.x * WARPS + warp; row < rows; row += gridDim.x * WARPS) {
+    float dyv[VPL * 8], xv[VPL * 8];
+    load_row<VPL>(dy + (size_t)row * H, lane, dyv);
+    if (dy_add != nullptr) {
+      float t[VPL * 8];
+      load_row<VPL>(dy_add + (size_t)row * H, lane, t);
+#pragma unroll
+      for (int i = 0; i < VPL * 8; ++i) dyv[i] += t[i];
+    }
+    if (mode == 1 && drop.thresh != 0) {
+#pragma unroll
+      for (int vv = 0; vv < VPL; ++vv) {
+        const uint32_t keep = dropout_keep8(drop, (unsigned long long)row * H + (vv * 32 + lane) * 8);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) dyv[vv * 8 + i] = ((keep >> i) & 1u) ? dyv[vv * 8 + i] * drop.scale : 0.f;
+      }
+    }
+    load_row<VPL>(x + (size_t)row * H, lane, xv);
+    const float mu = mean[row], rs = rstd[row];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL * 8; ++i) {
+      xv[i] = (xv[i] - mu) * rs;               // xhat
+      const float dxh = dyv[i] * g[i];
+      s1 += dxh;
+      s2 += dxh * xv[i];
+      acc_g[i] += dyv[i] * xv[i];
+      acc_b[i] += dyv[i];
+    }
+    s1 = warp_sum(s1) * (1.0f / H);
+    s2 = warp_sum(s2) * (1.0f / H);
+    float dxv[VPL * 8];
+#pragma unroll
+    for (int i = 0; i < VPL * 8; ++i) dxv[i] = rs * (dyv[i] * g[i] - s1 - xv[i] * s2);
+    store_row<VPL>(dx + (size_t)row * H, lane, dxv);
+    if (mode == 0) {
+      if (dx_drop != nullptr) {
+#pragma unroll
+        for (int vv = 0; vv < VPL; ++vv) {
+          const uint32_t keep = dropout_keep8(drop, (unsigned long long)row * H + (vv * 32 + lane) * 8);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            // the GEMMs consume the bf16-rounded value; sum exactly what they see
+            const float t = ((keep >> i) & 1u) ? dxv[vv * 8 + i] * drop.scale : 0.f;
+            dxv[vv * 8 + i] = bf16_round(t);
+          }
+        }
+        store_row<VPL>(dx_drop + (size_t)row * H, lane, dxv);
+      } else {
+#pragma unroll
+        for (int i = 0; i < VPL * 8; ++i) dxv[i] = bf16_round(dxv[i]);
+      }
+#pragma unroll
+      for (int i = 0; i < VPL * 8; ++i) acc_d[i] += dxv[i];
+    }
+  }
+
+  // block reduction of the three column-sum sets (warps -> smem -> one partial row per block)
+  __shared__ float red[WARPS][H];
+  float* out = partials + (size_t)blockIdx.x * 3 * H;
+#define B2_REDUCE_SET(ARR, WHICH)                                                          \
+  {                                                                                        \
+    _Pragma("unroll") for (int vv = 0; vv < VPL; ++vv)                                     \
+        _Pragma("unroll") for (int i = 0; i < 8; ++i) red[warp][(vv * 32 + lane) * 8 + i] = ARR[vv * 8 + i]; \
+    __syncthreads();                                                                       \
+    for (int c = threadIdx.x; c < H; c += blockDim.x) {                                    \
+      float s = 0.f;                                                                       \
+      _Pragma("unroll") for (int w = 0; w < WARPS; ++w) s += red[w][c];                    \
+      out[(WHICH)*H + c] = s;                                                              \
+    }                                                                                      \
+    __syncthreads();                                                                       \
+  }
+  B2_REDUCE_SET(acc_g, 0)
+  B2_REDUCE_SET(acc_b, 1)
+  B2_REDUCE_SET(acc_d, 2)
+#undef B2_REDUCE_SET
+}
+
+// partials [nparts][nsets][cols] fp32 -> up to three bf16 [cols] outputs
+__global__ void colsum_finish_kernel(const float* __restrict__ partials, int nparts, int nsets, int cols,
+                                     __nv_bfloat16* o0, __nv_bfloat16* o1, __nv_bfloat16* o2) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= nsets * cols) return;
+  const int set = idx / cols, c = idx % cols;
+  __nv_bfloat16* o = set == 0 ? o0 : (set == 1 ? o1 : o2);
+  if (o == nullptr) return;
+  float s = 0.f;
+  for (int p = 0; p < nparts; ++p) s += partials[((size_t)p * nsets + set) * cols + c];
+  o[c] = __float2bfloat16_rn(s);
+}
+
+// column sums of x[rows, cols] (bf16), optional row filter; block = 8 warps x (32 lanes x 8 columns)
+__global__ void __launch_bounds__(256) colsum_partial_kernel(const __nv_bfloat16* __restrict__ x, int rows, int cols,
+                                                            long long ldx, const int* __restrict__ filter,
+                                                            int filter_value, float* __restrict__ partials) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int col = blockIdx.x * 256 + lane * 8;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (col < cols) {
+    for (int r = blockIdx.y * 8 + warp; r < rows; r += gridDim.y * 8) {
+      if (filter != nullptr && filter[r] != filter_value) continue;
+      const uint4 v = ldg16(x + (size_t)r * ldx + col);
+      acc[0] += bf16_lo(v.x); acc[1] += bf16_hi(v.x); acc[2] += bf16_lo(v.y); acc[3] += bf16_hi(v.y);
+      acc[4] += bf16_lo(v.z); acc[5] += bf16_hi(v.z); acc[6] += bf16_lo(v.w); acc[7] += bf16_hi(v.w);
+    }
+  }
+  __shared__ float red[8][256];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) red[warp][lane * 8 + i] = acc[i];
+  __syncthreads();
+  const int c = threadIdx.x;
+  if (blockIdx.x * 256 + c < cols) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += red[w][c];
+    partials[(size_t)blockIdx.y * cols + blockIdx.x * 256 + c] = s;
+  }
+}
+
+int32_t launch_colsum(const void* x, int64_t rows, int64_t cols, int64_t ldx, const int* filter, int filter_value,
+                      void* out, float* scratch, int64_t scratch_bytes, cudaStream_t stream) {
+  B2_REQUIRE(cols % 8 == 0 && ldx % 8 == 0, "colsum: cols/ldx must be multiples of 8");
+  int nparts = (int)(scratch_bytes / (cols * 4));
+  if (nparts > 32) nparts = 32;
+  B2_REQUIRE(nparts >= 1, "colsum: scratch too small (%lld bytes for %lld columns)", (long long)scratch_bytes,
+             (long long)cols);
+  dim3 grid((unsigned)((cols + 255) / 256), (unsigned)nparts);
+  colsum_partial_kernel<<<grid, 256, 0, stream>>>((const __nv_bfloat16*)x, (int)rows, (int)cols, ldx, filter,
+                                                  filter_value, scratch);
+  B2_CUDA(cudaGetLastError());
+  colsum_finish_kernel<<<(unsigned)((cols + 255) / 256), 256, 0, stream>>>(scratch, nparts, 1, (int)cols,
+                                                                           (__nv_bfloat16*)out, nullptr, nullptr);
+  B2_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int32_t launch_layernorm_bwd(const void* dy, const void* dy_add, const void* x, const float* mean, const float* rstd,
+                             const void* gamma, int64_t rows, int64_t hidden, float dropout_p, const void* rng,
+                             uint32_t site, int mode, void* dx, void* dx_drop, void* d_gamma, void* d_beta,
+                             void* d_bias, float* scratch, int64_t scratch_bytes, cudaStream_t stream) {
+  B2_REQUIRE(hidden % 256 == 0 && hidden >= 256 && hidden <= 1024, "layernorm: hidden=%lld unsupported",
+             (long long)hidden);
+  int nblocks = (int)(scratch_bytes / (3 * hidden * 4));
+  const int want = 296;
+  if (nblocks > want) nblocks = want;
+  const int max_useful = (int)((rows + 7) / 8);
+  if (nblocks > max_useful) nblocks = max_useful;
+  B2_REQUIRE(nblocks >= 1, "layernorm_bwd: scratch too small");
+#define B2_LN_BWD(VPL_)                                                                                        \
+  case VPL_:                                                                                                   \
+    layernorm_bwd_kernel<VPL_><<<nblocks, 256, 0, stream>>>(                                                   \
+        (const __nv_bfloat16*)dy, (const __nv_bfloat16*)dy_add, (const __nv_bfloat16*)x, mean, rstd,           \
+        (const __nv_bfloat16*)gamma, (int)rows, dropout_p, (const unsigned long long*)rng, site, mode,         \
+        (__nv_bfloat16*)dx, (__nv_bfloat16*)dx_drop, scratch);                                                 \
+    break;
+  switch ((int)(hidden / 256)) {
+    B2_LN_BWD(1) B2_LN_BWD(2) B2_LN_BWD(3) B2_LN_BWD(4)
+  }
+#undef B2_LN_BWD
+  B2_CUDA(cudaGetLastError());
+  colsum_finish_kernel<<<(unsigned)((3 * hidden + 255) / 256), 256, 0, stream>>>(
+      scratch, nblocks, 3, (int)hidden, (__nv_bfloat16*)d_gamma, (__nv_bfloat16*)d_beta, (__nv_bfloat16*)d_bias);
+  B2_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace b2
+
+using namespace b2;
+
+extern "C" int32_t b2_layernorm_fwd(const void* x, const void* gamma, const void* beta, int64_t rows, int64_t hidden,
+                                    float eps, void* y, float* mean, float* rstd, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  B2_REQUIRE(x && gamma && beta && y && mean && rstd, "layernorm_fwd: null pointer");
+  B2_REQUIRE(rows > 0, "layernorm_fwd: rows=%lld", (long long)rows);
+  B2_REQUIRE(hidden % 256 == 0 && hidden >= 256 && hidden <= 1024, "layernorm_fwd: hidden=%lld unsupported",
+             (long long)hidden);
+  const unsigned grid = (unsigned)((rows + 3) / 4);
+#define B2_LN_FWD(VPL_)                                                                                       \
+  case VPL_:                                                                                                  \
+    layernorm_fwd_kernel<VPL_><<<grid, 128, 0, stream>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)gamma, \
+                                                         (const __nv_bfloat16*)beta, (int)rows, eps,           \
+                                                         (__nv_bfloat16*)y, mean, rstd);                       \
+    break;
+  switch ((int)(hidden / 256)) {
+    B2_LN_FWD(1) B2_LN_FWD(2) B2_LN_FWD(3) B2_LN_FWD(4)
+  }
+#undef B2_LN_FWD
+  B2_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int32_t b2_layernorm_bwd(const void* dy, const void* dy_add, const void* x, const float* mean,
+                                    const float* rstd, const void* gamma, int64_t rows, int64_t hidden,
+                                    float dropout_p, const void* rng_state, uint32_t rng_site, void* dx,
+                                    void* dx_drop, void* d_gamma, void* d_beta, void* d_bias,
+                                    float* scratch_partials, int64_t scratch_partials_bytes, void* stream_) {
+  B2_REQUIRE(dy && x && mean && rstd && gamma && dx && d_gamma && d_beta && scratch_partials,
+             "layernorm_bwd: null pointer");
+  B2_REQUIRE(rows > 0, "layernorm_bwd: rows=%lld", (long long)rows);
+  B2_REQUIRE(!(dropout_p > 0.f) || (rng_state && dx_drop), "layernorm_bwd: dropout needs rng_state and dx_drop");
+  return launch_layernorm_bwd(dy, dy_add, x, mean, rstd, gamma, rows, hidden, dropout_p, rng_state, rng_site, 0, dx,
+                              dropout_p > 0.f ? dx_drop : nullptr, d_gamma, d_beta, d_bias, scratch_partials,
+                              scratch_partials_bytes, (cudaStream_t)stream_);
+}
+
+extern "C" int32_t b2_colsum(const void* x, int64_t rows, int64_t cols, int64_t ldx, void* out,
+                             float* scratch_partials, int64_t scratch_partials_bytes, void* stream_) {
+  B2_REQUIRE(x && out && scratch_partials, "colsum: null pointer");
+  B2_REQUIRE(rows > 0 && cols > 0, "colsum: empty input");
+  return launch_colsum(x, rows, cols, ldx, nullptr, 0, out, scratch_partials, scratch_partials_bytes,
+                       (cudaStream_t)stream_);
+}

@@ -1,0 +1,193 @@
+// Gradient exchange + optimizer in one pass over HBM.
+//
+// Replaces three things the reference does separately and un-overlapped:
+//   optimizer.zero_grad()            multi-gpu-distributed-cls.py:172   (grads are consumed in place, never re-zeroed)
+//   DDP Reducer bucket all-reduce    SP/torch/nn/parallel/distributed.py:1255-1280, reducer.hpp:276-286
+//   HF AdamW.step python loop        transformers 4.28.1 optimization.py::AdamW.step (~1600 launches/step)
+//
+// Each rank owns a contiguous 1/world slice of every bucket: it reads that slice of the bf16 gradients straight
+// out of every peer's HBM (NVSwitch peer loads), sums in fp32 in fixed rank order, divides by world (DDP's mean),
+// applies the HF AdamW update to its fp32 master weights / moments, and stores the refreshed bf16 shadow weights
+// into every peer's weight buffer (NVSwitch peer stores).  world == 1 degenerates to a fused multi-tensor AdamW.
+#include "common.cuh"
+#include "../../include/b2_ddp_bert.h"
+
+namespace b2 {
+
+constexpr int MAX_WORLD = 8;
+
+struct ReduceAdamWParams {
+  const __nv_bfloat16* grads[MAX_WORLD];
+  __nv_bfloat16* shadow[MAX_WORLD];
+  int world;
+  float* master; float* m; float* v;
+  const uint8_t* decay;
+  long long begin, end;  // element range, multiples of 8
+  // scalars pre-rounded on the host exactly as torch rounds the python doubles HF AdamW passes to its ATen ops
+  double lr_d, beta1_d, beta2_d;
+  float lr, beta1, beta2, one_minus_beta1, one_minus_beta2, eps, lr_wd;
+  int correct_bias, has_wd;
+  const long long* step_counter;
+};
+
+__global__ void __launch_bounds__(256) reduce_adamw_kernel(const ReduceAdamWParams p) {
+  // HF AdamW bias correction: step_size = lr * sqrt(1 - b2^t) / (1 - b1^t), t = steps taken including this one
+  const long long t = *p.step_counter + 1;
+  float step_size = p.lr;
+  if (p.correct_bias) {
+    const double bc1 = 1.0 - pow(p.beta1_d, (double)t);
+    const double bc2 = 1.0 - pow(p.beta2_d, (double)t);
+    step_size = (float)(p.lr_d * sqrt(bc2) / bc1);
+  }
+  const float inv_world = 1.0f / (float)p.world;
+  const long long nvec = (p.end - p.begin) >> 3;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long e = p.begin + (i << 3);
+    float g[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int r = 0; r < MAX_WORLD; ++r) {
+      if (r < p.world) {
+        // peer-mapped pointer: plain 16-byte global load; the address aperture routes it over NVLink
+        const uint4 q = *reinterpret_cast<const uint4*>(p.grads[r] + e);
+        g[0] += bf16_lo(q.x); g[1] += bf16_hi(q.x); g[2] += bf16_lo(q.y); g[3] += bf16_hi(q.y);
+        g[4] += bf16_lo(q.z); g[5] += bf16_hi(q.z); g[6] += bf16_lo(q.w); g[7] += bf16_hi(q.w);
+      }
+    }
+    const bool decay = p.has_wd && p.decay[e >> 3];
+    float4 w0 = *reinterpret_cast<const float4*>(p.master + e), w1 = *reinterpret_cast<const float4*>(p.master + e + 4);
+    float4 m0 = *reinterpret_cast<const float4*>(p.m + e), m1 = *reinterpret_cast<const float4*>(p.m + e + 4);
+    float4 v0 = *reinterpret_cast<const float4*>(p.v + e), v1 = *reinterpret_cast<const float4*>(p.v + e + 4);
+    float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+    float mm[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+    float vv[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float gk = g[k] * inv_world;
+      mm[k] = mm[k] * p.beta1 + gk * p.one_minus_beta1;
+      vv[k] = vv[k] * p.beta2 + gk * gk * p.one_minus_beta2;
+      const float denom = sqrtf(vv[k]) + p.eps;
+      w[k] = w[k] - step_size * (mm[k] / denom);
+      if (decay) w[k] = w[k] - p.lr_wd * w[k];
+    }
+    *reinterpret_cast<float4*>(p.master + e) = make_float4(w[0], w[1], w[2], w[3]);
+    *reinterpret_cast<float4*>(p.master + e + 4) = make_float4(w[4], w[5], w[6], w[7]);
+    *reinterpret_cast<float4*>(p.m + e) = make_float4(mm[0], mm[1], mm[2], mm[3]);
+    *reinterpret_cast<float4*>(p.m + e + 4) = make_float4(mm[4], mm[5], mm[6], mm[7]);
+    *reinterpret_cast<float4*>(p.v + e) = make_float4(vv[0], vv[1], vv[2], vv[3]);
+    *reinterpret_cast<float4*>(p.v + e + 4) = make_float4(vv[4], vv[5], vv[6], vv[7]);
+    uint4 o;
+    o.x = pack_bf16(w[0], w[1]); o.y = pack_bf16(w[2], w[3]);
+    o.z = pack_bf16(w[4], w[5]); o.w = pack_bf16(w[6], w[7]);
+#pragma unroll
+    for (int r = 0; r < MAX_WORLD; ++r)
+      if (r < p.world) *reinterpret_cast<uint4*>(p.shadow[r] + e) = o;
+  }
+}
+
+__global__ void step_advance_kernel(long long* step, unsigned long long* rng) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    if (step) *step += 1;
+    if (rng) rng[1] += 1;
+  }
+}
+__global__ void rng_seed_kernel(unsigned long long* rng, unsigned long long seed, unsigned long long step) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    rng[0] = seed;
+    rng[1] = step;
+  }
+}
+
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long n) {
+  const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8;
+  if (i + 8 <= n) {
+    const float4 a = *reinterpret_cast<const float4*>(src + i), b = *reinterpret_cast<const float4*>(src + i + 4);
+    uint4 o;
+    o.x = pack_bf16(a.x, a.y); o.y = pack_bf16(a.z, a.w); o.z = pack_bf16(b.x, b.y); o.w = pack_bf16(b.z, b.w);
+    stg16(dst + i, o);
+  } else {
+    for (long long k = i; k < n; ++k) dst[k] = __float2bfloat16_rn(src[k]);
+  }
+}
+__global__ void cast_bf16_f32_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ dst, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = __bfloat162float(src[i]);
+}
+
+}  // namespace b2
+
+using namespace b2;
+
+extern "C" int32_t b2_bucket_reduce_adamw(const void* const* peer_grads, void* const* peer_shadow, int32_t world,
+                                          int32_t rank, float* master, float* exp_avg, float* exp_avg_sq,
+                                          const uint8_t* decay_flags, int64_t begin, int64_t end,
+                                          const b2_adamw_hparams_t* hp, const int64_t* step_counter, void* stream_) {
+  B2_REQUIRE(peer_grads && peer_shadow && master && exp_avg && exp_avg_sq && decay_flags && hp && step_counter,
+             "bucket_reduce_adamw: null pointer");
+  B2_REQUIRE(world >= 1 && world <= MAX_WORLD && rank >= 0 && rank < world, "bucket_reduce_adamw: world=%d rank=%d",
+             world, rank);
+  B2_REQUIRE(begin >= 0 && end >= begin && begin % 8 == 0 && end % 8 == 0,
+             "bucket_reduce_adamw: slice [%lld,%lld) must be 8-element aligned", (long long)begin, (long long)end);
+  if (end == begin) return 0;
+  ReduceAdamWParams p;
+  for (int r = 0; r < MAX_WORLD; ++r) {
+    p.grads[r] = r < world ? (const __nv_bfloat16*)peer_grads[r] : nullptr;
+    p.shadow[r] = r < world ? (__nv_bfloat16*)peer_shadow[r] : nullptr;
+    if (r < world) B2_REQUIRE(p.grads[r] && p.shadow[r], "bucket_reduce_adamw: null peer pointer for rank %d", r);
+  }
+  p.world = world;
+  p.master = master; p.m = exp_avg; p.v = exp_avg_sq; p.decay = decay_flags;
+  p.begin = begin; p.end = end;
+  p.lr_d = hp->lr; p.beta1_d = hp->beta1; p.beta2_d = hp->beta2;
+  p.lr = (float)hp->lr; p.beta1 = (float)hp->beta1; p.beta2 = (float)hp->beta2;
+  p.one_minus_beta1 = (float)(1.0 - hp->beta1); p.one_minus_beta2 = (float)(1.0 - hp->beta2);
+  p.eps = (float)hp->eps; p.lr_wd = (float)(hp->lr * hp->weight_decay);
+  p.correct_bias = hp->correct_bias; p.has_wd = hp->weight_decay > 0.0 ? 1 : 0;
+  p.step_counter = (const long long*)step_counter;
+  const long long nvec = (end - begin) >> 3;
+  long long blocks = (nvec + 255) / 256;
+  const long long cap = 148 * 8;
+  if (blocks > cap) blocks = cap;
+  reduce_adamw_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream_>>>(p);
+  B2_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int32_t b2_step_advance(int64_t* step_counter, void* rng_state, void* stream_) {
+  step_advance_kernel<<<1, 32, 0, (cudaStream_t)stream_>>>((long long*)step_counter, (unsigned long long*)rng_state);
+  B2_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int32_t b2_rng_seed(void* rng_state, uint64_t seed, uint64_t step, void* stream_) {
+  B2_REQUIRE(rng_state, "rng_seed: null pointer");
+  rng_seed_kernel<<<1, 32, 0, (cudaStream_t)stream_>>>((unsigned long long*)rng_state, seed, step);
+  B2_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int32_t b2_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream_) {
+  B2_REQUIRE(src && dst && n >= 0, "cast_f32_to_bf16: bad args");
+  B2_REQUIRE(((uintptr_t)src % 16 == 0) && ((uintptr_t)dst % 16 == 0), "cast_f32_to_bf16: 16-byte alignment required");
+  if (n == 0) return 0;
+  const long long nv = (n + 7) / 8;
+  cast_f32_bf16_kernel<<<(unsigned)((nv + 255) / 256), 256, 0, (cudaStream_t)stream_>>>(src, (__nv_bfloat16*)dst, n);
+  B2_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int32_t b2_cast_bf16_to_f32(const void* src, float* dst, int64_t n, void* stream_) {
+  B2_REQUIRE(src && dst && n >= 0, "cast_bf16_to_f32: bad args");
+  if (n == 0) return 0;
+  cast_bf16_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream_>>>((const __nv_bfloat16*)src, dst,
+                                                                                       n);
+  B2_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int32_t b2_zero(void* dst, int64_t bytes, void* stream_) {
+  B2_REQUIRE(dst && bytes >= 0, "zero: bad args");
+  if (bytes == 0) return 0;
+  B2_CUDA(cudaMemsetAsync(dst, 0, (size_t)bytes, (cudaStream_t)stream_));
+  return 0;
+}

@@ -1,0 +1,653 @@
+"""Drop-in ``BertForSequenceClassification`` whose forward/backward run on the sm_100a kernels of libb2ddpbert.so.
+
+Mirrors the surface `multi-gpu-distributed-cls.py` uses (reference lines in brackets):
+  * ``BertConfig(..., num_labels=6)`` / ``BertForSequenceClassification.from_pretrained(path, config=config)`` [:336-338]
+  * ``model.cuda()`` [:340], ``model.train()/eval()`` [:166,:200]
+  * ``model(input_ids=, token_type_ids=, attention_mask=, labels=)`` -> output with ``[0]`` = loss, ``[1]`` = logits
+    [:132-136] and ``.logits`` (`predict.py:133`)
+  * ``named_parameters()`` yielding the 201 HF parameter names (the no-decay filter at [:101-107] matches on them)
+  * ``state_dict()/load_state_dict()`` in HF naming, fp32 (`test.py:96-101`, [:192,:362])
+The arithmetic follows HF ``BertForSequenceClassification`` (SP/transformers/models/bert/modeling_bert.py:53-468,
+1077-1154, eager attention) in bf16 with fp32 accumulation/statistics; fp32 master weights stay the parameters
+the user sees.  There is no PyTorch fallback: without the CUDA library every call raises.
+"""
+import math
+import os
+from collections import OrderedDict
+
+import torch
+import torch.nn as nn
+
+from . import _lib as L
+
+
+class BertConfig:
+    """The subset of ``transformers.BertConfig`` the path reads; any object with these attributes works."""
+
+    def __init__(self, vocab_size=21128, hidden_size=768, num_hidden_layers=12, num_attention_heads=12,
+                 intermediate_size=3072, hidden_act="gelu", hidden_dropout_prob=0.1,
+                 attention_probs_dropout_prob=0.1, max_position_embeddings=512, type_vocab_size=2,
+                 initializer_range=0.02, layer_norm_eps=1e-12, pad_token_id=0, num_labels=2,
+                 classifier_dropout=None, **kwargs):
+        self.vocab_size = vocab_size
+        self.hidden_size = hidden_size
+        self.num_hidden_layers = num_hidden_layers
+        self.num_attention_heads = num_attention_heads
+        self.intermediate_size = intermediate_size
+        self.hidden_act = hidden_act
+        self.hidden_dropout_prob = hidden_dropout_prob
+        self.attention_probs_dropout_prob = attention_probs_dropout_prob
+        self.max_position_embeddings = max_position_embeddings
+        self.type_vocab_size = type_vocab_size
+        self.initializer_range = initializer_range
+        self.layer_norm_eps = layer_norm_eps
+        self.pad_token_id = pad_token_id
+        self.num_labels = num_labels
+        self.classifier_dropout = classifier_dropout
+        for k, v in kwargs.items():
+            setattr(self, k, v)
+
+    @classmethod
+    def from_pretrained(cls, path, **kwargs):
+        import json
+        cfg = {}
+        f = os.path.join(path, "config.json")
+        if os.path.exists(f):
+            with open(f) as fp:
+                cfg = json.load(fp)
+        cfg.update(kwargs)
+        return cls(**cfg)
+
+
+# presets named in BASELINE.json
+def chinese_bert_wwm_ext_config(num_labels=6, **kw):
+    return BertConfig(vocab_size=21128, num_labels=num_labels, **kw)
+
+
+def bert_base_config(num_labels=6, **kw):
+    return BertConfig(vocab_size=30522, num_labels=num_labels, **kw)
+
+
+def bert_large_config(num_labels=6, **kw):
+    return BertConfig(vocab_size=30522, hidden_size=1024, num_hidden_layers=24, num_attention_heads=16,
+                      intermediate_size=4096, num_labels=num_labels, **kw)
+
+
+class SequenceClassifierOutput:
+    """Tuple-like output: with labels ``(loss, logits)``, without ``(logits,)`` — as HF's ModelOutput indexes."""
+
+    def __init__(self, loss=None, logits=None):
+        self.loss = loss
+        self.logits = logits
+
+    def to_tuple(self):
+        return tuple(v for v in (self.loss, self.logits) if v is not None)
+
+    def __getitem__(self, i):
+        if isinstance(i, str):
+            return getattr(self, i)
+        return self.to_tuple()[i]
+
+    def __iter__(self):
+        return iter(self.to_tuple())
+
+    def __len__(self):
+        return len(self.to_tuple())
+
+
+def _round8(n):
+    return (n + 7) // 8 * 8
+
+
+class _Holder(nn.Module):
+    """Name-only container so that ``named_parameters()`` reproduces the HF module paths."""
+
+
+class _Layout:
+    """Flat parameter space: HF tensors in forward order, each padded to 8 elements, Q/K/V stacked contiguously.
+    Buckets (DDP exchange units) = embeddings | encoder layer 0..L-1 | head."""
+
+    def __init__(self, cfg):
+        H, I, L_ = cfg.hidden_size, cfg.intermediate_size, cfg.num_hidden_layers
+        self.entries = OrderedDict()  # hf name -> (offset, shape)
+        self.buckets = []             # (begin, end, label)
+        off = 0
+
+        def add(name, shape):
+            nonlocal off
+            n = 1
+            for s in shape:
+                n *= s
+            self.entries[name] = (off, tuple(shape))
+            off += _round8(n)
+
+        b0 = off
+        add("bert.embeddings.word_embeddings.weight", (cfg.vocab_size, H))
+        add("bert.embeddings.position_embeddings.weight", (cfg.max_position_embeddings, H))
+        add("bert.embeddings.token_type_embeddings.weight", (cfg.type_vocab_size, H))
+        add("bert.embeddings.LayerNorm.weight", (H,))
+        add("bert.embeddings.LayerNorm.bias", (H,))
+        self.buckets.append((b0, off, "embeddings"))
+        for l in range(L_):
+            p = "bert.encoder.layer.%d." % l
+            b0 = off
+            # stacked [3H, H] weight and [3H] bias: one GEMM for Q, K, V
+            add(p + "attention.self.query.weight", (H, H))
+            add(p + "attention.self.key.weight", (H, H))
+            add(p + "attention.self.value.weight", (H, H))
+            add(p + "attention.self.query.bias", (H,))
+            add(p + "attention.self.key.bias", (H,))
+            add(p + "attention.self.value.bias", (H,))
+            add(p + "attention.output.dense.weight", (H, H))
+            add(p + "attention.output.dense.bias", (H,))
+            add(p + "attention.output.LayerNorm.weight", (H,))
+            add(p + "attention.output.LayerNorm.bias", (H,))
+            add(p + "intermediate.dense.weight", (I, H))
+            add(p + "intermediate.dense.bias", (I,))
+            add(p + "output.dense.weight", (H, I))
+            add(p + "output.dense.bias", (H,))
+            add(p + "output.LayerNorm.weight", (H,))
+            add(p + "output.LayerNorm.bias", (H,))
+            self.buckets.append((b0, off, "layer%d" % l))
+        b0 = off
+        add("bert.pooler.dense.weight", (H, H))
+        add("bert.pooler.dense.bias", (H,))
+        add("classifier.weight", (cfg.num_labels, H))
+        add("classifier.bias", (cfg.num_labels,))
+        self.buckets.append((b0, off, "head"))
+        self.total = off
+
+    def off(self, name):
+        return self.entries[name][0]
+
+
+# HF named_parameters() order (201 tensors for 12 layers); differs from the flat order only inside attention.self
+def _hf_order(cfg):
+    names = ["bert.embeddings.word_embeddings.weight", "bert.embeddings.position_embeddings.weight",
+             "bert.embeddings.token_type_embeddings.weight", "bert.embeddings.LayerNorm.weight",
+             "bert.embeddings.LayerNorm.bias"]
+    for l in range(cfg.num_hidden_layers):
+        p = "bert.encoder.layer.%d." % l
+        for m in ("attention.self.query", "attention.self.key", "attention.self.value", "attention.output.dense",
+                  "attention.output.LayerNorm", "intermediate.dense", "output.dense", "output.LayerNorm"):
+            names += [p + m + ".weight", p + m + ".bias"]
+    names += ["bert.pooler.dense.weight", "bert.pooler.dense.bias", "classifier.weight", "classifier.bias"]
+    return names
+
+
+class _StepFn(torch.autograd.Function):
+    """logits (and HF's in-model loss) with a backward that runs the CUDA backward pass."""
+
+    @staticmethod
+    def forward(ctx, anchor, model, input_ids, token_type_ids, attention_mask, labels):
+        eng = model._engine
+        logits, loss = eng.forward(input_ids, token_type_ids, attention_mask, labels, training=model.training,
+                                   need_backward=True)
+        ctx.model = model
+        ctx.has_loss = loss is not None
+        ctx.set_materialize_grads(False)
+        if loss is None:
+            return logits.clone(), torch.zeros((), device=logits.device)
+        return logits.clone(), loss.clone()
+
+    @staticmethod
+    def backward(ctx, d_logits, d_loss):
+        eng = ctx.model._engine
+        if d_logits is None and (d_loss is None or not ctx.has_loss):
+            raise RuntimeError("backward reached the model without any gradient")
+        eng.backward(d_logits, d_loss if ctx.has_loss else None)
+        ctx.model._notify_backward_done()
+        return None, None, None, None, None, None
+
+
+class BertForSequenceClassification(nn.Module):
+    def __init__(self, config):
+        super().__init__()
+        self.config = config
+        cfg = config
+        assert cfg.hidden_size % cfg.num_attention_heads == 0
+        if cfg.hidden_size // cfg.num_attention_heads != 64:
+            raise ValueError("only head_dim 64 is on the path (BERT-base / BERT-large)")
+        if getattr(cfg, "hidden_act", "gelu") != "gelu":
+            raise ValueError("only the erf GELU of the reference config is on the path")
+        self.num_labels = cfg.num_labels
+        self._layout = _Layout(cfg)
+        lay = self._layout
+        # fp32 master weights: ONE flat tensor, every nn.Parameter is a view into it
+        self._flat = torch.zeros(lay.total, dtype=torch.float32)
+        self._build_skeleton()
+        self._init_weights()
+        self._engine = None
+        self._optimizer = None
+        self._ddp = None
+
+    # ---- module skeleton reproducing HF parameter paths -------------------------------------------------------
+    def _build_skeleton(self):
+        cfg = self.config
+        self._params_by_name = OrderedDict()
+        root = self
+
+        def holder(parent, path):
+            cur = parent
+            for part in path:
+                if part.isdigit():
+                    cur = cur[int(part)]
+                    continue
+                if not hasattr(cur, part):
+                    setattr(cur, part, nn.ModuleList() if part == "layer" else _Holder())
+                cur = getattr(cur, part)
+            return cur
+
+        # registration order fixes named_parameters() order: embeddings, encoder, pooler, classifier (as HF)
+        holder(root, ["bert", "embeddings"])
+        enc = holder(root, ["bert", "encoder"])
+        enc.layer = nn.ModuleList([_Holder() for _ in range(cfg.num_hidden_layers)])
+        for name in _hf_order(cfg):
+            off, shape = self._layout.entries[name]
+            n = 1
+            for s in shape:
+                n *= s
+            parts = name.split(".")
+            mod = holder(root, parts[:-1])
+            p = nn.Parameter(self._flat[off:off + n].view(shape))
+            p._b2_owner = self
+            p._b2_name = name
+            mod.register_parameter(parts[-1], p)
+            self._params_by_name[name] = p
+        # transformers 4.28.1 (the reference's pin) keeps position_ids as a persistent buffer in checkpoints
+        emb = holder(root, ["bert", "embeddings"])
+        emb.register_buffer("position_ids", torch.arange(cfg.max_position_embeddings).unsqueeze(0), persistent=True)
+
+    def _init_weights(self):
+        """HF ``_init_weights``: N(0, initializer_range) for Linear/Embedding weights, zero pad row / biases,
+        LayerNorm (1, 0)  (SP/transformers/models/bert/modeling_bert.py `_init_weights`)."""
+        cfg = self.config
+        with torch.no_grad():
+            for name, p in self._params_by_name.items():
+                if "LayerNorm.weight" in name:
+                    p.fill_(1.0)
+                elif name.endswith(".bias") or "LayerNorm.bias" in name:
+                    p.zero_()
+                else:
+                    p.normal_(mean=0.0, std=cfg.initializer_range)
+            pad = getattr(cfg, "pad_token_id", None)
+            if pad is not None:
+                self._params_by_name["bert.embeddings.word_embeddings.weight"][pad].zero_()
+
+    # ---- construction helpers ----------------------------------------------------------------------------------
+    @classmethod
+    def from_config(cls, config, seed=None):
+        if seed is not None:
+            torch.manual_seed(seed)
+        return cls(config)
+
+    @classmethod
+    def from_pretrained(cls, model_path, config=None, **kwargs):
+        """Loads HF-format weights (``pytorch_model.bin`` / ``model.safetensors``) when present; like HF, tensors
+        absent from the checkpoint (the fresh classifier) keep their random init."""
+        if config is None:
+            config = BertConfig.from_pretrained(model_path, **kwargs)
+        model = cls(config)
+        sd = None
+        binf = os.path.join(model_path, "pytorch_model.bin")
+        sft = os.path.join(model_path, "model.safetensors")
+        if os.path.exists(binf):
+            sd = torch.load(binf, map_location="cpu")
+        elif os.path.exists(sft):
+            from safetensors.torch import load_file
+            sd = load_file(sft)
+        if sd is None:
+            raise FileNotFoundError("no pytorch_model.bin / model.safetensors under %s" % model_path)
+        model.load_state_dict(sd, strict=False)
+        return model
+
+    # ---- device movement keeps the flat storage ---------------------------------------------------------------
+    def _apply(self, fn, recurse=True):
+        new_flat = fn(self._flat)
+        if new_flat.dtype != torch.float32:
+            raise TypeError("master weights stay fp32 (the kernels compute in bf16 from a shadow copy)")
+        self._flat = new_flat.contiguous()
+        for name, p in self._params_by_name.items():
+            off, shape = self._layout.entries[name]
+            n = p.numel()
+            p.data = self._flat[off:off + n].view(shape)
+        for mod in self.modules():
+            for key, buf in list(mod._buffers.items()):
+                if buf is not None:
+                    mod._buffers[key] = fn(buf)
+        if self._flat.is_cuda:
+            self._engine = _Engine(self)
+        else:
+            self._engine = None
+        return self
+
+    # ---- state dict -----------------------------------------------------------------------------------------------
+    def load_state_dict(self, state_dict, strict=True, assign=False):
+        own = self._params_by_name
+        missing = [k for k in own if k not in state_dict]
+        unexpected = [k for k in state_dict if k not in own and not k.endswith("position_ids")
+                      and not k.endswith("embeddings.token_type_ids")]
+        if strict and (missing or unexpected):
+            raise RuntimeError("Error(s) in loading state_dict: missing %s unexpected %s" % (missing, unexpected))
+        with torch.no_grad():
+            for k, p in own.items():
+                if k in state_dict:
+                    src = state_dict[k]
+                    if tuple(src.shape) != tuple(p.shape):
+                        raise RuntimeError("size mismatch for %s: %s vs %s" % (k, tuple(src.shape), tuple(p.shape)))
+                    p.copy_(src.to(dtype=torch.float32))
+        if self._engine is not None:
+            self._engine.refresh_shadow()
+        return torch.nn.modules.module._IncompatibleKeys(missing, unexpected)
+
+    def state_dict(self, *args, **kwargs):
+        if self._ddp is not None:
+            self._ddp._gather_master()
+        return super().state_dict(*args, **kwargs)
+
+    # ---- forward ------------------------------------------------------------------------------------------------------
+    def forward(self, input_ids=None, token_type_ids=None, attention_mask=None, labels=None, **unused):
+        if self._engine is None:
+            raise RuntimeError("BertForSequenceClassification (b200) only runs on CUDA: call model.cuda() first; "
+                               "there is no CPU path.")
+        if input_ids is None:
+            raise ValueError("input_ids is required")
+        if torch.is_grad_enabled() and self.training:
+            anchor = self._params_by_name["classifier.bias"]
+            logits, loss = _StepFn.apply(anchor, self, input_ids, token_type_ids, attention_mask, labels)
+            return SequenceClassifierOutput(loss=loss if labels is not None else None, logits=logits)
+        logits, loss = self._engine.forward(input_ids, token_type_ids, attention_mask, labels,
+                                            training=self.training, need_backward=False)
+        return SequenceClassifierOutput(loss=None if loss is None else loss.clone(), logits=logits.clone())
+
+    def _notify_backward_done(self):
+        if self._ddp is not None:
+            self._ddp._on_backward_done()
+
+    # ---- test / tooling helpers -----------------------------------------------------------------------------------------
+    def grad_dict(self):
+        """fp32 copies of the (bf16) gradients of the last backward, keyed by HF parameter name."""
+        if self._engine is None:
+            raise RuntimeError("no engine (model not on CUDA)")
+        out = OrderedDict()
+        g = self._engine.grads
+        for name, p in self._params_by_name.items():
+            off, shape = self._layout.entries[name]
+            out[name] = g[off:off + p.numel()].view(shape).float()
+        return out
+
+
+class _Engine:
+    """Owns the device-side state of one model replica and drives the kernels (forward, backward)."""
+
+    def __init__(self, model):
+        L.load()
+        self.model = model
+        self.cfg = cfg = model.config
+        self.lay = model._layout
+        self.dev = model._flat.device
+        self.H, self.I = cfg.hidden_size, cfg.intermediate_size
+        self.heads, self.nl, self.C = cfg.num_attention_heads, cfg.num_hidden_layers, cfg.num_labels
+        self.p_hidden = float(cfg.hidden_dropout_prob)
+        self.p_attn = float(cfg.attention_probs_dropout_prob)
+        cd = getattr(cfg, "classifier_dropout", None)
+        self.p_cls = float(cd if cd is not None else cfg.hidden_dropout_prob)
+        n = self.lay.total
+        self.shadow = torch.empty(n, dtype=torch.bfloat16, device=self.dev)   # bf16 copy the GEMMs read
+        self.grads = torch.zeros(n, dtype=torch.bfloat16, device=self.dev)    # bf16 gradient bucket space
+        self.rng = torch.zeros(2, dtype=torch.int64, device=self.dev)         # {seed, step} for the dropout streams
+        self.owner = torch.empty(cfg.vocab_size, dtype=torch.int32, device=self.dev)
+        self.split_ws = torch.empty(64 << 20, dtype=torch.uint8, device=self.dev)
+        self.partials = torch.empty(8 << 20, dtype=torch.uint8, device=self.dev)
+        self._ws = {}
+        self._saved = None
+        s = self.stream()
+        L.call("b2_embed_owner_init", L.ptr(self.owner), cfg.vocab_size, s)
+        L.call("b2_rng_seed", L.ptr(self.rng), int(torch.initial_seed()) & ((1 << 63) - 1), 0, s)
+        self.refresh_shadow()
+
+    # ---- plumbing ----
+    def stream(self):
+        return torch.cuda.current_stream(self.dev).cuda_stream
+
+    def rebind(self, shadow, grads):
+        """DDP moves the exchanged buffers into IPC-shared allocations."""
+        shadow.copy_(self.shadow)
+        grads.zero_()
+        self.shadow, self.grads = shadow, grads
+
+    def refresh_shadow(self):
+        L.call("b2_cast_f32_to_bf16", L.ptr(self.model._flat), L.ptr(self.shadow), self.lay.total, self.stream())
+
+    def seed_dropout(self, seed, step=0):
+        L.call("b2_rng_seed", L.ptr(self.rng), int(seed), int(step), self.stream())
+
+    def w(self, name):
+        return self.shadow.data_ptr() + 2 * self.lay.off(name)
+
+    def g(self, name):
+        return self.grads.data_ptr() + 2 * self.lay.off(name)
+
+    def workspace(self, B, S):
+        key = (B, S)
+        ws = self._ws.get(key)
+        if ws is not None:
+            return ws
+        H, I, M, nl = self.H, self.I, B * S, self.nl
+        bf, f32, dev = torch.bfloat16, torch.float32, self.dev
+
+        def e(*shape, dtype=bf):
+            return torch.empty(*shape, dtype=dtype, device=dev)
+
+        ws = {
+            "emb_out": e(M, H), "emb_pre": e(M, H), "emb_mean": e(M, dtype=f32), "emb_rstd": e(M, dtype=f32),
+            "ids32": e(M, dtype=torch.int32), "tt32": e(M, dtype=torch.int32),
+            "layers": [
+                {"qkv": e(M, 3 * H), "ctx": e(M, H), "lse": e(B * self.heads * S, dtype=f32), "z1": e(M, H),
+                 "x1": e(M, H), "mean1": e(M, dtype=f32), "rstd1": e(M, dtype=f32), "u": e(M, I), "h": e(M, I),
+                 "z2": e(M, H), "x2": e(M, H), "mean2": e(M, dtype=f32), "rstd2": e(M, dtype=f32)}
+                for _ in range(nl)],
+            "pooled": e(B, H), "logits": e(B, self.C, dtype=f32), "loss": e((), dtype=f32),
+            "dlogits": e(B, self.C, dtype=f32), "dloss_logits": e(B, self.C, dtype=f32),
+            "dxA": e(M, H), "dxB": e(M, H), "dz": e(M, H), "dzd": e(M, H), "dz1": e(M, H), "dz1d": e(M, H),
+            "dU": e(M, I), "dctx": e(M, H), "dqkv": e(M, 3 * H), "head_scratch": e(B, H, dtype=f32),
+            "dq_accum": e(M, H, dtype=f32) if S > 128 else None,
+            "zeros_tt": torch.zeros(B, S, dtype=torch.int64, device=dev),
+        }
+        self._ws[key] = ws
+        return ws
+
+    def gemm(self, M, N, K, A, lda, a_major, Bm, ldb, b_major, D, ldd, epi=L.EPI_NONE, bias=None, aux_in=None,
+             ld_aux_in=0, aux_out=None, ld_aux_out=0, p=0.0, site=0, split=False, stream=None):
+        a = L.GemmArgs()
+        a.M, a.N, a.K = M, N, K
+        a.A, a.lda, a.a_major = A, lda, a_major
+        a.B, a.ldb, a.b_major = Bm, ldb, b_major
+        a.D, a.ldd, a.epilogue = D, ldd, epi
+        a.bias, a.aux_in, a.ld_aux_in, a.aux_out, a.ld_aux_out = bias, aux_in, ld_aux_in, aux_out, ld_aux_out
+        a.dropout_p, a.rng_state, a.rng_site = p, self.rng.data_ptr(), site
+        if split:
+            a.workspace, a.workspace_bytes = self.split_ws.data_ptr(), self.split_ws.numel()
+        else:
+            a.workspace, a.workspace_bytes = None, 0
+        a.force_bn = int(os.environ.get("B2_FORCE_BN", "0"))
+        a.force_splits = 0
+        L.call("b2_gemm_bf16", a, stream if stream is not None else self.stream())
+
+    # ---- forward --------------------------------------------------------------------------------------------------------
+    def forward(self, input_ids, token_type_ids, attention_mask, labels, training, need_backward):
+        cfg, H, I = self.cfg, self.H, self.I
+        if input_ids.dim() != 2:
+            raise ValueError("input_ids must be [batch, seq]")
+        B, S = input_ids.shape
+        if B == 0 or S == 0:
+            raise ValueError("empty batch")
+        if S % 128 != 0 or S > 512 or S > cfg.max_position_embeddings:
+            raise ValueError("seq_len=%d: the attention kernel covers multiples of 128 up to 512 "
+                             "(the reference pads every batch to max_seq_len=128)" % S)
+        for t, nm in ((input_ids, "input_ids"), (token_type_ids, "token_type_ids"),
+                      (attention_mask, "attention_mask"), (labels, "labels")):
+            if t is not None:
+                if t.device != self.dev:
+                    raise RuntimeError("%s is on %s, model on %s" % (nm, t.device, self.dev))
+                if t.dtype != torch.int64:
+                    raise TypeError("%s must be int64 (as the reference Collate produces)" % nm)
+        ws = self.workspace(B, S)
+        M = B * S
+        s = self.stream()
+        ids = input_ids.contiguous()
+        tt = (token_type_ids if token_type_ids is not None else ws["zeros_tt"]).contiguous()
+        mask = attention_mask.contiguous() if attention_mask is not None else None
+        p_h = self.p_hidden if training else 0.0
+        p_a = self.p_attn if training else 0.0
+        p_c = self.p_cls if training else 0.0
+        rng = self.rng.data_ptr()
+        w = self.w
+        KM, MN = L.MAJOR_K, L.MAJOR_MN
+
+        L.call("b2_embed_fwd", ids.data_ptr(), tt.data_ptr(), B, S, w("bert.embeddings.word_embeddings.weight"),
+               w("bert.embeddings.position_embeddings.weight"), w("bert.embeddings.token_type_embeddings.weight"),
+               w("bert.embeddings.LayerNorm.weight"), w("bert.embeddings.LayerNorm.bias"), H, cfg.vocab_size,
+               cfg.type_vocab_size, float(cfg.layer_norm_eps), p_h, rng, 0, L.ptr(ws["emb_out"]),
+               L.ptr(ws["emb_pre"]), L.ptr(ws["emb_mean"]), L.ptr(ws["emb_rstd"]), L.ptr(ws["ids32"]),
+               L.ptr(ws["tt32"]), s)
+        x = ws["emb_out"]
+        for l in range(self.nl):
+            a = ws["layers"][l]
+            pre = "bert.encoder.layer.%d." % l
+            self.gemm(M, 3 * H, H, x.data_ptr(), H, KM, w(pre + "attention.self.query.weight"), H, KM,
+                      a["qkv"].data_ptr(), 3 * H, L.EPI_BIAS, bias=w(pre + "attention.self.query.bias"))
+            L.call("b2_attention_fwd", a["qkv"].data_ptr(), L.ptr(mask), B, S, self.heads, 64, p_a, rng, 1 + 3 * l,
+                   a["ctx"].data_ptr(), a["lse"].data_ptr(), s)
+            self.gemm(M, H, H, a["ctx"].data_ptr(), H, KM, w(pre + "attention.output.dense.weight"), H, KM,
+                      a["z1"].data_ptr(), H, L.EPI_BIAS_DROPOUT_RESIDUAL, bias=w(pre + "attention.output.dense.bias"),
+                      aux_in=x.data_ptr(), ld_aux_in=H, p=p_h, site=2 + 3 * l)
+            L.call("b2_layernorm_fwd", a["z1"].data_ptr(), w(pre + "attention.output.LayerNorm.weight"),
+                   w(pre + "attention.output.LayerNorm.bias"), M, H, float(cfg.layer_norm_eps), a["x1"].data_ptr(),
+                   a["mean1"].data_ptr(), a["rstd1"].data_ptr(), s)
+            self.gemm(M, I, H, a["x1"].data_ptr(), H, KM, w(pre + "intermediate.dense.weight"), H, KM,
+                      a["h"].data_ptr(), I, L.EPI_BIAS_GELU, bias=w(pre + "intermediate.dense.bias"),
+                      aux_out=a["u"].data_ptr(), ld_aux_out=I)
+            self.gemm(M, H, I, a["h"].data_ptr(), I, KM, w(pre + "output.dense.weight"), I, KM,
+                      a["z2"].data_ptr(), H, L.EPI_BIAS_DROPOUT_RESIDUAL, bias=w(pre + "output.dense.bias"),
+                      aux_in=a["x1"].data_ptr(), ld_aux_in=H, p=p_h, site=3 + 3 * l)
+            L.call("b2_layernorm_fwd", a["z2"].data_ptr(), w(pre + "output.LayerNorm.weight"),
+                   w(pre + "output.LayerNorm.bias"), M, H, float(cfg.layer_norm_eps), a["x2"].data_ptr(),
+                   a["mean2"].data_ptr(), a["rstd2"].data_ptr(), s)
+            x = a["x2"]
+        L.call("b2_head_fwd", x.data_ptr(), B, S, H, w("bert.pooler.dense.weight"), w("bert.pooler.dense.bias"),
+               w("classifier.weight"), w("classifier.bias"), self.C, p_c, rng, 1 + 3 * self.nl,
+               ws["pooled"].data_ptr(), ws["logits"].data_ptr(), s)
+        loss = None
+        if labels is not None:
+            lab = labels.contiguous().view(-1)
+            if lab.numel() != B:
+                raise ValueError("labels must be [batch]")
+            L.call("b2_ce_fwd_bwd", ws["logits"].data_ptr(), lab.data_ptr(), B, self.C, ws["loss"].data_ptr(),
+                   ws["dloss_logits"].data_ptr() if need_backward else None, s)
+            loss = ws["loss"]
+        if need_backward:
+            self._saved = (B, S, mask, p_h, p_a, p_c)
+        return ws["logits"], loss
+
+    # ---- backward ---------------------------------------------------------------------------------------------------------
+    def backward(self, d_logits, d_loss=None, stream=None):
+        """d_logits: fp32 [B, C] gradient wrt the returned logits; d_loss: optional scalar gradient wrt HF's loss."""
+        if self._saved is None:
+            raise RuntimeError("backward called without a training forward")
+        B, S, mask, p_h, p_a, p_c = self._saved
+        self._saved = None
+        cfg, H, I, M = self.cfg, self.H, self.I, B * S
+        ws = self.workspace(B, S)
+        s = self.stream()
+        rng = self.rng.data_ptr()
+        w, g = self.w, self.g
+        KM, MN = L.MAJOR_K, L.MAJOR_MN
+        scratch, scratch_bytes = self.partials.data_ptr(), self.partials.numel()
+
+        dl = ws["dlogits"]
+        if d_logits is not None:
+            dl.copy_(d_logits.to(torch.float32).reshape(B, self.C))
+        else:
+            dl.zero_()
+        if d_loss is not None:
+            dl.add_(ws["dloss_logits"] * d_loss.to(torch.float32))
+        return self._backward_from_dlogits(dl, B, S, mask, p_h, p_a, p_c)
+
+    def _backward_from_dlogits(self, dl, B, S, mask, p_h, p_a, p_c):
+        cfg, H, I, M = self.cfg, self.H, self.I, B * S
+        ws = self.workspace(B, S)
+        s = self.stream()
+        rng = self.rng.data_ptr()
+        w, g = self.w, self.g
+        KM, MN = L.MAJOR_K, L.MAJOR_MN
+        scratch, scratch_bytes = self.partials.data_ptr(), self.partials.numel()
+        hooks = self.model._ddp
+
+        # embedding-table gradients are scatter targets: clear the whole bucket (word rows not in the batch, unused
+        # position rows and padding must read as zero for the dense DDP/AdamW pass, like the reference's dense grads)
+        eb, ee, _ = self.lay.buckets[0]
+        L.call("b2_zero", self.grads.data_ptr() + 2 * eb, 2 * (ee - eb), s)
+
+        x_last = ws["layers"][-1]["x2"] if self.nl > 0 else ws["emb_out"]
+        L.call("b2_head_bwd", dl.data_ptr(), x_last.data_ptr(), ws["pooled"].data_ptr(), B, S, H,
+               w("bert.pooler.dense.weight"), w("classifier.weight"), self.C, p_c, rng, 1 + 3 * self.nl,
+               g("bert.pooler.dense.weight"), g("bert.pooler.dense.bias"), g("classifier.weight"),
+               g("classifier.bias"), ws["dxA"].data_ptr(), ws["head_scratch"].data_ptr(), s)
+        if hooks is not None:
+            hooks._bucket_ready(len(self.lay.buckets) - 1)
+        dx, dx_other = ws["dxA"], ws["dxB"]
+        for l in reversed(range(self.nl)):
+            a = ws["layers"][l]
+            x_in = ws["layers"][l - 1]["x2"] if l > 0 else ws["emb_out"]
+            pre = "bert.encoder.layer.%d." % l
+            # --- BertOutput: LN2 backward (+ dropout mask, bias grad), FFN2 wgrad/dgrad(+GELU')
+            L.call("b2_layernorm_bwd", dx.data_ptr(), None, a["z2"].data_ptr(), a["mean2"].data_ptr(),
+                   a["rstd2"].data_ptr(), w(pre + "output.LayerNorm.weight"), M, H, p_h, rng, 3 + 3 * l,
+                   ws["dz"].data_ptr(), ws["dzd"].data_ptr(), g(pre + "output.LayerNorm.weight"),
+                   g(pre + "output.LayerNorm.bias"), g(pre + "output.dense.bias"), scratch, scratch_bytes, s)
+            dy2 = ws["dzd"] if p_h > 0 else ws["dz"]
+            self.gemm(H, I, M, dy2.data_ptr(), H, MN, a["h"].data_ptr(), I, MN, g(pre + "output.dense.weight"), I,
+                      split=True)
+            self.gemm(M, I, H, dy2.data_ptr(), H, KM, w(pre + "output.dense.weight"), I, MN, ws["dU"].data_ptr(), I,
+                      L.EPI_GELU_BWD, aux_in=a["u"].data_ptr(), ld_aux_in=I)
+            # --- BertIntermediate
+            L.call("b2_colsum", ws["dU"].data_ptr(), M, I, I, g(pre + "intermediate.dense.bias"), scratch,
+                   scratch_bytes, s)
+            self.gemm(I, H, M, ws["dU"].data_ptr(), I, MN, a["x1"].data_ptr(), H, MN,
+                      g(pre + "intermediate.dense.weight"), H, split=True)
+            self.gemm(M, H, I, ws["dU"].data_ptr(), I, KM, w(pre + "intermediate.dense.weight"), H, MN,
+                      dx_other.data_ptr(), H, L.EPI_RESIDUAL, aux_in=ws["dz"].data_ptr(), ld_aux_in=H)
+            # --- BertSelfOutput
+            L.call("b2_layernorm_bwd", dx_other.data_ptr(), None, a["z1"].data_ptr(), a["mean1"].data_ptr(),
+                   a["rstd1"].data_ptr(), w(pre + "attention.output.LayerNorm.weight"), M, H, p_h, rng, 2 + 3 * l,
+                   ws["dz1"].data_ptr(), ws["dz1d"].data_ptr(), g(pre + "attention.output.LayerNorm.weight"),
+                   g(pre + "attention.output.LayerNorm.bias"), g(pre + "attention.output.dense.bias"), scratch,
+                   scratch_bytes, s)
+            dy1 = ws["dz1d"] if p_h > 0 else ws["dz1"]
+            self.gemm(H, H, M, dy1.data_ptr(), H, MN, a["ctx"].data_ptr(), H, MN,
+                      g(pre + "attention.output.dense.weight"), H, split=True)
+            self.gemm(M, H, H, dy1.data_ptr(), H, KM, w(pre + "attention.output.dense.weight"), H, MN,
+                      ws["dctx"].data_ptr(), H)
+            # --- BertSelfAttention
+            L.call("b2_attention_bwd", a["qkv"].data_ptr(), L.ptr(mask), a["ctx"].data_ptr(), ws["dctx"].data_ptr(),
+                   a["lse"].data_ptr(), B, S, self.heads, 64, p_a, rng, 1 + 3 * l, ws["dqkv"].data_ptr(),
+                   L.ptr(ws["dq_accum"]), s)
+            L.call("b2_colsum", ws["dqkv"].data_ptr(), M, 3 * H, 3 * H, g(pre + "attention.self.query.bias"), scratch,
+                   scratch_bytes, s)
+            self.gemm(3 * H, H, M, ws["dqkv"].data_ptr(), 3 * H, MN, x_in.data_ptr(), H, MN,
+                      g(pre + "attention.self.query.weight"), H, split=True)
+            self.gemm(M, H, 3 * H, ws["dqkv"].data_ptr(), 3 * H, KM, w(pre + "attention.self.query.weight"), H, MN,
+                      dx.data_ptr(), H, L.EPI_RESIDUAL, aux_in=ws["dz1"].data_ptr(), ld_aux_in=H)
+            if hooks is not None:
+                hooks._bucket_ready(1 + l)
+        L.call("b2_embed_bwd", dx.data_ptr(), ws["emb_pre"].data_ptr(), ws["emb_mean"].data_ptr(),
+               ws["emb_rstd"].data_ptr(), w("bert.embeddings.LayerNorm.weight"), ws["ids32"].data_ptr(),
+               ws["tt32"].data_ptr(), B, S, H, cfg.vocab_size, cfg.type_vocab_size,
+               -1 if getattr(cfg, "pad_token_id", None) is None else int(cfg.pad_token_id), p_h, rng, 0,
+               g("bert.embeddings.word_embeddings.weight"), g("bert.embeddings.position_embeddings.weight"),
+               g("bert.embeddings.token_type_embeddings.weight"), g("bert.embeddings.LayerNorm.weight"),
+               g("bert.embeddings.LayerNorm.bias"), ws["dxB"].data_ptr(), scratch, scratch_bytes,
+               self.owner.data_ptr(), s)
+        if hooks is not None:
+            hooks._bucket_ready(0)

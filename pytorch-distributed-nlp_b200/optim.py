@@ -1,0 +1,136 @@
+"""HF-semantics ``AdamW`` + the reference's ``build_optimizer`` on top of the fused CUDA update.
+
+Reference surface: ``build_optimizer(model, args)`` (multi-gpu-distributed-cls.py:100-111) returning an object with
+``zero_grad()`` [:172] and ``step()`` [:174].  The arithmetic is transformers 4.28.1 ``optimization.py::AdamW.step``
+(eps added to sqrt(v) before the bias correction, weight decay applied after the Adam update with the updated
+weight, ``correct_bias=True``) — NOT ``torch.optim.AdamW``.  One kernel updates the whole flat parameter space
+(or, under DDP, this rank's slice of every bucket, fused with the gradient mean over peers).
+"""
+import torch
+
+from . import _lib as L
+
+
+class AdamW(torch.optim.Optimizer):
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-6, weight_decay=0.0, correct_bias=True,
+                 no_deprecation_warning=True):
+        if lr < 0.0:
+            raise ValueError(f"Invalid learning rate: {lr} - should be >= 0.0")
+        if not 0.0 <= betas[0] < 1.0:
+            raise ValueError(f"Invalid beta parameter: {betas[0]} - should be in [0.0, 1.0)")
+        if not 0.0 <= betas[1] < 1.0:
+            raise ValueError(f"Invalid beta parameter: {betas[1]} - should be in [0.0, 1.0)")
+        if not 0.0 <= eps:
+            raise ValueError(f"Invalid epsilon value: {eps} - should be >= 0.0")
+        defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, correct_bias=correct_bias)
+        super().__init__(params, defaults)
+        owners = {id(getattr(p, "_b2_owner", None)) for g in self.param_groups for p in g["params"]}
+        first = self.param_groups[0]["params"][0]
+        self._model = getattr(first, "_b2_owner", None)
+        if self._model is None or len(owners) != 1:
+            raise TypeError("this AdamW drives the fused CUDA update of ONE b200 BertForSequenceClassification; "
+                            "got parameters that do not belong to such a model")
+        g0 = self.param_groups[0]
+        for g in self.param_groups[1:]:
+            if (g["lr"], tuple(g["betas"]), g["eps"], g["correct_bias"]) != \
+                    (g0["lr"], tuple(g0["betas"]), g0["eps"], g0["correct_bias"]):
+                raise ValueError("param groups may differ only in weight_decay (as the reference's two groups do)")
+        wds = sorted({float(g["weight_decay"]) for g in self.param_groups if g["weight_decay"] > 0})
+        if len(wds) > 1:
+            raise ValueError("at most one non-zero weight_decay value is supported")
+        self._wd = wds[0] if wds else 0.0
+        lay = self._model._layout
+        covered = set()
+        flags = torch.zeros(lay.total // 8, dtype=torch.uint8)
+        for g in self.param_groups:
+            for p in g["params"]:
+                off, _shape = lay.entries[p._b2_name]
+                covered.add(p._b2_name)
+                if g["weight_decay"] > 0:
+                    flags[off // 8:(off + (p.numel() + 7) // 8 * 8) // 8] = 1
+        if covered != set(lay.entries):
+            raise ValueError("the fused update steps every parameter of the model; %d of %d were passed"
+                             % (len(covered), len(lay.entries)))
+        self._decay_flags_cpu = flags
+        self._dev_state = None
+        self._model._optimizer = self
+
+    # -- device state (fp32 moments, step counter) ------------------------------------------------------------------
+    def _state(self):
+        eng = self._model._engine
+        if eng is None:
+            raise RuntimeError("optimizer.step(): the model is not on CUDA")
+        if self._dev_state is None or self._dev_state["dev"] != eng.dev:
+            n = self._model._layout.total
+            self._dev_state = {
+                "dev": eng.dev,
+                "exp_avg": torch.zeros(n, dtype=torch.float32, device=eng.dev),
+                "exp_avg_sq": torch.zeros(n, dtype=torch.float32, device=eng.dev),
+                "step": torch.zeros(1, dtype=torch.int64, device=eng.dev),
+                "decay": self._decay_flags_cpu.to(eng.dev),
+            }
+        return self._dev_state
+
+    def hparams(self):
+        g = self.param_groups[0]
+        hp = L.AdamWHParams()
+        hp.lr, hp.beta1, hp.beta2, hp.eps = float(g["lr"]), float(g["betas"][0]), float(g["betas"][1]), float(g["eps"])
+        hp.weight_decay = float(self._wd)
+        hp.correct_bias = 1 if g["correct_bias"] else 0
+        return hp
+
+    def zero_grad(self, set_to_none=True):
+        """Gradients live in the bf16 bucket space and are overwritten by every backward: nothing to clear
+        (the reference's zero_grad [:172] exists only because torch accumulates into .grad)."""
+        return None
+
+    def update_range(self, begin, end, world, rank, peer_grads, peer_shadow, stream):
+        """Fused (mean over peers +) HF-AdamW on flat elements [begin, end)."""
+        st = self._state()
+        hp = self.hparams()
+        model = self._model
+        L.call("b2_bucket_reduce_adamw", L.ptr_array(peer_grads), L.ptr_array(peer_shadow), world, rank,
+               L.ptr(model._flat), L.ptr(st["exp_avg"]), L.ptr(st["exp_avg_sq"]), L.ptr(st["decay"]), begin, end,
+               hp, L.ptr(st["step"]), stream)
+
+    def advance(self, stream):
+        st = self._state()
+        L.call("b2_step_advance", L.ptr(st["step"]), L.ptr(self._model._engine.rng), stream)
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = closure() if closure is not None else None
+        model = self._model
+        eng = model._engine
+        if eng is None:
+            raise RuntimeError("optimizer.step(): the model is not on CUDA")
+        if model._ddp is not None and model._ddp.world > 1:
+            model._ddp._optimizer_step(self)
+        else:
+            s = eng.stream()
+            self.update_range(0, model._layout.total, 1, 0, [eng.grads.data_ptr()], [eng.shadow.data_ptr()], s)
+            self.advance(s)
+        return loss
+
+    def moments(self):
+        """(exp_avg, exp_avg_sq) fp32 by HF parameter name — for tests/checkpoint tooling."""
+        st = self._state()
+        out = {}
+        for name, p in self._model._params_by_name.items():
+            off, shape = self._model._layout.entries[name]
+            out[name] = (st["exp_avg"][off:off + p.numel()].view(shape), st["exp_avg_sq"][off:off + p.numel()].view(shape))
+        return out
+
+
+def build_optimizer(model, args):
+    """Same grouping rule as the reference (multi-gpu-distributed-cls.py:100-111): no weight decay for names
+    containing 'bias' or 'LayerNorm.weight'; lr = args.learning_rate; HF AdamW defaults otherwise."""
+    no_decay = ['bias', 'LayerNorm.weight']
+    optimizer_grouped_parameters = [
+        {'params': [p for n, p in model.named_parameters() if not any(nd in n for nd in no_decay)],
+         'weight_decay': args.weight_decay},
+        {'params': [p for n, p in model.named_parameters() if any(nd in n for nd in no_decay)],
+         'weight_decay': 0.0}
+    ]
+    optimizer = AdamW(optimizer_grouped_parameters, lr=args.learning_rate)
+    return optimizer
