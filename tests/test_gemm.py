@@ -1,0 +1,155 @@
+"""tcgen05 GEMM through the C ABI vs a torch fp32 matmul of the same bf16 operands (GPU)."""
+import pytest
+import torch
+
+from parity import b2, philox_keep_mask
+from pytorch_distributed_nlp_b200 import _lib as L
+
+pytestmark = pytest.mark.gpu
+
+
+def _rng_state(dev, seed=77, step=3):
+    return torch.tensor([seed, step], dtype=torch.int64, device=dev)
+
+
+def _call(M, N, K, A, lda, a_major, B, ldb, b_major, D, epi=L.EPI_NONE, bias=None, aux_in=None, aux_out=None,
+          p=0.0, rng=None, site=0, ws=None, bn=0, splits=0):
+    a = L.GemmArgs()
+    a.M, a.N, a.K = M, N, K
+    a.A, a.lda, a.a_major = A.data_ptr(), lda, a_major
+    a.B, a.ldb, a.b_major = B.data_ptr(), ldb, b_major
+    a.D, a.ldd, a.epilogue = D.data_ptr(), D.shape[1], epi
+    a.bias = L.ptr(bias)
+    a.aux_in, a.ld_aux_in = L.ptr(aux_in), (aux_in.shape[1] if aux_in is not None else 0)
+    a.aux_out, a.ld_aux_out = L.ptr(aux_out), (aux_out.shape[1] if aux_out is not None else 0)
+    a.dropout_p, a.rng_state, a.rng_site = p, L.ptr(rng), site
+    a.workspace, a.workspace_bytes = L.ptr(ws), (ws.numel() if ws is not None else 0)
+    a.force_bn, a.force_splits = bn, splits
+    L.call("b2_gemm_bf16", a, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+
+
+def _rand(shape, dev, scale=1.0):
+    return (torch.randn(*shape, device=dev) * scale).to(torch.bfloat16)
+
+
+def _check(got, ref, tol=2e-2):
+    ref = ref.float()
+    err = (got.float() - ref).abs().max().item()
+    scale = ref.abs().max().item() + 1e-6
+    assert err <= tol * scale, "max err %.4g vs scale %.4g" % (err, scale)
+
+
+@pytest.mark.parametrize("bn", [128, 192, 256])
+@pytest.mark.parametrize("shape", [(256, 768, 64), (384, 768, 768), (4096, 2304, 768), (200, 768, 136)])
+def test_nt_bias(cuda_dev, bn, shape):
+    M, N, K = shape
+    torch.manual_seed(0)
+    A, B, bias = _rand((M, K), cuda_dev), _rand((N, K), cuda_dev, 0.05), _rand((N,), cuda_dev)
+    D = torch.zeros(M, N, dtype=torch.bfloat16, device=cuda_dev)
+    _call(M, N, K, A, K, L.MAJOR_K, B, K, L.MAJOR_K, D, L.EPI_BIAS, bias=bias, bn=bn)
+    _check(D, A.float() @ B.float().t() + bias.float())
+
+
+@pytest.mark.parametrize("bn", [128, 192, 256])
+def test_nn_dgrad(cuda_dev, bn):
+    M, N, K = 512, 768, 3072
+    torch.manual_seed(1)
+    A, B = _rand((M, K), cuda_dev), _rand((K, N), cuda_dev, 0.05)
+    D = torch.zeros(M, N, dtype=torch.bfloat16, device=cuda_dev)
+    _call(M, N, K, A, K, L.MAJOR_K, B, N, L.MAJOR_MN, D, bn=bn)
+    _check(D, A.float() @ B.float())
+
+
+@pytest.mark.parametrize("bn,splits", [(128, 1), (192, 1), (256, 1), (128, 4), (256, 2)])
+def test_tn_wgrad(cuda_dev, bn, splits):
+    M, N, K = 768, 768, 2048   # dW[M,N] = dY[K,M]^T X[K,N]
+    torch.manual_seed(2)
+    A, B = _rand((K, M), cuda_dev), _rand((K, N), cuda_dev)
+    D = torch.zeros(M, N, dtype=torch.bfloat16, device=cuda_dev)
+    ws = torch.empty(splits * M * N * 4, dtype=torch.uint8, device=cuda_dev)
+    _call(M, N, K, A, M, L.MAJOR_MN, B, N, L.MAJOR_MN, D, ws=ws, bn=bn, splits=splits)
+    _check(D, A.float().t() @ B.float())
+
+
+def test_auto_config_and_ld(cuda_dev):
+    """auto tile/split choice + strided operands (Q columns of a packed QKV activation)."""
+    M, N, K = 1024, 768, 768
+    torch.manual_seed(3)
+    big = _rand((M, 3 * K), cuda_dev)
+    A = big[:, K:2 * K]
+    B = _rand((N, K), cuda_dev, 0.05)
+    D = torch.zeros(M, N, dtype=torch.bfloat16, device=cuda_dev)
+    _call(M, N, K, A, 3 * K, L.MAJOR_K, B, K, L.MAJOR_K, D)
+    _check(D, A.float() @ B.float().t())
+
+
+def test_bias_gelu(cuda_dev):
+    M, N, K = 512, 3072, 768
+    torch.manual_seed(4)
+    A, B, bias = _rand((M, K), cuda_dev), _rand((N, K), cuda_dev, 0.05), _rand((N,), cuda_dev)
+    D = torch.zeros(M, N, dtype=torch.bfloat16, device=cuda_dev)
+    U = torch.zeros(M, N, dtype=torch.bfloat16, device=cuda_dev)
+    _call(M, N, K, A, K, L.MAJOR_K, B, K, L.MAJOR_K, D, L.EPI_BIAS_GELU, bias=bias, aux_out=U)
+    u = A.float() @ B.float().t() + bias.float()
+    _check(U, u)
+    _check(D, torch.nn.functional.gelu(U.float()), tol=1e-2)
+
+
+@pytest.mark.parametrize("p", [0.0, 0.1])
+def test_bias_dropout_residual(cuda_dev, p):
+    M, N, K = 512, 768, 3072
+    torch.manual_seed(5)
+    A, B, bias, R = _rand((M, K), cuda_dev), _rand((N, K), cuda_dev, 0.02), _rand((N,), cuda_dev), _rand((M, N), cuda_dev)
+    D = torch.zeros(M, N, dtype=torch.bfloat16, device=cuda_dev)
+    rng = _rng_state(cuda_dev)
+    _call(M, N, K, A, K, L.MAJOR_K, B, K, L.MAJOR_K, D, L.EPI_BIAS_DROPOUT_RESIDUAL, bias=bias, aux_in=R, p=p,
+          rng=rng, site=9)
+    y = A.float() @ B.float().t() + bias.float()
+    if p > 0:
+        keep = torch.from_numpy(philox_keep_mask(M * N, 77, 3, 9, p).reshape(M, N)).to(cuda_dev)
+        assert abs(keep.float().mean().item() - (1 - p)) < 5e-3
+        y = y * keep / (1 - p)
+    _check(D, y + R.float())
+
+
+def test_residual_and_gelu_bwd(cuda_dev):
+    M, N, K = 384, 768, 768
+    torch.manual_seed(6)
+    A, B, R = _rand((M, K), cuda_dev), _rand((K, N), cuda_dev, 0.05), _rand((M, N), cuda_dev)
+    D = torch.zeros(M, N, dtype=torch.bfloat16, device=cuda_dev)
+    _call(M, N, K, A, K, L.MAJOR_K, B, N, L.MAJOR_MN, D, L.EPI_RESIDUAL, aux_in=R)
+    _check(D, A.float() @ B.float() + R.float())
+    U = _rand((M, N), cuda_dev)
+    _call(M, N, K, A, K, L.MAJOR_K, B, N, L.MAJOR_MN, D, L.EPI_GELU_BWD, aux_in=U)
+    u = U.float().requires_grad_(True)
+    torch.nn.functional.gelu(u).sum().backward()
+    _check(D, (A.float() @ B.float()) * u.grad)
+
+
+def test_linearity_full_size(cuda_dev):
+    """size-independent property at the benchmark shape: GEMM(a1 + a2) == GEMM(a1) + GEMM(a2) within bf16 rounding."""
+    M, N, K = 4096, 3072, 768
+    torch.manual_seed(7)
+    A1, A2, B = _rand((M, K), cuda_dev), _rand((M, K), cuda_dev), _rand((N, K), cuda_dev, 0.05)
+    D1, D2, D3 = (torch.zeros(M, N, dtype=torch.bfloat16, device=cuda_dev) for _ in range(3))
+    _call(M, N, K, A1, K, L.MAJOR_K, B, K, L.MAJOR_K, D1)
+    _call(M, N, K, A2, K, L.MAJOR_K, B, K, L.MAJOR_K, D2)
+    A3 = (A1.float() + A2.float()).to(torch.bfloat16)
+    _call(M, N, K, A3, K, L.MAJOR_K, B, K, L.MAJOR_K, D3)
+    _check(D3, A3.float() @ B.float().t())
+    _check(D3, D1.float() + D2.float(), tol=3e-2)
+
+
+def test_errors(cuda_dev):
+    A = _rand((128, 64), cuda_dev)
+    D = torch.zeros(128, 64, dtype=torch.bfloat16, device=cuda_dev)
+    a = L.GemmArgs()
+    a.M, a.N, a.K = 0, 64, 64
+    a.A, a.B, a.D = A.data_ptr(), A.data_ptr(), D.data_ptr()
+    with pytest.raises(RuntimeError, match="empty problem"):
+        L.call("b2_gemm_bf16", a, None)
+    a.M, a.N, a.K = 128, 60, 64
+    a.lda = a.ldb = a.ldd = 64
+    with pytest.raises(RuntimeError, match="multiple of 32"):
+        L.call("b2_gemm_bf16", a, None)

@@ -1,0 +1,136 @@
+"""CPU: the C-ABI library loads and exports what include/b2_ddp_bert.h declares; host-side logic of the drop-in layer
+(parameter naming/layout, optimizer grouping, bucket slicing, error behaviour without a GPU)."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+from parity import b2, tiny_config, full_config
+from pytorch_distributed_nlp_b200 import _lib as L
+from pytorch_distributed_nlp_b200.modeling import _Layout, _hf_order
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    lib = L.load()
+    assert lib.b2_abi_version() == L.ABI_VERSION
+    hdr = open(os.path.join(ROOT, "include", "b2_ddp_bert.h")).read()
+    declared = set(re.findall(r"\b(b2_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "no declarations parsed"
+    raw = ctypes.CDLL(L.LIB_PATH)
+    for sym in sorted(declared):
+        assert hasattr(raw, sym), "library does not export %s" % sym
+    assert declared == set(L.EXPORTED_SYMBOLS), declared ^ set(L.EXPORTED_SYMBOLS)
+
+
+def test_error_convention_without_gpu():
+    a = L.GemmArgs()
+    with pytest.raises(RuntimeError, match="empty problem"):
+        L.call("b2_gemm_bf16", a, None)
+    assert "empty problem" in L.last_error()
+
+
+def test_no_cpu_fallback():
+    model = b2.BertForSequenceClassification(tiny_config())
+    ids = torch.zeros(2, 128, dtype=torch.int64)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        model(input_ids=ids)
+
+
+def test_parameter_names_order_and_count_match_hf():
+    from oracle import cpu_step
+    cfg = full_config()
+    names = _hf_order(cfg)
+    assert len(names) == 201
+    lay = _Layout(cfg)
+    assert set(lay.entries) == set(names)
+    n_params = sum(int(torch.tensor(s).prod()) for _, s in lay.entries.values())
+    assert n_params == 102_272_262
+    assert lay.total % 8 == 0 and all(off % 8 == 0 for off, _ in lay.entries.values())
+    assert len(lay.buckets) == 14                       # embeddings | 12 layers | head
+    assert lay.buckets[0][0] == 0 and lay.buckets[-1][1] == lay.total
+    for (b0, e0, _), (b1, _e1, _) in zip(lay.buckets, lay.buckets[1:]):
+        assert e0 == b1
+    tcfg = tiny_config()
+    m = b2.BertForSequenceClassification(tcfg)
+    hf = cpu_step.build_hf_model(tcfg)
+    assert [n for n, _ in m.named_parameters()] == [n for n, _ in hf.named_parameters()]
+    for (n, p), (_, q) in zip(m.named_parameters(), hf.named_parameters()):
+        assert tuple(p.shape) == tuple(q.shape), n
+    # Q/K/V are adjacent in the flat space so one [3H, H] GEMM serves them
+    q, k, v = (lay.off("bert.encoder.layer.3.attention.self.%s.weight" % t) for t in ("query", "key", "value"))
+    H = cfg.hidden_size
+    assert k - q == H * H and v - k == H * H
+
+
+def test_parameters_are_views_of_one_flat_buffer_and_init_is_hf_like():
+    torch.manual_seed(0)
+    cfg = tiny_config()
+    m = b2.BertForSequenceClassification(cfg)
+    base = m._flat.data_ptr()
+    for n, p in m.named_parameters():
+        off, _ = m._layout.entries[n]
+        assert p.data_ptr() == base + 4 * off
+    sd = m.state_dict()
+    assert float(sd["bert.embeddings.word_embeddings.weight"][0].abs().max()) == 0.0      # pad row
+    assert float(sd["bert.embeddings.LayerNorm.weight"].min()) == 1.0
+    assert float(sd["classifier.bias"].abs().max()) == 0.0
+    std = float(sd["bert.encoder.layer.0.intermediate.dense.weight"].std())
+    assert 0.018 < std < 0.022
+    with pytest.raises(RuntimeError, match="size mismatch"):
+        m.load_state_dict({**sd, "classifier.weight": torch.zeros(3, 3)})
+    with pytest.raises(RuntimeError, match="missing"):
+        m.load_state_dict({})
+
+
+def test_build_optimizer_grouping_matches_reference_rule():
+    class A:
+        weight_decay, learning_rate = 0.01, 3e-5
+    cfg = tiny_config()
+    m = b2.BertForSequenceClassification(cfg)
+    opt = b2.build_optimizer(m, A)
+    assert len(opt.param_groups) == 2
+    decay_names = {p._b2_name for p in opt.param_groups[0]["params"]}
+    nodecay_names = {p._b2_name for p in opt.param_groups[1]["params"]}
+    assert all(("bias" not in n and "LayerNorm.weight" not in n) for n in decay_names)
+    assert all(("bias" in n or "LayerNorm.weight" in n) for n in nodecay_names)
+    assert opt.param_groups[0]["eps"] == 1e-6 and opt.param_groups[0]["betas"] == (0.9, 0.999)
+    flags = opt._decay_flags_cpu
+    for n, (off, shape) in m._layout.entries.items():
+        want = 1 if n in decay_names else 0
+        assert int(flags[off // 8]) == want, n
+    with pytest.raises(ValueError, match="every parameter"):
+        b2.AdamW([m._params_by_name["classifier.weight"]], lr=1e-3)
+    with pytest.raises(TypeError, match="b200"):
+        b2.AdamW([torch.nn.Parameter(torch.zeros(3))], lr=1e-3)
+    with pytest.raises(RuntimeError, match="not on CUDA"):
+        opt.step()
+
+
+def test_bucket_slices_partition_every_bucket():
+    """the per-rank slices the DDP wrapper hands to b2_bucket_reduce_adamw tile each bucket exactly, 8-aligned"""
+    from pytorch_distributed_nlp_b200.ddp import DistributedDataParallel as D
+    lay = _Layout(full_config())
+    for world in (2, 4, 8):
+        for (b, e, _label) in lay.buckets:
+            covered = 0
+            prev = b
+            for r in range(world):
+                fake = type("F", (), {})()
+                fake.module = type("M", (), {"_layout": type("L", (), {"buckets": [(b, e, "x")]})()})()
+                fake.world, fake.rank = world, r
+                (sb, se), = D._make_slices(fake)
+                assert sb % 8 == 0 and se % 8 == 0 and sb == prev and se >= sb
+                covered += se - sb
+                prev = se
+            assert covered == e - b and prev == e
+
+
+def test_output_object_indexing():
+    o = b2.SequenceClassifierOutput(loss=torch.tensor(1.0), logits=torch.zeros(2, 6))
+    assert o[0] is o.loss and o[1] is o.logits and len(o) == 2 and o["logits"] is o.logits
+    o2 = b2.SequenceClassifierOutput(logits=torch.zeros(2, 6))
+    assert o2[0] is o2.logits and len(o2) == 1

@@ -1,0 +1,174 @@
+"""Whole-step parity of the CUDA path (through the reference-facing Python surface) against the fp32 oracle (GPU)."""
+import os
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from parity import (TOL_GRAD_REL, TOL_LOGITS, TOL_LOSS, TOL_TRAJ, adamw_ref, b2, bert_ref, full_config, grad_report,
+                    make_model, oracle_masks, state_from_hf_init, tiny_config, to_dev)
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _fwd_bwd(model, batch, dev):
+    d = to_dev(batch, dev)
+    out = model(input_ids=d["input_ids"], token_type_ids=d["token_type_ids"], attention_mask=d["attention_mask"],
+                labels=d["label"])
+    loss = F.cross_entropy(out[1], d["label"])      # the reference's criterion(logits, label) [:169]
+    loss.backward()
+    torch.cuda.synchronize()
+    return out, loss
+
+
+@pytest.mark.parametrize("padded", [False, True])
+@pytest.mark.parametrize("dropout", [False, True])
+def test_tiny_step_matches_oracle(cuda_dev, padded, dropout):
+    cfg = tiny_config() if dropout else tiny_config(hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0)
+    state = state_from_hf_init(cfg)
+    model = make_model(cfg, state, cuda_dev).train()
+    model._engine.seed_dropout(99, 7)
+    batch = bert_ref.synthetic_batch(cfg, 4, 128, 1000, padded=padded)
+    out, loss = _fwd_bwd(model, batch, cuda_dev)
+    masks = oracle_masks(cfg, 4, 128, 99, 7) if dropout else None
+    rl, rz, rg = bert_ref.loss_and_grads(state, cfg, batch, masks=masks)
+    assert abs(float(loss) - float(rl)) <= TOL_LOSS
+    assert abs(float(out[0]) - float(rl)) <= TOL_LOSS            # HF's in-model loss == criterion loss
+    assert float((out[1].detach().cpu() - rz).abs().max()) <= TOL_LOGITS
+    worst, rows = grad_report(model.grad_dict(), rg)
+    assert worst <= TOL_GRAD_REL, sorted(rows, key=lambda r: -r[1])[:5]
+
+
+def test_eval_forward_and_output_surface(cuda_dev):
+    cfg = tiny_config()
+    state = state_from_hf_init(cfg)
+    model = make_model(cfg, state, cuda_dev).eval()
+    batch = bert_ref.synthetic_batch(cfg, 4, 128, 5, padded=True)
+    d = to_dev(batch, cuda_dev)
+    with torch.no_grad():
+        out = model(input_ids=d["input_ids"], token_type_ids=d["token_type_ids"], attention_mask=d["attention_mask"],
+                    labels=d["label"])
+        out2 = model(input_ids=d["input_ids"], attention_mask=d["attention_mask"])
+    rl, rz = bert_ref.forward(state, cfg, batch["input_ids"], batch["token_type_ids"], batch["attention_mask"],
+                              batch["label"])
+    assert len(out) == 2 and out[1] is out.logits and out[0] is out.loss
+    assert len(out2) == 1 and out2[0] is out2.logits
+    assert float((out.logits.cpu() - rz).abs().max()) <= TOL_LOGITS
+    assert abs(float(out.loss) - float(rl)) <= TOL_LOSS
+    assert float((out2.logits - out.logits).abs().max()) == 0.0   # token_type_ids=None == zeros
+    with pytest.raises(ValueError, match="multiples of 128"):
+        model(input_ids=d["input_ids"][:, :100])
+    with pytest.raises(TypeError, match="int64"):
+        model(input_ids=d["input_ids"].int())
+
+
+def test_tiny_trajectory_eager_and_fused(cuda_dev):
+    """5 optimizer steps (dropout off): reference-style eager loop, the fused CUDA-graph step, and the oracle agree."""
+    cfg = tiny_config(hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0)
+    state = state_from_hf_init(cfg)
+    batches = [bert_ref.synthetic_batch(cfg, 4, 128, 2000 + i, padded=(i % 2 == 1)) for i in range(5)]
+
+    class A:
+        weight_decay, learning_rate = 0.01, 3e-5
+
+    ref_params = {k: v.clone() for k, v in state.items()}
+    hist = __import__("oracle.ddp_ref", fromlist=["train"]).train(ref_params, cfg, [[b] for b in batches])
+
+    # eager, reference-shaped loop
+    model = make_model(cfg, state, cuda_dev).train()
+    opt = b2.build_optimizer(model, A)
+    losses = []
+    for b in batches:
+        d = to_dev(b, cuda_dev)
+        out = model(input_ids=d["input_ids"], token_type_ids=d["token_type_ids"],
+                    attention_mask=d["attention_mask"], labels=d["label"])
+        loss = F.cross_entropy(out[1], d["label"])
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        losses.append(float(loss))
+    for i, h in enumerate(hist):
+        assert abs(losses[i] - float(h["loss_mean"])) <= TOL_TRAJ, (i, losses[i], float(h["loss_mean"]))
+    sd = model.state_dict()
+    for k, v in ref_params.items():
+        assert float((sd[k].cpu() - v).abs().max()) <= 2e-4, k      # lr 3e-5 * 5 steps bounds any drift
+
+    # fused CUDA-graph step
+    model2 = make_model(cfg, state, cuda_dev).train()
+    opt2 = b2.build_optimizer(model2, A)
+    step = b2.FusedTrainStep(model2, opt2, 4, 128)
+    losses2 = []
+    for b in batches:
+        step(b)
+        losses2.append(step.loss_to_host())
+    assert step.graph is not None
+    for a, c in zip(losses, losses2):
+        assert abs(a - c) <= 1e-5, (losses, losses2)
+    sd2 = model2.state_dict()
+    for k in sd:   # same kernels, same order; only d(loss)/d(logits) comes from torch in one case, our CE kernel in the other
+        assert float((sd[k].double() - sd2[k].double()).abs().max()) <= 1e-6, k
+
+
+def test_state_dict_round_trip_and_hf_loadable(cuda_dev):
+    cfg = tiny_config()
+    state = state_from_hf_init(cfg)
+    model = make_model(cfg, state, cuda_dev)
+    sd = model.state_dict()
+    assert "bert.embeddings.position_ids" in sd
+    for k, v in state.items():
+        assert torch.equal(sd[k].cpu(), v)
+    from oracle import cpu_step
+    hf = cpu_step.build_hf_model(cfg, seed=1)
+    res = hf.load_state_dict({k: v.cpu() for k, v in sd.items()}, strict=False)
+    assert not res.missing_keys
+    wrapped = {"module." + k: v for k, v in sd.items()}          # what the reference's DDP checkpoints look like
+    stripped = {k[len("module."):]: v for k, v in wrapped.items()}
+    model.load_state_dict(stripped)
+
+
+def test_full_config_step_matches_golden(cuda_dev):
+    """BASELINE config A (chinese-bert-wwm-ext, B=32, S=128), dropout off: loss / logits / per-tensor gradient norms
+    against the fixture produced by tests/golden/make_golden.py from HF transformers on CPU."""
+    path = os.path.join(GOLD, "config_a_step0.pt")
+    gold = torch.load(path)
+    cfg = full_config(hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0)
+    state = state_from_hf_init(cfg)
+    chk = float(sum(v.double().sum() for v in state.values()))
+    assert abs(chk - gold["init_checksum"]) <= 1e-6 * max(1.0, abs(gold["init_checksum"])), \
+        "HF init under seed 123 differs from the fixture's"
+    model = make_model(cfg, state, cuda_dev).train()
+    batch = bert_ref.synthetic_batch(cfg, 32, 128, 1000, padded=True)
+    assert torch.equal(batch["input_ids"], gold["input_ids"])
+    out, loss = _fwd_bwd(model, batch, cuda_dev)
+    assert abs(float(loss) - gold["loss"]) <= TOL_LOSS
+    assert float((out[1].detach().cpu() - gold["logits"]).abs().max()) <= TOL_LOGITS
+    g = model.grad_dict()
+    scale = max(gold["grad_norms"].values())
+    for k, n in gold["grad_norms"].items():
+        got = float(g[k].double().norm())
+        assert abs(got - n) <= TOL_GRAD_REL * max(n, 1e-3 * scale), (k, got, n)
+    for k, ref in gold["grad_samples"].items():
+        got = g[k].flatten()[: ref.numel()].cpu()
+        assert float((got - ref).norm()) <= TOL_GRAD_REL * max(float(ref.norm()), 1e-3 * scale), k
+
+
+def test_dropout_statistics_and_determinism(cuda_dev):
+    """p=0.1 training forward: keep-rate 0.9 +- 0.002, same (seed, step) -> same output,
+    next step -> different mask."""
+    from parity import philox_keep_mask
+    keep = philox_keep_mask(8 * 1_000_000, 123, 0, 5, 0.1)
+    assert abs(keep.mean() - 0.9) < 2e-3
+    cfg = tiny_config()
+    state = state_from_hf_init(cfg)
+    model = make_model(cfg, state, cuda_dev).train()
+    d = to_dev(bert_ref.synthetic_batch(cfg, 4, 128, 1, padded=False), cuda_dev)
+
+    def run(step):
+        model._engine.seed_dropout(5, step)
+        with torch.no_grad():
+            return model(input_ids=d["input_ids"], attention_mask=d["attention_mask"]).logits.clone()
+
+    a, b, c = run(0), run(0), run(1)
+    assert torch.equal(a, b)
+    assert not torch.equal(a, c)
