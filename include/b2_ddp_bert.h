@@ -29,6 +29,7 @@ extern "C" {
 const char* b2_last_error(void);
 int32_t b2_abi_version(void);             /* bumped when a struct below changes */
 #define B2_ABI_VERSION 1
+int64_t b2_launch_count(void);            /* kernels launched by this library so far (process-wide) */
 
 /* ------------------------------------------------------------------------------------------------------ */
 /* GEMM (tcgen05 + TMA)                                                                                   */

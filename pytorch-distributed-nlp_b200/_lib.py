@@ -67,7 +67,7 @@ _SIGNATURES = {
     "b2_allgather_rows": [vp, i64, C.POINTER(vp), C.POINTER(vp), i32, i32, i32, vp, vp],
     "b2_scalar_allreduce_mean": [vp, vp, C.POINTER(vp), C.POINTER(vp), i32, i32, i32, vp, vp],
 }
-EXPORTED_SYMBOLS = sorted(list(_SIGNATURES) + ["b2_last_error", "b2_abi_version"])
+EXPORTED_SYMBOLS = sorted(list(_SIGNATURES) + ["b2_last_error", "b2_abi_version", "b2_launch_count"])
 
 _lib = None
 
@@ -86,6 +86,8 @@ def load():
     lib.b2_last_error.argtypes = []
     lib.b2_abi_version.restype = i32
     lib.b2_abi_version.argtypes = []
+    lib.b2_launch_count.restype = i64
+    lib.b2_launch_count.argtypes = []
     if lib.b2_abi_version() != ABI_VERSION:
         raise RuntimeError("libb2ddpbert.so ABI %d != expected %d: rebuild" % (lib.b2_abi_version(), ABI_VERSION))
     for name, argtypes in _SIGNATURES.items():
@@ -94,6 +96,10 @@ def load():
         fn.argtypes = argtypes
     _lib = lib
     return lib
+
+
+def launch_count():
+    return int(load().b2_launch_count())
 
 
 def last_error():

@@ -5,12 +5,15 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <atomic>
 #include <mutex>
 #include <unordered_map>
 
 namespace b2 {
 
 static thread_local char g_err[1024] = "";
+static std::atomic<long long> g_launches{0};
+void count_launches(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -97,3 +100,4 @@ int32_t get_tensor_map_2d(CUtensorMap* out, const void* base, uint64_t rows, uin
 
 extern "C" const char* b2_last_error(void) { return b2::g_err; }
 extern "C" int32_t b2_abi_version(void) { return B2_ABI_VERSION; }
+extern "C" int64_t b2_launch_count(void) { return (int64_t)b2::g_launches.load(std::memory_order_relaxed); }

@@ -484,6 +484,7 @@ extern "C" int32_t b2_attention_fwd(const void* qkv, const int64_t* attention_ma
   dim3 grid((unsigned)(seq / 128), (unsigned)heads, (unsigned)batch);
   attention_fwd_kernel<<<grid, ATT_THREADS, kFwdSmem, stream>>>(tm, p);
   B2_CUDA(cudaGetLastError());
+  count_launches(1);
   return 0;
 }
 
@@ -521,11 +522,13 @@ extern "C" int32_t b2_attention_bwd(const void* qkv, const int64_t* attention_ma
   dim3 grid((unsigned)(seq / 128), (unsigned)heads, (unsigned)batch);
   attention_bwd_kernel<<<grid, ATT_THREADS, kBwdSmem, stream>>>(tm_qkv, tm_do, p);
   B2_CUDA(cudaGetLastError());
+  count_launches(1);
   if (p.dq_accum) {
     const long long n4 = tokens * hidden / 4;
     dq_convert_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, stream>>>(p.dq_accum, (__nv_bfloat16*)d_qkv, tokens,
                                                                         (int)hidden);
     B2_CUDA(cudaGetLastError());
+  count_launches(1);
   }
   return 0;
 }

@@ -155,6 +155,7 @@ extern "C" int32_t b2_peer_barrier(void* const* peer_flags, int32_t world, int32
   if (st) return st;
   peer_barrier_kernel<<<1, 32, 0, (cudaStream_t)stream_>>>(f, world, rank, slot, epoch);
   B2_CUDA(cudaGetLastError());
+  count_launches(1);
   return 0;
 }
 
@@ -174,6 +175,7 @@ extern "C" int32_t b2_allgather_rows(const void* src, int64_t bytes, void* const
   allgather_rows_kernel<<<1, 256, 0, (cudaStream_t)stream_>>>((const uint32_t*)src, bytes / 4, d, f, world, rank, slot,
                                                               epoch);
   B2_CUDA(cudaGetLastError());
+  count_launches(1);
   return 0;
 }
 
@@ -191,5 +193,6 @@ extern "C" int32_t b2_scalar_allreduce_mean(const float* src, float* dst, float*
   if (st) return st;
   scalar_allreduce_mean_kernel<<<1, 32, 0, (cudaStream_t)stream_>>>(src, dst, s, f, world, rank, slot, epoch);
   B2_CUDA(cudaGetLastError());
+  count_launches(1);
   return 0;
 }

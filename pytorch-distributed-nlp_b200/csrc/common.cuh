@@ -19,6 +19,7 @@ namespace b2 {
 // ----------------------------------------------------------------------------------------------
 void set_error(const char* fmt, ...);
 int32_t check_cuda(cudaError_t e, const char* what);
+void count_launches(int n);  // kernels launched by this library (bench.py reports them as gpu_launches)
 #define B2_CUDA(expr)                                                   \
   do {                                                                  \
     int32_t _s = ::b2::check_cuda((expr), #expr);                       \

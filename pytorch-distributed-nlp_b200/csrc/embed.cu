@@ -166,6 +166,7 @@ extern "C" int32_t b2_embed_fwd(const int64_t* input_ids, const int64_t* token_t
   switch ((int)(hidden / 256)) { B2_EMB(1) B2_EMB(2) B2_EMB(3) B2_EMB(4) }
 #undef B2_EMB
   B2_CUDA(cudaGetLastError());
+  count_launches(1);
   return 0;
 }
 
@@ -191,14 +192,17 @@ extern "C" int32_t b2_embed_bwd(const void* dy, const void* pre_ln, const float*
   // 2. word rows (d_word pre-zeroed by the caller)
   embed_owner_kernel<<<(tokens + 255) / 256, 256, 0, stream>>>(ids32, tokens, (int)pad_token_id, owner);
   B2_CUDA(cudaGetLastError());
+  count_launches(1);
   embed_word_scatter_kernel<<<tokens, 128, 0, stream>>>((const __nv_bfloat16*)scratch_dx, ids32, tokens, (int)hidden,
                                                         (int)pad_token_id, owner, (__nv_bfloat16*)d_word);
   B2_CUDA(cudaGetLastError());
+  count_launches(1);
   // 3. position rows: the table has `max_pos` rows but only the first `seq` receive gradient; the caller passes
   //    d_pos sized [seq rows used]; rows beyond are zeroed by the caller's bucket memset
   embed_pos_kernel<<<(unsigned)seq, (unsigned)(hidden / 8), 0, stream>>>((const __nv_bfloat16*)scratch_dx, (int)batch,
                                                                          (int)seq, (int)hidden, (__nv_bfloat16*)d_pos);
   B2_CUDA(cudaGetLastError());
+  count_launches(1);
   // 4. token-type rows
   for (int ty = 0; ty < (int)type_vocab; ++ty) {
     st = launch_colsum(scratch_dx, tokens, hidden, hidden, tt32, ty, (__nv_bfloat16*)d_type + (size_t)ty * hidden,
@@ -213,5 +217,6 @@ extern "C" int32_t b2_embed_owner_init(int32_t* owner, int64_t vocab, void* stre
   B2_REQUIRE(owner && vocab > 0, "embed_owner_init: bad args");
   fill_int_kernel<<<(unsigned)((vocab + 255) / 256), 256, 0, (cudaStream_t)stream_>>>(owner, (int)vocab, INT_MAX);
   B2_CUDA(cudaGetLastError());
+  count_launches(1);
   return 0;
 }

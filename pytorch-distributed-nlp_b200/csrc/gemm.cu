@@ -337,11 +337,13 @@ static int32_t launch_gemm(const b2_gemm_args_t& a, int splits, cudaStream_t str
   const int grid = work < num_sms() ? work : num_sms();
   kern<<<grid, GEMM_THREADS, Cfg::kSmemBytes, stream>>>(ta, tb, p);
   B2_CUDA(cudaGetLastError());
+  count_launches(1);
   if (splits > 1) {
     const long long total = (long long)p.M * p.N / 4;
     splitk_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(
         (const float*)a.workspace, (__nv_bfloat16*)a.D, a.ldd, p.M, p.N, splits);
     B2_CUDA(cudaGetLastError());
+  count_launches(1);
   }
   return 0;
 }

@@ -186,10 +186,12 @@ extern "C" int32_t b2_head_fwd(const void* hidden_states, int64_t batch, int64_t
       (const __nv_bfloat16*)hidden_states, (int)batch, (int)seq, (int)hidden, (const __nv_bfloat16*)pool_w,
       (const __nv_bfloat16*)pool_b, (__nv_bfloat16*)pooled);
   B2_CUDA(cudaGetLastError());
+  count_launches(1);
   classifier_fwd_kernel<<<(unsigned)((batch * num_labels + 7) / 8), 256, 0, stream>>>(
       (const __nv_bfloat16*)pooled, (int)batch, (int)hidden, (const __nv_bfloat16*)cls_w, (const __nv_bfloat16*)cls_b,
       (int)num_labels, dropout_p, (const unsigned long long*)rng_state, rng_site, logits);
   B2_CUDA(cudaGetLastError());
+  count_launches(1);
   return 0;
 }
 
@@ -200,6 +202,7 @@ extern "C" int32_t b2_ce_fwd_bwd(const float* logits, const int64_t* labels, int
   ce_fwd_bwd_kernel<<<1, 256, 0, (cudaStream_t)stream_>>>(logits, (const long long*)labels, (int)batch,
                                                           (int)num_labels, loss, dlogits);
   B2_CUDA(cudaGetLastError());
+  count_launches(1);
   return 0;
 }
 
@@ -221,12 +224,15 @@ extern "C" int32_t b2_head_bwd(const float* dlogits, const void* hidden_states, 
       dropout_p, (const unsigned long long*)rng_state, rng_site, scratch, (__nv_bfloat16*)d_cls_w,
       (__nv_bfloat16*)d_cls_b);
   B2_CUDA(cudaGetLastError());
+  count_launches(1);
   head_bwd_k2<<<(unsigned)hidden, (unsigned)(hidden / 8), 0, stream>>>(
       scratch, (const __nv_bfloat16*)hidden_states, (int)batch, (int)seq, (int)hidden, (__nv_bfloat16*)d_pool_w,
       (__nv_bfloat16*)d_pool_b);
   B2_CUDA(cudaGetLastError());
+  count_launches(1);
   head_bwd_k3<<<(unsigned)batch, (unsigned)(hidden / 8), 0, stream>>>(scratch, (const __nv_bfloat16*)pool_w, (int)seq,
                                                                       (int)hidden, (__nv_bfloat16*)d_hidden);
   B2_CUDA(cudaGetLastError());
+  count_launches(1);
   return 0;
 }

@@ -179,9 +179,11 @@ int32_t launch_colsum(const void* x, int64_t rows, int64_t cols, int64_t ldx, co
   colsum_partial_kernel<<<grid, 256, 0, stream>>>((const __nv_bfloat16*)x, (int)rows, (int)cols, ldx, filter,
                                                   filter_value, scratch);
   B2_CUDA(cudaGetLastError());
+  count_launches(1);
   colsum_finish_kernel<<<(unsigned)((cols + 255) / 256), 256, 0, stream>>>(scratch, nparts, 1, (int)cols,
                                                                            (__nv_bfloat16*)out, nullptr, nullptr);
   B2_CUDA(cudaGetLastError());
+  count_launches(1);
   return 0;
 }
 
@@ -209,9 +211,11 @@ int32_t launch_layernorm_bwd(const void* dy, const void* dy_add, const void* x, 
   }
 #undef B2_LN_BWD
   B2_CUDA(cudaGetLastError());
+  count_launches(1);
   colsum_finish_kernel<<<(unsigned)((3 * hidden + 255) / 256), 256, 0, stream>>>(
       scratch, nblocks, 3, (int)hidden, (__nv_bfloat16*)d_gamma, (__nv_bfloat16*)d_beta, (__nv_bfloat16*)d_bias);
   B2_CUDA(cudaGetLastError());
+  count_launches(1);
   return 0;
 }
 
@@ -238,6 +242,7 @@ extern "C" int32_t b2_layernorm_fwd(const void* x, const void* gamma, const void
   }
 #undef B2_LN_FWD
   B2_CUDA(cudaGetLastError());
+  count_launches(1);
   return 0;
 }
 

@@ -150,12 +150,14 @@ extern "C" int32_t b2_bucket_reduce_adamw(const void* const* peer_grads, void* c
   if (blocks > cap) blocks = cap;
   reduce_adamw_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream_>>>(p);
   B2_CUDA(cudaGetLastError());
+  count_launches(1);
   return 0;
 }
 
 extern "C" int32_t b2_step_advance(int64_t* step_counter, void* rng_state, void* stream_) {
   step_advance_kernel<<<1, 32, 0, (cudaStream_t)stream_>>>((long long*)step_counter, (unsigned long long*)rng_state);
   B2_CUDA(cudaGetLastError());
+  count_launches(1);
   return 0;
 }
 
@@ -163,6 +165,7 @@ extern "C" int32_t b2_rng_seed(void* rng_state, uint64_t seed, uint64_t step, vo
   B2_REQUIRE(rng_state, "rng_seed: null pointer");
   rng_seed_kernel<<<1, 32, 0, (cudaStream_t)stream_>>>((unsigned long long*)rng_state, seed, step);
   B2_CUDA(cudaGetLastError());
+  count_launches(1);
   return 0;
 }
 
@@ -173,6 +176,7 @@ extern "C" int32_t b2_cast_f32_to_bf16(const float* src, void* dst, int64_t n, v
   const long long nv = (n + 7) / 8;
   cast_f32_bf16_kernel<<<(unsigned)((nv + 255) / 256), 256, 0, (cudaStream_t)stream_>>>(src, (__nv_bfloat16*)dst, n);
   B2_CUDA(cudaGetLastError());
+  count_launches(1);
   return 0;
 }
 
@@ -182,6 +186,7 @@ extern "C" int32_t b2_cast_bf16_to_f32(const void* src, float* dst, int64_t n, v
   cast_bf16_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream_>>>((const __nv_bfloat16*)src, dst,
                                                                                        n);
   B2_CUDA(cudaGetLastError());
+  count_launches(1);
   return 0;
 }
 
