@@ -1,0 +1,90 @@
+"""Run under torchrun (one rank per GPU): the peer-HBM DDP path vs the oracle's DDP restatement.
+Exits non-zero on any mismatch.  Used by tests/test_ddp.py and by hand: 
+    python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29555 tests/ddp_worker.py
+"""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import torch
+import torch.distributed as dist
+import torch.nn.functional as F
+
+from parity import TOL_TRAJ, b2, bert_ref, state_from_hf_init, tiny_config
+from oracle import ddp_ref
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    cfg = tiny_config(hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0)
+    state = state_from_hf_init(cfg, seed=123)
+    steps = 6
+    batches = [[bert_ref.synthetic_batch(cfg, 4, 128, 7000 + 10 * s + r, padded=(s % 2 == 1)) for r in range(world)]
+               for s in range(steps)]
+    ref = {k: v.clone() for k, v in state.items()}
+    hist = ddp_ref.train(ref, cfg, batches)
+
+    class A:
+        weight_decay, learning_rate = 0.01, 3e-5
+
+    for mode in ("eager", "fused"):
+        # every rank but 0 starts from different weights: the wrap-time broadcast must make rank 0 win
+        init = state if rank == 0 else state_from_hf_init(cfg, seed=999)
+        model = b2.BertForSequenceClassification(cfg)
+        model.load_state_dict(init)
+        model.cuda()
+        ddp = b2.DistributedDataParallel(model, device_ids=[local])
+        opt = b2.build_optimizer(ddp, A)
+        assert [n for n, _ in ddp.named_parameters()][0].startswith("module.")
+        fused = b2.FusedTrainStep(ddp, opt, 4, 128) if mode == "fused" else None
+        for s in range(steps):
+            b = batches[s][rank]
+            if fused is not None:
+                loss = fused(b)
+            else:
+                d = {k: v.to(dev) for k, v in b.items()}
+                out = ddp(input_ids=d["input_ids"], token_type_ids=d["token_type_ids"],
+                          attention_mask=d["attention_mask"], labels=d["label"])
+                loss = F.cross_entropy(out[1], d["label"])
+                opt.zero_grad()
+                loss.backward()
+                opt.step()
+            red = ddp.loss_reduce(loss)
+            lv, rv = float(loss), float(red)
+            assert abs(lv - float(hist[s]["loss_per_rank"][rank])) <= TOL_TRAJ, (mode, s, rank, lv)
+            assert abs(rv - float(hist[s]["loss_mean"])) <= TOL_TRAJ, (mode, s, rank, rv)
+        sd = ddp.state_dict()
+        assert all(k.startswith("module.") for k in sd)
+        for k, v in ref.items():
+            err = float((sd["module." + k].cpu() - v).abs().max())
+            assert err <= 2e-4, (mode, k, err)
+        # every rank holds identical bf16 weights after the exchange
+        chk = model._engine.shadow.float().sum().reshape(1)
+        allc = [torch.zeros_like(chk) for _ in range(world)]
+        dist.all_gather(allc, chk)
+        assert all(float(c) == float(allc[0]) for c in allc), allc
+        # eval-time gather (Trainer.output_reduce)
+        t = torch.full((4, 6), float(rank), device=dev)
+        g = ddp.all_gather_rows(t)
+        assert g.shape == (4 * world, 6)
+        for r in range(world):
+            assert float(g[4 * r:4 * r + 4].mean()) == float(r)
+        lab = torch.arange(4, device=dev) + 100 * rank
+        gl = ddp.all_gather_rows(lab)
+        assert gl.tolist() == [i + 100 * r for r in range(world) for i in range(4)]
+        torch.cuda.synchronize()
+        dist.barrier()
+        if rank == 0:
+            print("ddp_worker: mode %s OK (world %d)" % (mode, world), flush=True)
+        del fused, opt, ddp, model
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
