@@ -107,7 +107,7 @@ def run_reference(args):
     import pytorch_distributed_nlp_b200 as b2
     from oracle import cpu_step
     cfg = b2.chinese_bert_wwm_ext_config(num_labels=6)
-    cores = os.cpu_count() or 1
+    cores = cpu_step.usable_cores()
     # a full B=32 step costs seconds of CPU; bound the sample so K + W steps stay within a few minutes
     probe = cpu_step.time_steps(cfg, 8, SEQ, steps=1, warmup=1, threads=cores)
     per_sample = probe["ms_per_step"] / 8 / 1e3
@@ -182,14 +182,23 @@ def time_gemm_family(eng, cfg, B, S, peaks):
         for s in sets:
             launch(s)
         torch.cuda.synchronize(dev)
+        # the launches go through Python/ctypes (~10 us of host time each): capture the loop once so that the events
+        # bracket device time, not host launch latency
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for _ in range(REP):
+                for s in sets:
+                    launch(s)
+        g.replay()
+        torch.cuda.synchronize(dev)
+        stream = torch.cuda.current_stream(dev)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
-        for _ in range(REP):
-            for s in sets:
-                launch(s)
+        g.replay()
         e1.record(stream)
         torch.cuda.synchronize(dev)
         ms = e0.elapsed_time(e1) / (REP * NSET)
+        del g
         flops = 2.0 * m * n * k
         detail.append({"gemm": name, "us": round(ms * 1e3, 2), "tflops": round(flops / ms / 1e9, 1)})
         tot_flops += flops
@@ -310,7 +319,7 @@ def run_b200(args):
         cpu = None
         if world == 1:
             from oracle import cpu_step
-            cores = os.cpu_count() or 1
+            cores = cpu_step.usable_cores()
             r = cpu_step.time_steps(cfg, 16, SEQ, steps=2, warmup=1, threads=cores)
             cpu = {"value": round(r["samples_per_s"], 3), "unit": "samples/s", "cores": cores, "kind": "port",
                    "sample": "2 timed steps (+1 warm-up) of batch 16 x seq 128: single-gpu-cls.py loop body, HF "

