@@ -28,7 +28,7 @@ extern "C" {
 /* ------------------------------------------------------------------------------------------------------ */
 const char* b2_last_error(void);
 int32_t b2_abi_version(void);             /* bumped when a struct below changes */
-#define B2_ABI_VERSION 1
+#define B2_ABI_VERSION 2
 int64_t b2_launch_count(void);            /* kernels launched by this library so far (process-wide) */
 
 /* ------------------------------------------------------------------------------------------------------ */
@@ -71,6 +71,7 @@ typedef struct b2_gemm_args {
   int64_t workspace_bytes;
   int32_t force_bn;       /* 0 = auto, else 128 / 192 / 256 (tests, tuning)                                  */
   int32_t force_splits;   /* 0 = auto, else >= 1                                                             */
+  int32_t force_kernel;   /* 0 = auto, 1 = single-CTA 128xBN kernel, 2 = CTA-pair (cta_group::2) 256xBN kernel        */
 } b2_gemm_args_t;
 
 int32_t b2_gemm_bf16(const b2_gemm_args_t* args, void* stream);

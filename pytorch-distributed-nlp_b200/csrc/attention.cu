@@ -291,7 +291,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_bwd_kernel(const __grid
 
     // delta = rowsum(dO * O) and the row's log-sum-exp, straight from HBM while the MMAs run
     float delta = 0.f;
-    if (nq != 1) {
+    {
       const __nv_bfloat16* o_row = p.ctx_in + (size_t)(row0 + q_row) * p.hidden + h * 64;
       const __nv_bfloat16* do_row = p.d_ctx + (size_t)(row0 + q_row) * p.hidden + h * 64;
 #pragma unroll
@@ -307,40 +307,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_bwd_kernel(const __grid
     mbar_wait(bar_s, ph_s);
     ph_s ^= 1;
     tc_fence_after();
-    // Dropout keep bits of this row's 128 columns (16 groups of 8), drawn once and reused by both passes.
-    uint32_t keepw[4];
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      keepw[c] = 0;
-#pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        const unsigned long long idx =
-            (((unsigned long long)(b * p.heads + h) * p.seq + q_row) * p.seq) + jb * 128 + c * 32 + g * 8;
-        keepw[c] |= dropout_keep8(drop, idx) << (8 * g);
-      }
-    }
-    // delta_i = sum_j P_ij dP_ij.  With a single key block the whole row is in TMEM: take the sum from the very
-    // values dS is built from.  (rowsum(dO*O) is the same quantity algebraically, but O was rounded to bf16 and
-    // the rounding error -- proportional to |O|, not to the spread of dP -- does not cancel in (dP - delta):
-    // measured 3% error on late-layer Q/K weight gradients.)  Longer sequences keep the rowsum form.
-    if (nq == 1) {
-      float dsum = 0.f;
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t vs[32], vd[32];
-        tmem_ld32(tm_s + lane_base + c * 32, vs);
-        tmem_ld32(tm_dp + lane_base + c * 32, vd);
-        tmem_ld_wait();
-#pragma unroll
-        for (int e = 0; e < 32; ++e) {
-          const float pr = exp2f(__uint_as_float(vs[e]) * c2 + s_bias[c * 32 + e] - lse2);
-          const bool kp = (keepw[c] >> e) & 1u;
-          dsum += kp ? pr * __uint_as_float(vd[e]) * drop.scale : 0.f;
-        }
-      }
-      delta = dsum;
-    }
-#pragma unroll
+#pragma unroll 1
     for (int c = 0; c < 4; ++c) {
       uint32_t vs[32], vd[32];
       tmem_ld32(tm_s + lane_base + c * 32, vs);
@@ -348,12 +315,15 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_bwd_kernel(const __grid
       tmem_ld_wait();
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
+        const unsigned long long idx =
+            (((unsigned long long)(b * p.heads + h) * p.seq + q_row) * p.seq) + jb * 128 + c * 32 + g * 8;
+        const uint32_t keep = dropout_keep8(drop, idx);
         float pd[8], ds[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
           const int cc = g * 8 + e;
           const float pr = exp2f(__uint_as_float(vs[cc]) * c2 + s_bias[c * 32 + cc] - lse2);
-          const bool kp = (keepw[c] >> cc) & 1u;
+          const bool kp = (keep >> e) & 1u;
           pd[e] = kp ? pr * drop.scale : 0.f;
           const float dp = kp ? __uint_as_float(vd[cc]) * drop.scale : 0.f;
           ds[e] = pr * (dp - delta) * p.scale;

@@ -4,9 +4,16 @@
 // BertOutput (transformers modeling_bert.py:179-181, :295, :340, :353) and their autograd dgrad / wgrad
 // twins.
 //
-// Structure (persistent, warp specialised, one CTA per SM):
+// Two kernels share one epilogue:
+//   gemm2_bf16_kernel  CTA PAIR (cluster of 2, tcgen05 cta_group::2): the pair owns a 256 x BN output tile, each
+//                      CTA stages its own 128 A rows and HALF of the B tile, the leader's single thread issues
+//                      256 x BN x 16 MMAs that read both halves.  Per flop this moves 1/3 fewer bytes out of L2 and
+//                      through shared memory than a 128 x 256 single-CTA tile -- the first profile showed the
+//                      single-CTA kernel pinned at ~10 TB/s of L2->SM traffic (650 TF/s), not at the tensor pipe.
+//   gemm_bf16_kernel   single CTA, 128 x BN (BN 128/192/256): small or oddly shaped problems.
+// Common structure (persistent, warp specialised, one CTA per SM):
 //   warp 0      TMA producer      global -> 128B-swizzled smem ring (full/empty mbarriers)
-//   warp 1      MMA issuer        one lane issues tcgen05.mma (128 x BN x 16), commits to mbarriers
+//   warp 1      MMA issuer        one lane issues tcgen05.mma, commits to mbarriers
 //   warp 2      TMEM allocator    2 accumulator stages so tile i+1's MMAs overlap tile i's epilogue
 //   warps 4-11  epilogue          tcgen05.ld -> bias / GELU / dropout / residual -> bf16 global stores
 // Operand layouts are expressed only through the TMA box + UMMA descriptor (no transposes in HBM):
@@ -24,17 +31,6 @@ constexpr int UMMA_K = 16;
 constexpr int NUM_EPI_WARPS = 8;
 constexpr int GEMM_THREADS = (4 + NUM_EPI_WARPS) * 32;
 
-template <int BN>
-struct GemmCfg {
-  static constexpr int kStages = (BN == 256) ? 4 : (BN == 192 ? 5 : 6);
-  static constexpr int kABytes = BM * BK * 2;
-  static constexpr int kBBytes = BN * BK * 2;
-  static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kAccStride = (BN <= 128) ? 128 : 256;  // TMEM columns between the 2 accumulators
-  static constexpr int kTmemCols = 2 * kAccStride;            // 256 or 512 (power of two)
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
-};
-
 struct GemmKernelParams {
   int M, N, K;
   int tiles_m, tiles_n, splits, kblocks_per_split, kblocks_total;
@@ -45,6 +41,121 @@ struct GemmKernelParams {
   __nv_bfloat16* aux_out; long long ld_aux_out;
   float* partial;  // split-K fp32 partials [splits][M][N]
   float dropout_p; const unsigned long long* rng; unsigned rng_site;
+};
+
+// ------------------------------------------------------------------------------------------------------------
+// epilogue for one 32-column chunk of one output row (thread == row), shared by both kernels
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void epilogue_chunk(const GemmKernelParams& p, const DropCtx& drop, const uint32_t (&v)[32],
+                                               int m, int n, int split) {
+  if (p.epilogue == B2_EPI_PARTIAL_F32) {
+    float* dst = p.partial + ((size_t)split * p.M + m) * p.N + n;
+#pragma unroll
+    for (int j = 0; j < 32; j += 4)
+      *reinterpret_cast<float4*>(dst + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                                        __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+    return;
+  }
+  float f[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+  if (p.bias != nullptr) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {
+      const uint4 b = ldg16(p.bias + n + j);
+      f[j + 0] += bf16_lo(b.x); f[j + 1] += bf16_hi(b.x);
+      f[j + 2] += bf16_lo(b.y); f[j + 3] += bf16_hi(b.y);
+      f[j + 4] += bf16_lo(b.z); f[j + 5] += bf16_hi(b.z);
+      f[j + 6] += bf16_lo(b.w); f[j + 7] += bf16_hi(b.w);
+    }
+  }
+  if (p.epilogue == B2_EPI_BIAS_GELU) {
+    // keep the pre-activation (bf16) for the backward pass, emit gelu(pre-activation)
+    __nv_bfloat16* u = p.aux_out + (size_t)m * p.ld_aux_out + n;
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {
+      uint4 o;
+      o.x = pack_bf16(f[j], f[j + 1]); o.y = pack_bf16(f[j + 2], f[j + 3]);
+      o.z = pack_bf16(f[j + 4], f[j + 5]); o.w = pack_bf16(f[j + 6], f[j + 7]);
+      stg16(u + j, o);
+    }
+#pragma unroll
+    for (int j = 0; j < 32; ++j) f[j] = gelu_erf(bf16_round(f[j]));
+  } else if (p.epilogue == B2_EPI_BIAS_DROPOUT_RESIDUAL) {
+    const __nv_bfloat16* r = p.aux_in + (size_t)m * p.ld_aux_in + n;
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {
+      const uint32_t keep = dropout_keep8(drop, (unsigned long long)m * p.N + n + j);
+      const uint4 rr = ldg16(r + j);
+      const float res[8] = {bf16_lo(rr.x), bf16_hi(rr.x), bf16_lo(rr.y), bf16_hi(rr.y),
+                            bf16_lo(rr.z), bf16_hi(rr.z), bf16_lo(rr.w), bf16_hi(rr.w)};
+#pragma unroll
+      for (int i = 0; i < 8; ++i) f[j + i] = (((keep >> i) & 1u) ? f[j + i] * drop.scale : 0.f) + res[i];
+    }
+  } else if (p.epilogue == B2_EPI_RESIDUAL) {
+    const __nv_bfloat16* r = p.aux_in + (size_t)m * p.ld_aux_in + n;
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {
+      const uint4 rr = ldg16(r + j);
+      f[j + 0] += bf16_lo(rr.x); f[j + 1] += bf16_hi(rr.x);
+      f[j + 2] += bf16_lo(rr.y); f[j + 3] += bf16_hi(rr.y);
+      f[j + 4] += bf16_lo(rr.z); f[j + 5] += bf16_hi(rr.z);
+      f[j + 6] += bf16_lo(rr.w); f[j + 7] += bf16_hi(rr.w);
+    }
+  } else if (p.epilogue == B2_EPI_GELU_BWD) {
+    const __nv_bfloat16* u = p.aux_in + (size_t)m * p.ld_aux_in + n;
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {
+      const uint4 uu = ldg16(u + j);
+      f[j + 0] *= gelu_erf_grad(bf16_lo(uu.x)); f[j + 1] *= gelu_erf_grad(bf16_hi(uu.x));
+      f[j + 2] *= gelu_erf_grad(bf16_lo(uu.y)); f[j + 3] *= gelu_erf_grad(bf16_hi(uu.y));
+      f[j + 4] *= gelu_erf_grad(bf16_lo(uu.z)); f[j + 5] *= gelu_erf_grad(bf16_hi(uu.z));
+      f[j + 6] *= gelu_erf_grad(bf16_lo(uu.w)); f[j + 7] *= gelu_erf_grad(bf16_hi(uu.w));
+    }
+  }
+  __nv_bfloat16* d = p.D + (size_t)m * p.ldd + n;
+#pragma unroll
+  for (int j = 0; j < 32; j += 8) {
+    uint4 o;
+    o.x = pack_bf16(f[j], f[j + 1]); o.y = pack_bf16(f[j + 2], f[j + 3]);
+    o.z = pack_bf16(f[j + 4], f[j + 5]); o.w = pack_bf16(f[j + 6], f[j + 7]);
+    stg16(d + j, o);
+  }
+}
+
+// 8 epilogue warps drain one [128 rows x BN cols] accumulator: warp -> (TMEM lane quarter, column half)
+template <int BN>
+__device__ __forceinline__ void epilogue_tile(const GemmKernelParams& p, const DropCtx& drop, uint32_t tmem_acc,
+                                              int warp, int lane, int m_base, int n0, int split) {
+  const int quarter = warp & 3;           // TMEM lane quarter this warp may touch
+  const int colhalf = (warp - 4) >> 2;    // which half of the BN columns
+  constexpr int kColsPerWarp = BN / 2;
+  constexpr int kChunks = kColsPerWarp / 32;
+  const int m = m_base + quarter * 32 + lane;
+  const bool row_ok = m < p.M;
+#pragma unroll 1
+  for (int c = 0; c < kChunks; ++c) {
+    const int n = n0 + colhalf * kColsPerWarp + c * 32;
+    uint32_t v[32];
+    tmem_ld32(tmem_acc + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(colhalf * kColsPerWarp + c * 32), v);
+    tmem_ld_wait();
+    if (n < p.N && row_ok) epilogue_chunk(p, drop, v, m, n, split);
+    __syncwarp();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// single-CTA kernel
+// ------------------------------------------------------------------------------------------------------------
+template <int BN>
+struct GemmCfg {
+  static constexpr int kStages = (BN == 256) ? 4 : (BN == 192 ? 5 : 6);
+  static constexpr int kABytes = BM * BK * 2;
+  static constexpr int kBBytes = BN * BK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kAccStride = (BN <= 128) ? 128 : 256;  // TMEM columns between the 2 accumulators
+  static constexpr int kTmemCols = 2 * kAccStride;            // 256 or 512 (power of two)
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
 };
 
 template <int BN, bool A_MN, bool B_MN>
@@ -155,11 +266,6 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
   } else if (warp >= 4) {
     // ------------------------------ epilogue ------------------------------
-    const int ew = warp - 4;
-    const int quarter = warp & 3;            // TMEM lane quarter this warp may touch
-    const int colhalf = ew >> 2;             // which half of the BN columns
-    constexpr int kColsPerWarp = BN / 2;
-    constexpr int kChunks = kColsPerWarp / 32;
     const DropCtx drop = make_drop_ctx(p.rng, p.rng_site, p.dropout_p);
     int acc = 0; uint32_t acc_phase = 0;
     for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
@@ -167,94 +273,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       const int m0 = (tile / p.tiles_n) * BM, n0 = (tile % p.tiles_n) * BN;
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      const int m = m0 + quarter * 32 + lane;
-      const bool row_ok = m < p.M;
-#pragma unroll 1
-      for (int c = 0; c < kChunks; ++c) {
-        const int n = n0 + colhalf * kColsPerWarp + c * 32;
-        uint32_t v[32];
-        tmem_ld32(tmem_base + acc * Cfg::kAccStride + ((uint32_t)(quarter * 32) << 16) +
-                      (uint32_t)(colhalf * kColsPerWarp + c * 32), v);
-        tmem_ld_wait();
-        if (n < p.N && row_ok) {
-        if (p.epilogue == B2_EPI_PARTIAL_F32) {
-          float* dst = p.partial + ((size_t)split * p.M + m) * p.N + n;
-#pragma unroll
-          for (int j = 0; j < 32; j += 4)
-            *reinterpret_cast<float4*>(dst + j) =
-                make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
-                            __uint_as_float(v[j + 3]));
-        } else {
-        float f[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-        if (p.bias != nullptr) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            const uint4 b = ldg16(p.bias + n + j);
-            f[j + 0] += bf16_lo(b.x); f[j + 1] += bf16_hi(b.x);
-            f[j + 2] += bf16_lo(b.y); f[j + 3] += bf16_hi(b.y);
-            f[j + 4] += bf16_lo(b.z); f[j + 5] += bf16_hi(b.z);
-            f[j + 6] += bf16_lo(b.w); f[j + 7] += bf16_hi(b.w);
-          }
-        }
-        if (p.epilogue == B2_EPI_BIAS_GELU) {
-          // keep the pre-activation (bf16) for the backward pass, emit gelu(pre-activation)
-          __nv_bfloat16* u = p.aux_out + (size_t)m * p.ld_aux_out + n;
-#pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            uint4 o;
-            o.x = pack_bf16(f[j], f[j + 1]); o.y = pack_bf16(f[j + 2], f[j + 3]);
-            o.z = pack_bf16(f[j + 4], f[j + 5]); o.w = pack_bf16(f[j + 6], f[j + 7]);
-            stg16(u + j, o);
-          }
-#pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = gelu_erf(bf16_round(f[j]));
-        } else if (p.epilogue == B2_EPI_BIAS_DROPOUT_RESIDUAL) {
-          const __nv_bfloat16* r = p.aux_in + (size_t)m * p.ld_aux_in + n;
-#pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            const uint32_t keep = dropout_keep8(drop, (unsigned long long)m * p.N + n + j);
-            const uint4 rr = ldg16(r + j);
-            const float res[8] = {bf16_lo(rr.x), bf16_hi(rr.x), bf16_lo(rr.y), bf16_hi(rr.y),
-                                  bf16_lo(rr.z), bf16_hi(rr.z), bf16_lo(rr.w), bf16_hi(rr.w)};
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-              f[j + i] = (((keep >> i) & 1u) ? f[j + i] * drop.scale : 0.f) + res[i];
-          }
-        } else if (p.epilogue == B2_EPI_RESIDUAL) {
-          const __nv_bfloat16* r = p.aux_in + (size_t)m * p.ld_aux_in + n;
-#pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            const uint4 rr = ldg16(r + j);
-            f[j + 0] += bf16_lo(rr.x); f[j + 1] += bf16_hi(rr.x);
-            f[j + 2] += bf16_lo(rr.y); f[j + 3] += bf16_hi(rr.y);
-            f[j + 4] += bf16_lo(rr.z); f[j + 5] += bf16_hi(rr.z);
-            f[j + 6] += bf16_lo(rr.w); f[j + 7] += bf16_hi(rr.w);
-          }
-        } else if (p.epilogue == B2_EPI_GELU_BWD) {
-          const __nv_bfloat16* u = p.aux_in + (size_t)m * p.ld_aux_in + n;
-#pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            const uint4 uu = ldg16(u + j);
-            f[j + 0] *= gelu_erf_grad(bf16_lo(uu.x)); f[j + 1] *= gelu_erf_grad(bf16_hi(uu.x));
-            f[j + 2] *= gelu_erf_grad(bf16_lo(uu.y)); f[j + 3] *= gelu_erf_grad(bf16_hi(uu.y));
-            f[j + 4] *= gelu_erf_grad(bf16_lo(uu.z)); f[j + 5] *= gelu_erf_grad(bf16_hi(uu.z));
-            f[j + 6] *= gelu_erf_grad(bf16_lo(uu.w)); f[j + 7] *= gelu_erf_grad(bf16_hi(uu.w));
-          }
-        }
-        __nv_bfloat16* d = p.D + (size_t)m * p.ldd + n;
-#pragma unroll
-        for (int j = 0; j < 32; j += 8) {
-          uint4 o;
-          o.x = pack_bf16(f[j], f[j + 1]); o.y = pack_bf16(f[j + 2], f[j + 3]);
-          o.z = pack_bf16(f[j + 4], f[j + 5]); o.w = pack_bf16(f[j + 6], f[j + 7]);
-          stg16(d + j, o);
-        }
-        }  // bf16 epilogues
-        }  // in range
-        __syncwarp();
-      }
+      epilogue_tile<BN>(p, drop, tmem_base + acc * Cfg::kAccStride, warp, lane, m0, n0, split);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
@@ -267,6 +286,220 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// CTA-pair kernel (cta_group::2).  Pair tile 256 x BN; CTA rank r stages A rows [m0 + 128 r, +128) and B rows
+// [n0 + r BN/2, +BN/2).  All mbarriers exist in both CTAs at identical offsets:
+//   full[s]        lives in the LEADER (rank 0): armed by the leader's producer with the bytes of BOTH CTAs; both
+//                  CTAs' TMA loads complete_tx on it; the leader's MMA thread waits on it
+//   empty[s]       one per CTA, released by a multicast tcgen05.commit (both producers wait their own copy)
+//   tmem_full[a]   one per CTA, multicast commit (each CTA's epilogue warps wait their own copy)
+//   tmem_empty[a]  lives in the leader, count 2 x 8: the peer's epilogue warps arrive remotely
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t smem_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA tile load whose completion bytes are credited to an mbarrier given by its shared::cluster address
+__device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* m, uint32_t bar_cluster_addr,
+                                                int32_t c0, int32_t c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], "
+      "[%2];" ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t* smem_holder, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_holder)),
+               "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrives (once the issued MMAs are complete) on the barrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
+  const uint16_t mask = 3;
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"(mask)
+      : "memory");
+}
+
+template <int BN>
+struct Gemm2Cfg {
+  static constexpr int kABytes = BM * BK * 2;            // this CTA's 128 A rows
+  static constexpr int kBBytes = (BN / 2) * BK * 2;      // this CTA's half of the B tile
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = (BN == 256) ? 6 : 8;
+  static constexpr int kAccStride = (BN <= 128) ? 128 : 256;
+  static constexpr int kTmemCols = 2 * kAccStride;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
+};
+
+template <int BN, bool A_MN, bool B_MN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                  const GemmKernelParams p) {
+  using Cfg = Gemm2Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint64_t* empty_bar = full_bar + Cfg::kStages;
+  uint64_t* tmem_full = empty_bar + Cfg::kStages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < Cfg::kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full[s], 1);
+      mbar_init(&tmem_empty[s], 2 * NUM_EPI_WARPS);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc_2sm(tmem_holder, Cfg::kTmemCols);
+  tc_fence_before();
+  cluster_sync_all();   // barrier inits + TMEM allocation visible pair-wide before any remote arrive / TMA credit
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  const int num_work = p.tiles_m * p.tiles_n * p.splits;   // tiles_m counts 256-row tiles here
+
+  if (warp == 0) {
+    // ------------------------------ TMA producer (both CTAs) ------------------------------
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int w = pair; w < num_work; w += npairs) {
+        const int tile = w / p.splits, split = w % p.splits;
+        const int m0 = (tile / p.tiles_n) * (2 * BM) + (int)rank * BM;
+        const int n0 = (tile % p.tiles_n) * BN + (int)rank * (BN / 2);
+        const int kb0 = split * p.kblocks_per_split;
+        const int kb1 = min(kb0 + p.kblocks_per_split, p.kblocks_total);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (leader) mbar_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
+          const uint32_t bar = mapa_u32(smem_u32(&full_bar[stage]), 0);   // the leader's full barrier
+          uint8_t* sa = smem + stage * Cfg::kStageBytes;
+          uint8_t* sb = sa + Cfg::kABytes;
+          const int k0 = kb * BK;
+          if (!A_MN) {
+            tma_load_2d_2sm(sa, &tmap_a, bar, k0, m0);                     // box {64 k, 128 rows}
+          } else {
+#pragma unroll
+            for (int j = 0; j < BM / 64; ++j)                                // box {64 m, 64 k-rows}
+              tma_load_2d_2sm(sa + j * (BK * 128), &tmap_a, bar, m0 + 64 * j, k0);
+          }
+          if (!B_MN) {
+            tma_load_2d_2sm(sb, &tmap_b, bar, k0, n0);                     // box {64 k, BN/2 rows}
+          } else {
+#pragma unroll
+            for (int j = 0; j < BN / 128; ++j)
+              tma_load_2d_2sm(sb + j * (BK * 128), &tmap_b, bar, n0 + 64 * j, k0);
+          }
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------ MMA issuer (leader CTA only) ------------------------------
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(2 * BM, BN, A_MN, B_MN);
+      constexpr uint32_t a_lbo = A_MN ? BK * 128 : 16, b_lbo = B_MN ? BK * 128 : 16;
+      constexpr uint32_t a_kstep = A_MN ? UMMA_K * 128 : UMMA_K * 2;
+      constexpr uint32_t b_kstep = B_MN ? UMMA_K * 128 : UMMA_K * 2;
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int w = pair; w < num_work; w += npairs) {
+        const int split = w % p.splits;
+        const int kb0 = split * p.kblocks_per_split;
+        const int kb1 = min(kb0 + p.kblocks_per_split, p.kblocks_total);
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * Cfg::kAccStride;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
+          const uint32_t sb = sa + Cfg::kABytes;
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            const uint64_t da = make_smem_desc(sa + k * a_kstep, a_lbo, 1024);
+            const uint64_t db = make_smem_desc(sb + k * b_kstep, b_lbo, 1024);
+            umma_bf16_2sm(d_tmem, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit_2sm(&empty_bar[stage]);
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit_2sm(&tmem_full[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------ epilogue (both CTAs, own 128 rows) ------------------------------
+    const DropCtx drop = make_drop_ctx(p.rng, p.rng_site, p.dropout_p);
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int w = pair; w < num_work; w += npairs) {
+      const int tile = w / p.splits, split = w % p.splits;
+      const int m0 = (tile / p.tiles_n) * (2 * BM) + (int)rank * BM;
+      const int n0 = (tile % p.tiles_n) * BN;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      epilogue_tile<BN>(p, drop, tmem_base + acc * Cfg::kAccStride, warp, lane, m0, n0, split);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (leader) mbar_arrive(&tmem_empty[acc]);
+        else mbar_arrive_remote(mapa_u32(smem_u32(&tmem_empty[acc]), 0));
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  // no CTA may exit (or free TMEM) while its partner can still multicast-commit into it or read its smem
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, Cfg::kTmemCols);
   }
 }
 
@@ -300,6 +533,31 @@ static int num_sms() {
   return g_num_sms;
 }
 
+static void fill_params(GemmKernelParams& p, const b2_gemm_args_t& a, int tile_m, int bn, int splits) {
+  p.M = (int)a.M; p.N = (int)a.N; p.K = (int)a.K;
+  p.tiles_m = (p.M + tile_m - 1) / tile_m;
+  p.tiles_n = (p.N + bn - 1) / bn;
+  p.kblocks_total = (p.K + BK - 1) / BK;
+  p.splits = splits;
+  p.kblocks_per_split = (p.kblocks_total + splits - 1) / splits;
+  p.epilogue = splits > 1 ? B2_EPI_PARTIAL_F32 : a.epilogue;
+  p.D = (__nv_bfloat16*)a.D; p.ldd = a.ldd;
+  p.bias = (const __nv_bfloat16*)a.bias;
+  p.aux_in = (const __nv_bfloat16*)a.aux_in; p.ld_aux_in = a.ld_aux_in;
+  p.aux_out = (__nv_bfloat16*)a.aux_out; p.ld_aux_out = a.ld_aux_out;
+  p.partial = (float*)a.workspace;
+  p.dropout_p = a.dropout_p; p.rng = (const unsigned long long*)a.rng_state; p.rng_site = a.rng_site;
+}
+
+static int32_t launch_splitk_reduce(const b2_gemm_args_t& a, int splits, cudaStream_t stream) {
+  const long long total = (long long)a.M * a.N / 4;
+  splitk_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(
+      (const float*)a.workspace, (__nv_bfloat16*)a.D, a.ldd, (int)a.M, (int)a.N, splits);
+  B2_CUDA(cudaGetLastError());
+  count_launches(1);
+  return 0;
+}
+
 template <int BN, bool A_MN, bool B_MN>
 static int32_t launch_gemm(const b2_gemm_args_t& a, int splits, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
@@ -311,22 +569,8 @@ static int32_t launch_gemm(const b2_gemm_args_t& a, int splits, cudaStream_t str
   if (!B_MN) st = get_tensor_map_2d(&tb, a.B, (uint64_t)a.N, (uint64_t)a.K, (uint64_t)a.ldb * 2, BN, 64);
   else       st = get_tensor_map_2d(&tb, a.B, (uint64_t)a.K, (uint64_t)a.N, (uint64_t)a.ldb * 2, BK, 64);
   if (st) return st;
-
   GemmKernelParams p;
-  p.M = (int)a.M; p.N = (int)a.N; p.K = (int)a.K;
-  p.tiles_m = (p.M + BM - 1) / BM;
-  p.tiles_n = (p.N + BN - 1) / BN;
-  p.kblocks_total = (p.K + BK - 1) / BK;
-  p.splits = splits;
-  p.kblocks_per_split = (p.kblocks_total + splits - 1) / splits;
-  p.epilogue = splits > 1 ? B2_EPI_PARTIAL_F32 : a.epilogue;
-  p.D = (__nv_bfloat16*)a.D; p.ldd = a.ldd;
-  p.bias = (const __nv_bfloat16*)a.bias;
-  p.aux_in = (const __nv_bfloat16*)a.aux_in; p.ld_aux_in = a.ld_aux_in;
-  p.aux_out = (__nv_bfloat16*)a.aux_out; p.ld_aux_out = a.ld_aux_out;
-  p.partial = (float*)a.workspace;
-  p.dropout_p = a.dropout_p; p.rng = (const unsigned long long*)a.rng_state; p.rng_site = a.rng_site;
-
+  fill_params(p, a, BM, BN, splits);
   auto kern = gemm_bf16_kernel<BN, A_MN, B_MN>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -338,42 +582,76 @@ static int32_t launch_gemm(const b2_gemm_args_t& a, int splits, cudaStream_t str
   kern<<<grid, GEMM_THREADS, Cfg::kSmemBytes, stream>>>(ta, tb, p);
   B2_CUDA(cudaGetLastError());
   count_launches(1);
-  if (splits > 1) {
-    const long long total = (long long)p.M * p.N / 4;
-    splitk_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(
-        (const float*)a.workspace, (__nv_bfloat16*)a.D, a.ldd, p.M, p.N, splits);
-    B2_CUDA(cudaGetLastError());
-  count_launches(1);
-  }
+  if (splits > 1) return launch_splitk_reduce(a, splits, stream);
   return 0;
 }
 
-// Tile-width / split-K choice: maximise the fraction of SM-slots busy over whole waves.
-static void choose_config(const b2_gemm_args_t& a, int* bn_out, int* splits_out) {
+template <int BN, bool A_MN, bool B_MN>
+static int32_t launch_gemm2(const b2_gemm_args_t& a, int splits, cudaStream_t stream) {
+  using Cfg = Gemm2Cfg<BN>;
+  CUtensorMap ta, tb;
+  int32_t st;
+  if (!A_MN) st = get_tensor_map_2d(&ta, a.A, (uint64_t)a.M, (uint64_t)a.K, (uint64_t)a.lda * 2, BM, 64);
+  else       st = get_tensor_map_2d(&ta, a.A, (uint64_t)a.K, (uint64_t)a.M, (uint64_t)a.lda * 2, BK, 64);
+  if (st) return st;
+  if (!B_MN) st = get_tensor_map_2d(&tb, a.B, (uint64_t)a.N, (uint64_t)a.K, (uint64_t)a.ldb * 2, BN / 2, 64);
+  else       st = get_tensor_map_2d(&tb, a.B, (uint64_t)a.K, (uint64_t)a.N, (uint64_t)a.ldb * 2, BK, 64);
+  if (st) return st;
+  GemmKernelParams p;
+  fill_params(p, a, 2 * BM, BN, splits);
+  auto kern = gemm2_bf16_kernel<BN, A_MN, B_MN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  const int work = p.tiles_m * p.tiles_n * p.splits;
+  const int max_pairs = num_sms() / 2;
+  const int pairs = work < max_pairs ? work : max_pairs;
+  kern<<<2 * pairs, GEMM_THREADS, Cfg::kSmemBytes, stream>>>(ta, tb, p);
+  B2_CUDA(cudaGetLastError());
+  count_launches(1);
+  if (splits > 1) return launch_splitk_reduce(a, splits, stream);
+  return 0;
+}
+
+// Kernel / tile-width / split-K choice.  Cost model per candidate: rounds of whole waves x per-k-block time, where
+// the k-block time is the larger of the tensor-pipe time and the L2->SM feed time (measured ceiling ~10 TB/s).
+struct Choice { int pair, bn, splits; };
+static Choice choose_config(const b2_gemm_args_t& a) {
   const int sms = num_sms();
-  const int tiles_m = (int)((a.M + BM - 1) / BM);
   const int kblocks = (int)((a.K + BK - 1) / BK);
   const bool can_split = (a.epilogue == B2_EPI_NONE) && a.workspace != nullptr && a.bias == nullptr;
-  double best = -1.0; int best_bn = 128, best_s = 1;
-  const int bns[3] = {256, 192, 128};
-  for (int bi = 0; bi < 3; ++bi) {
-    const int bn = bns[bi];
-    if (a.N % bn != 0 && !(bn == 128)) continue;
-    const int tiles = tiles_m * (int)((a.N + bn - 1) / bn);
-    const int max_s = can_split ? 8 : 1;
-    for (int s = 1; s <= max_s; s *= 2) {
-      if (s > 1 && (kblocks / s < 8)) break;
-      if (s > 1 && (size_t)s * a.M * a.N * 4 > (size_t)a.workspace_bytes) break;
-      const int work = tiles * s;
-      const int waves = (work + sms - 1) / sms;
-      double eff = (double)work / ((double)waves * sms);
-      // per-tile fixed costs (prologue/epilogue) favour wider tiles and fewer splits a little
-      eff *= (bn == 256 ? 1.0 : bn == 192 ? 0.97 : 0.93);
-      if (s > 1) eff *= 0.92;
-      if (eff > best) { best = eff; best_bn = bn; best_s = s; }
+  double best = 1e30;
+  Choice c{0, 128, 1};
+  const double l2_bytes_per_cycle = 5500.0;   // ~10 TB/s at ~1.85 GHz, shared by the busy SMs
+  for (int pair = 0; pair <= 1; ++pair) {
+    const int bns[3] = {256, 192, 128};
+    for (int bi = 0; bi < 3; ++bi) {
+      const int bn = bns[bi];
+      if (pair && bn == 192) continue;                       // half tiles of 96 columns break the 64-wide MN chunks
+      if (a.N % bn != 0 && (pair || bn != 128)) continue;
+      const int tile_m = pair ? 256 : 128;
+      const int tiles = (int)((a.M + tile_m - 1) / tile_m) * (int)((a.N + bn - 1) / bn);
+      const int slots = pair ? sms / 2 : sms;
+      const int max_s = can_split ? 8 : 1;
+      for (int s = 1; s <= max_s; s *= 2) {
+        if (s > 1 && (kblocks / s < 8)) break;
+        if (s > 1 && (size_t)s * a.M * a.N * 4 > (size_t)a.workspace_bytes) break;
+        const int work = tiles * s;
+        const int rounds = (work + slots - 1) / slots;
+        const int busy_sms = (work < slots ? work : slots) * (pair ? 2 : 1);
+        const double mma_cycles = 128.0 * bn * 64 / 4096.0;                    // per SM, per k-block
+        const double bytes_per_sm = pair ? (128 + bn / 2) * 128.0 : (128 + bn) * 128.0;
+        const double feed_cycles = bytes_per_sm * busy_sms / l2_bytes_per_cycle;
+        const double kb_cycles = mma_cycles > feed_cycles ? mma_cycles : feed_cycles;
+        double t = rounds * ((double)((kblocks + s - 1) / s) * kb_cycles + 2500.0 /*prologue + epilogue tail*/);
+        if (s > 1) t += 1500.0 + (double)s * a.M * a.N * 8 / 3000.0;            // partial write + reduce pass
+        if (t < best) { best = t; c = Choice{pair, bn, s}; }
+      }
     }
   }
-  *bn_out = best_bn; *splits_out = best_s;
+  return c;
 }
 
 }  // namespace b2
@@ -405,32 +683,45 @@ extern "C" int32_t b2_gemm_bf16(const b2_gemm_args_t* a, void* stream_) {
     B2_REQUIRE(a->rng_state != nullptr, "b2_gemm_bf16: dropout needs rng_state");
   B2_REQUIRE(a->dropout_p >= 0.f && a->dropout_p < 1.f, "b2_gemm_bf16: dropout_p out of range");
 
-  int bn = 128, splits = 1;
-  choose_config(*a, &bn, &splits);
+  Choice c = choose_config(*a);
+  if (a->force_kernel == 1) c.pair = 0;
+  if (a->force_kernel == 2) c.pair = 1;
   if (a->force_bn == 128 || a->force_bn == 192 || a->force_bn == 256) {
-    B2_REQUIRE(a->N % a->force_bn == 0 || a->force_bn == 128, "b2_gemm_bf16: force_bn does not divide N");
-    bn = a->force_bn;
+    B2_REQUIRE(a->N % a->force_bn == 0 || (a->force_bn == 128 && !c.pair), "b2_gemm_bf16: force_bn does not divide N");
+    c.bn = a->force_bn;
+  }
+  if (c.pair) {
+    if (c.bn == 192) c.bn = (a->N % 256 == 0) ? 256 : 128;
+    B2_REQUIRE(a->N % c.bn == 0, "b2_gemm_bf16: the CTA-pair kernel needs N %% %d == 0 (N=%lld)", c.bn,
+               (long long)a->N);
+  } else if (a->N % c.bn != 0 && c.bn != 128) {
+    c.bn = 128;
   }
   if (a->force_splits >= 1) {
     B2_REQUIRE(a->force_splits == 1 ||
                    (a->epilogue == B2_EPI_NONE && a->workspace &&
                     (size_t)a->force_splits * a->M * a->N * 4 <= (size_t)a->workspace_bytes),
                "b2_gemm_bf16: split-K needs EPI_NONE and a large enough workspace");
-    splits = a->force_splits;
+    c.splits = a->force_splits;
   }
   const bool a_mn = a->a_major == B2_MAJOR_MN, b_mn = a->b_major == B2_MAJOR_MN;
   B2_REQUIRE(!(a_mn && !b_mn), "b2_gemm_bf16: layout TT (A MN-major, B K-major) is not on the path");
 
-#define B2_DISPATCH(BN_)                                                                \
-  if (bn == BN_) {                                                                      \
-    if (!a_mn && !b_mn) return launch_gemm<BN_, false, false>(*a, splits, stream);      \
-    if (!a_mn && b_mn) return launch_gemm<BN_, false, true>(*a, splits, stream);        \
-    return launch_gemm<BN_, true, true>(*a, splits, stream);                            \
+#define B2_DISPATCH(FN, BN_)                                                           \
+  if (c.bn == BN_) {                                                                   \
+    if (!a_mn && !b_mn) return FN<BN_, false, false>(*a, c.splits, stream);            \
+    if (!a_mn && b_mn) return FN<BN_, false, true>(*a, c.splits, stream);              \
+    return FN<BN_, true, true>(*a, c.splits, stream);                                  \
   }
-  B2_DISPATCH(128)
-  B2_DISPATCH(192)
-  B2_DISPATCH(256)
+  if (c.pair) {
+    B2_DISPATCH(launch_gemm2, 128)
+    B2_DISPATCH(launch_gemm2, 256)
+  } else {
+    B2_DISPATCH(launch_gemm, 128)
+    B2_DISPATCH(launch_gemm, 192)
+    B2_DISPATCH(launch_gemm, 256)
+  }
 #undef B2_DISPATCH
-  set_error("b2_gemm_bf16: no kernel for BN=%d", bn);
+  set_error("b2_gemm_bf16: no kernel for pair=%d BN=%d", c.pair, c.bn);
   return -2;
 }

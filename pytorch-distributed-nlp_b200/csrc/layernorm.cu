@@ -31,31 +31,27 @@ __global__ void __launch_bounds__(128) layernorm_fwd_kernel(const __nv_bfloat16*
 
 // mode 0: dropout mask (if any) applies to the LN *input* branch -> emit dx_drop = dx*mask*scale (encoder LNs)
 // mode 1: dropout mask applies to the LN *output* (embeddings: y = dropout(LN(x))) -> dy is masked on load
-// 16 warps per CTA, one row per warp at a time; the three column sums (d_gamma, d_beta, d_bias) accumulate in shared
-// memory with native fp32 shared atomics, which keeps the register footprint small enough for 16 resident warps
-// (rows are few -- 4096 -- so latency hiding comes from warps in flight, not from long per-warp loops).
 template <int VPL>
-__global__ void __launch_bounds__(512, 1) layernorm_bwd_kernel(
+__global__ void __launch_bounds__(256) layernorm_bwd_kernel(
     const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ dy_add,
     const __nv_bfloat16* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ rstd,
     const __nv_bfloat16* __restrict__ gamma, int rows, float dropout_p, const unsigned long long* rng,
     unsigned rng_site, int mode, __nv_bfloat16* __restrict__ dx, __nv_bfloat16* __restrict__ dx_drop,
     float* __restrict__ partials /* [gridDim.x][3][H] */) {
   constexpr int H = VPL * 256;
-  constexpr int WARPS = 16;
-  __shared__ float acc[3][H];
+  constexpr int WARPS = 8;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const DropCtx drop = make_drop_ctx(rng, rng_site, dropout_p);
-  for (int c = threadIdx.x; c < 3 * H; c += blockDim.x) (&acc[0][0])[c] = 0.f;
-  __syncthreads();
 
   float g[VPL * 8];
   load_row<VPL>(gamma, lane, g);
+  float acc_g[VPL * 8], acc_b[VPL * 8], acc_d[VPL * 8];
+#pragma unroll
+  for (int i = 0; i < VPL * 8; ++i) acc_g[i] = acc_b[i] = acc_d[i] = 0.f;
 
   for (int row = blockIdx.x * WARPS + warp; row < rows; row += gridDim.x * WARPS) {
     float dyv[VPL * 8], xv[VPL * 8];
     load_row<VPL>(dy + (size_t)row * H, lane, dyv);
-    load_row<VPL>(x + (size_t)row * H, lane, xv);
     if (dy_add != nullptr) {
       float t[VPL * 8];
       load_row<VPL>(dy_add + (size_t)row * H, lane, t);
@@ -70,46 +66,65 @@ __global__ void __launch_bounds__(512, 1) layernorm_bwd_kernel(
         for (int i = 0; i < 8; ++i) dyv[vv * 8 + i] = ((keep >> i) & 1u) ? dyv[vv * 8 + i] * drop.scale : 0.f;
       }
     }
+    load_row<VPL>(x + (size_t)row * H, lane, xv);
     const float mu = mean[row], rs = rstd[row];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int vv = 0; vv < VPL; ++vv)
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int e = vv * 8 + i, col = (vv * 32 + lane) * 8 + i;
-        xv[e] = (xv[e] - mu) * rs;               // xhat
-        const float dxh = dyv[e] * g[e];
-        s1 += dxh;
-        s2 += dxh * xv[e];
-        atomicAdd(&acc[0][col], dyv[e] * xv[e]);
-        atomicAdd(&acc[1][col], dyv[e]);
-      }
+    for (int i = 0; i < VPL * 8; ++i) {
+      xv[i] = (xv[i] - mu) * rs;               // xhat
+      const float dxh = dyv[i] * g[i];
+      s1 += dxh;
+      s2 += dxh * xv[i];
+      acc_g[i] += dyv[i] * xv[i];
+      acc_b[i] += dyv[i];
+    }
     s1 = warp_sum(s1) * (1.0f / H);
     s2 = warp_sum(s2) * (1.0f / H);
+    float dxv[VPL * 8];
 #pragma unroll
-    for (int i = 0; i < VPL * 8; ++i) dyv[i] = rs * (dyv[i] * g[i] - s1 - xv[i] * s2);   // dx
-    store_row<VPL>(dx + (size_t)row * H, lane, dyv);
+    for (int i = 0; i < VPL * 8; ++i) dxv[i] = rs * (dyv[i] * g[i] - s1 - xv[i] * s2);
+    store_row<VPL>(dx + (size_t)row * H, lane, dxv);
     if (mode == 0) {
       if (dx_drop != nullptr) {
 #pragma unroll
         for (int vv = 0; vv < VPL; ++vv) {
           const uint32_t keep = dropout_keep8(drop, (unsigned long long)row * H + (vv * 32 + lane) * 8);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) dyv[vv * 8 + i] = ((keep >> i) & 1u) ? dyv[vv * 8 + i] * drop.scale : 0.f;
+          for (int i = 0; i < 8; ++i) {
+            // the GEMMs consume the bf16-rounded value; sum exactly what they see
+            const float t = ((keep >> i) & 1u) ? dxv[vv * 8 + i] * drop.scale : 0.f;
+            dxv[vv * 8 + i] = bf16_round(t);
+          }
         }
-        store_row<VPL>(dx_drop + (size_t)row * H, lane, dyv);
+        store_row<VPL>(dx_drop + (size_t)row * H, lane, dxv);
+      } else {
+#pragma unroll
+        for (int i = 0; i < VPL * 8; ++i) dxv[i] = bf16_round(dxv[i]);
       }
-      // the GEMMs consume the bf16-rounded value; the bias gradient sums exactly what they see
 #pragma unroll
-      for (int vv = 0; vv < VPL; ++vv)
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-          atomicAdd(&acc[2][(vv * 32 + lane) * 8 + i], bf16_round(dyv[vv * 8 + i]));
+      for (int i = 0; i < VPL * 8; ++i) acc_d[i] += dxv[i];
     }
   }
-  __syncthreads();
+
+  // block reduction of the three column-sum sets (warps -> smem -> one partial row per block)
+  __shared__ float red[WARPS][H];
   float* out = partials + (size_t)blockIdx.x * 3 * H;
-  for (int c = threadIdx.x; c < 3 * H; c += blockDim.x) out[c] = (&acc[0][0])[c];
+#define B2_REDUCE_SET(ARR, WHICH)                                                          \
+  {                                                                                        \
+    _Pragma("unroll") for (int vv = 0; vv < VPL; ++vv)                                     \
+        _Pragma("unroll") for (int i = 0; i < 8; ++i) red[warp][(vv * 32 + lane) * 8 + i] = ARR[vv * 8 + i]; \
+    __syncthreads();                                                                       \
+    for (int c = threadIdx.x; c < H; c += blockDim.x) {                                    \
+      float s = 0.f;                                                                       \
+      _Pragma("unroll") for (int w = 0; w < WARPS; ++w) s += red[w][c];                    \
+      out[(WHICH)*H + c] = s;                                                              \
+    }                                                                                      \
+    __syncthreads();                                                                       \
+  }
+  B2_REDUCE_SET(acc_g, 0)
+  B2_REDUCE_SET(acc_b, 1)
+  B2_REDUCE_SET(acc_d, 2)
+#undef B2_REDUCE_SET
 }
 
 // partials [nparts][nsets][cols] fp32 -> up to three bf16 [cols] outputs.  Block = 32 columns x 8 part-lanes so the
@@ -199,14 +214,14 @@ int32_t launch_layernorm_bwd(const void* dy, const void* dy_add, const void* x, 
   B2_REQUIRE(hidden % 256 == 0 && hidden >= 256 && hidden <= 1024, "layernorm: hidden=%lld unsupported",
              (long long)hidden);
   int nblocks = (int)(scratch_bytes / (3 * hidden * 4));
-  const int want = 148;
+  const int want = 296;
   if (nblocks > want) nblocks = want;
-  const int max_useful = (int)((rows + 15) / 16);
+  const int max_useful = (int)((rows + 7) / 8);
   if (nblocks > max_useful) nblocks = max_useful;
   B2_REQUIRE(nblocks >= 1, "layernorm_bwd: scratch too small");
 #define B2_LN_BWD(VPL_)                                                                                        \
   case VPL_:                                                                                                   \
-    layernorm_bwd_kernel<VPL_><<<nblocks, 512, 0, stream>>>(                                                   \
+    layernorm_bwd_kernel<VPL_><<<nblocks, 256, 0, stream>>>(                                                   \
         (const __nv_bfloat16*)dy, (const __nv_bfloat16*)dy_add, (const __nv_bfloat16*)x, mean, rstd,           \
         (const __nv_bfloat16*)gamma, (int)rows, dropout_p, (const unsigned long long*)rng, site, mode,         \
         (__nv_bfloat16*)dx, (__nv_bfloat16*)dx_drop, scratch);                                                 \

@@ -472,6 +472,7 @@ class _Engine:
             a.workspace, a.workspace_bytes = None, 0
         a.force_bn = int(os.environ.get("B2_FORCE_BN", "0"))
         a.force_splits = 0
+        a.force_kernel = int(os.environ.get("B2_FORCE_KERNEL", "0"))
         L.call("b2_gemm_bf16", a, stream if stream is not None else self.stream())
 
     # ---- forward --------------------------------------------------------------------------------------------------------

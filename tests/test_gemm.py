@@ -13,7 +13,7 @@ def _rng_state(dev, seed=77, step=3):
 
 
 def _call(M, N, K, A, lda, a_major, B, ldb, b_major, D, epi=L.EPI_NONE, bias=None, aux_in=None, aux_out=None,
-          p=0.0, rng=None, site=0, ws=None, bn=0, splits=0):
+          p=0.0, rng=None, site=0, ws=None, bn=0, splits=0, kernel=0):
     a = L.GemmArgs()
     a.M, a.N, a.K = M, N, K
     a.A, a.lda, a.a_major = A.data_ptr(), lda, a_major
@@ -24,7 +24,7 @@ def _call(M, N, K, A, lda, a_major, B, ldb, b_major, D, epi=L.EPI_NONE, bias=Non
     a.aux_out, a.ld_aux_out = L.ptr(aux_out), (aux_out.shape[1] if aux_out is not None else 0)
     a.dropout_p, a.rng_state, a.rng_site = p, L.ptr(rng), site
     a.workspace, a.workspace_bytes = L.ptr(ws), (ws.numel() if ws is not None else 0)
-    a.force_bn, a.force_splits = bn, splits
+    a.force_bn, a.force_splits, a.force_kernel = bn, splits, kernel
     L.call("b2_gemm_bf16", a, torch.cuda.current_stream().cuda_stream)
     torch.cuda.synchronize()
 
@@ -40,36 +40,54 @@ def _check(got, ref, tol=2e-2):
     assert err <= tol * scale, "max err %.4g vs scale %.4g" % (err, scale)
 
 
-@pytest.mark.parametrize("bn", [128, 192, 256])
+# (kernel, bn): 1 = single-CTA 128 x bn tiles, 2 = CTA-pair (cta_group::2) 256 x bn tiles
+KERNELS = [(1, 128), (1, 192), (1, 256), (2, 128), (2, 256)]
+
+
+@pytest.mark.parametrize("kernel,bn", KERNELS)
 @pytest.mark.parametrize("shape", [(256, 768, 64), (384, 768, 768), (4096, 2304, 768), (200, 768, 136)])
-def test_nt_bias(cuda_dev, bn, shape):
+def test_nt_bias(cuda_dev, kernel, bn, shape):
     M, N, K = shape
     torch.manual_seed(0)
     A, B, bias = _rand((M, K), cuda_dev), _rand((N, K), cuda_dev, 0.05), _rand((N,), cuda_dev)
     D = torch.zeros(M, N, dtype=torch.bfloat16, device=cuda_dev)
-    _call(M, N, K, A, K, L.MAJOR_K, B, K, L.MAJOR_K, D, L.EPI_BIAS, bias=bias, bn=bn)
+    _call(M, N, K, A, K, L.MAJOR_K, B, K, L.MAJOR_K, D, L.EPI_BIAS, bias=bias, bn=bn, kernel=kernel)
     _check(D, A.float() @ B.float().t() + bias.float())
 
 
-@pytest.mark.parametrize("bn", [128, 192, 256])
-def test_nn_dgrad(cuda_dev, bn):
+@pytest.mark.parametrize("kernel,bn", KERNELS)
+def test_nn_dgrad(cuda_dev, kernel, bn):
     M, N, K = 512, 768, 3072
     torch.manual_seed(1)
     A, B = _rand((M, K), cuda_dev), _rand((K, N), cuda_dev, 0.05)
     D = torch.zeros(M, N, dtype=torch.bfloat16, device=cuda_dev)
-    _call(M, N, K, A, K, L.MAJOR_K, B, N, L.MAJOR_MN, D, bn=bn)
+    _call(M, N, K, A, K, L.MAJOR_K, B, N, L.MAJOR_MN, D, bn=bn, kernel=kernel)
     _check(D, A.float() @ B.float())
 
 
-@pytest.mark.parametrize("bn,splits", [(128, 1), (192, 1), (256, 1), (128, 4), (256, 2)])
-def test_tn_wgrad(cuda_dev, bn, splits):
+@pytest.mark.parametrize("kernel,bn,splits", [(1, 128, 1), (1, 192, 1), (1, 256, 1), (1, 128, 4), (1, 256, 2),
+                                              (2, 128, 1), (2, 256, 1), (2, 256, 4), (2, 128, 8)])
+def test_tn_wgrad(cuda_dev, kernel, bn, splits):
     M, N, K = 768, 768, 2048   # dW[M,N] = dY[K,M]^T X[K,N]
     torch.manual_seed(2)
     A, B = _rand((K, M), cuda_dev), _rand((K, N), cuda_dev)
     D = torch.zeros(M, N, dtype=torch.bfloat16, device=cuda_dev)
     ws = torch.empty(splits * M * N * 4, dtype=torch.uint8, device=cuda_dev)
-    _call(M, N, K, A, M, L.MAJOR_MN, B, N, L.MAJOR_MN, D, ws=ws, bn=bn, splits=splits)
+    _call(M, N, K, A, M, L.MAJOR_MN, B, N, L.MAJOR_MN, D, ws=ws, bn=bn, splits=splits, kernel=kernel)
     _check(D, A.float().t() @ B.float())
+
+
+def test_pair_kernel_many_tiles_per_pair(cuda_dev):
+    """persistent loop + TMEM double buffering of the CTA-pair kernel: 16 x 12 = 192 tiles over 74 pairs"""
+    M, N, K = 4096, 3072, 768
+    torch.manual_seed(8)
+    A, B, bias = _rand((M, K), cuda_dev), _rand((N, K), cuda_dev, 0.05), _rand((N,), cuda_dev)
+    D = torch.zeros(M, N, dtype=torch.bfloat16, device=cuda_dev)
+    U = torch.zeros(M, N, dtype=torch.bfloat16, device=cuda_dev)
+    _call(M, N, K, A, K, L.MAJOR_K, B, K, L.MAJOR_K, D, L.EPI_BIAS_GELU, bias=bias, aux_out=U, bn=256, kernel=2)
+    u = A.float() @ B.float().t() + bias.float()
+    _check(U, u)
+    _check(D, torch.nn.functional.gelu(U.float()), tol=1e-2)
 
 
 def test_auto_config_and_ld(cuda_dev):
