@@ -28,7 +28,7 @@ extern "C" {
 /* ------------------------------------------------------------------------------------------------------ */
 const char* b2_last_error(void);
 int32_t b2_abi_version(void);             /* bumped when a struct below changes */
-#define B2_ABI_VERSION 2
+#define B2_ABI_VERSION 3
 int64_t b2_launch_count(void);            /* kernels launched by this library so far (process-wide) */
 
 /* ------------------------------------------------------------------------------------------------------ */
@@ -45,6 +45,7 @@ enum {
   B2_EPI_BIAS_DROPOUT_RESIDUAL = 3, /* D = dropout(acc + bias) + aux_in         (BertSelfOutput / BertOutput) */
   B2_EPI_RESIDUAL = 4,              /* D = acc + aux_in                         (dgrad joining a residual)    */
   B2_EPI_GELU_BWD = 5,              /* D = acc * gelu_erf'(aux_in)              (dgrad through GELU)          */
+  B2_EPI_RESIDUAL_F32 = 6,          /* D(fp32) = acc + aux_in(fp32); ldd / ld_aux_in count fp32 elements      */
   B2_EPI_PARTIAL_F32 = 100          /* internal: split-K partials                                           */
 };
 
@@ -96,7 +97,7 @@ int32_t b2_embed_owner_init(int32_t* owner, int64_t vocab, void* stream);
 /* backward of the above: LN backward, then the three scatter-adds (deterministic: one owner CTA per touched
  * vocabulary row sums its duplicates in token order).  d_word must be zeroed by the caller (b2_zero).  The row
  * `pad_token_id` gets no gradient (nn.Embedding padding_idx semantics, modeling_bert.py:58).                 */
-int32_t b2_embed_bwd(const void* dy, const void* pre_ln, const float* mean, const float* rstd, const void* gamma,
+int32_t b2_embed_bwd(const void* dy /* bf16, or fp32 when dy_fp32 */, int32_t dy_fp32, const void* pre_ln, const float* mean, const float* rstd, const void* gamma,
                      const int32_t* ids32, const int32_t* tt32, int64_t batch, int64_t seq, int64_t hidden,
                      int64_t vocab, int64_t type_vocab, int64_t pad_token_id /* -1: none */, float dropout_p,
                      const void* rng_state, uint32_t rng_site, void* d_word, void* d_pos, void* d_type, void* d_gamma, void* d_beta, void* scratch_dx,
@@ -114,7 +115,8 @@ int32_t b2_layernorm_fwd(const void* x, const void* gamma, const void* beta, int
  * `dy_add` (optional) is added to dy first (second consumer of the LN output, e.g. a residual path).       */
 int32_t b2_layernorm_bwd(const void* dy, const void* dy_add, const void* x, const float* mean, const float* rstd,
                          const void* gamma, int64_t rows, int64_t hidden, float dropout_p, const void* rng_state,
-                         uint32_t rng_site, void* dx, void* dx_drop, void* d_gamma, void* d_beta, void* d_bias,
+                         uint32_t rng_site, int32_t grad_fp32 /* 1: dy, dy_add, dx are fp32 (dx_drop stays bf16 and
+                         is then always written: it is what the GEMMs consume) */, void* dx, void* dx_drop, void* d_gamma, void* d_beta, void* d_bias,
                          float* scratch_partials, int64_t scratch_partials_bytes, void* stream);
 
 /* column sums of a bf16 [rows, cols] matrix -> bf16 [cols]   (bias gradients of QKV / intermediate dense)  */
@@ -151,8 +153,9 @@ int32_t b2_ce_fwd_bwd(const float* logits, const int64_t* labels, int64_t batch,
 int32_t b2_head_bwd(const float* dlogits, const void* hidden_states, const void* pooled, int64_t batch,
                     int64_t seq, int64_t hidden, const void* pool_w, const void* cls_w, int64_t num_labels,
                     float dropout_p, const void* rng_state, uint32_t rng_site, void* d_pool_w, void* d_pool_b,
-                    void* d_cls_w, void* d_cls_b, void* d_hidden /* bf16 [batch*seq, hidden], rows != CLS zeroed */,
-                    float* scratch /* fp32 [batch, hidden] */, void* stream);
+                    void* d_cls_w, void* d_cls_b, void* d_hidden /* [batch*seq, hidden], rows != CLS zeroed */,
+                    int32_t d_hidden_fp32 /* 0: bf16, 1: fp32 */, float* scratch /* fp32 [batch, hidden] */,
+                    void* stream);
 
 /* ------------------------------------------------------------------------------------------------------ */
 /* optimizer + gradient exchange                                                                          */

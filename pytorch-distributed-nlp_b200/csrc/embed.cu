@@ -170,7 +170,8 @@ extern "C" int32_t b2_embed_fwd(const int64_t* input_ids, const int64_t* token_t
   return 0;
 }
 
-extern "C" int32_t b2_embed_bwd(const void* dy, const void* pre_ln, const float* mean, const float* rstd,
+extern "C" int32_t b2_embed_bwd(const void* dy, int32_t dy_fp32, const void* pre_ln, const float* mean,
+                                const float* rstd,
                                 const void* gamma, const int32_t* ids32, const int32_t* tt32, int64_t batch,
                                 int64_t seq, int64_t hidden, int64_t vocab, int64_t type_vocab, int64_t pad_token_id,
                                 float dropout_p, const void* rng_state, uint32_t rng_site, void* d_word, void* d_pos,
@@ -186,8 +187,8 @@ extern "C" int32_t b2_embed_bwd(const void* dy, const void* pre_ln, const float*
   const int tokens = (int)(batch * seq);
   // 1. LayerNorm backward (dropout sits on the LN output here -> mode 1); dx lands in scratch_dx
   int32_t st = launch_layernorm_bwd(dy, nullptr, pre_ln, mean, rstd, gamma, tokens, hidden, dropout_p, rng_state,
-                                    rng_site, 1, scratch_dx, nullptr, d_gamma, d_beta, nullptr, scratch_partials,
-                                    scratch_partials_bytes, stream);
+                                    rng_site, 1, dy_fp32 ? 1 : 0, 0, scratch_dx, nullptr, d_gamma, d_beta, nullptr,
+                                    scratch_partials, scratch_partials_bytes, stream);
   if (st) return st;
   // 2. word rows (d_word pre-zeroed by the caller)
   embed_owner_kernel<<<(tokens + 255) / 256, 256, 0, stream>>>(ids32, tokens, (int)pad_token_id, owner);

@@ -10,17 +10,19 @@
 //                      256 x BN x 16 MMAs that read both halves.  Per flop this moves 1/3 fewer bytes out of L2 and
 //                      through shared memory than a 128 x 256 single-CTA tile -- the first profile showed the
 //                      single-CTA kernel pinned at ~10 TB/s of L2->SM traffic (650 TF/s), not at the tensor pipe.
-//   gemm_bf16_kernel   single CTA, 128 x BN (BN 128/192/256): small or oddly shaped problems.
+//   gemm_bf16_kernel   single CTA, 128 x BN (BN 128/256): small or oddly shaped problems.
 // Common structure (persistent, warp specialised, one CTA per SM):
 //   warp 0      TMA producer      global -> 128B-swizzled smem ring (full/empty mbarriers)
 //   warp 1      MMA issuer        one lane issues tcgen05.mma, commits to mbarriers
 //   warp 2      TMEM allocator    2 accumulator stages so tile i+1's MMAs overlap tile i's epilogue
-//   warps 4-11  epilogue          tcgen05.ld -> bias / GELU / dropout / residual -> bf16 global stores
+//   warps 4-11  epilogue          tcgen05.ld -> bias / GELU / dropout / residual -> smem staging -> coalesced stores
+//                                 (gemm_epilogue.cuh)
 // Operand layouts are expressed only through the TMA box + UMMA descriptor (no transposes in HBM):
 //   NT  A[M,K] K-major,  B[N,K] K-major   (forward:  y = x W^T)
 //   NN  A[M,K] K-major,  B[K,N] MN-major  (dgrad:    dx = dy W)
 //   TN  A[K,M] MN-major, B[K,N] MN-major  (wgrad:    dW = dy^T x), optional split-K over the token axis
 #include "common.cuh"
+#include "gemm_epilogue.cuh"
 #include "../../include/b2_ddp_bert.h"
 
 namespace b2 {
@@ -31,131 +33,19 @@ constexpr int UMMA_K = 16;
 constexpr int NUM_EPI_WARPS = 8;
 constexpr int GEMM_THREADS = (4 + NUM_EPI_WARPS) * 32;
 
-struct GemmKernelParams {
-  int M, N, K;
-  int tiles_m, tiles_n, splits, kblocks_per_split, kblocks_total;
-  int epilogue;
-  __nv_bfloat16* D; long long ldd;
-  const __nv_bfloat16* bias;
-  const __nv_bfloat16* aux_in; long long ld_aux_in;
-  __nv_bfloat16* aux_out; long long ld_aux_out;
-  float* partial;  // split-K fp32 partials [splits][M][N]
-  float dropout_p; const unsigned long long* rng; unsigned rng_site;
-};
-
-// ------------------------------------------------------------------------------------------------------------
-// epilogue for one 32-column chunk of one output row (thread == row), shared by both kernels
-// ------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void epilogue_chunk(const GemmKernelParams& p, const DropCtx& drop, const uint32_t (&v)[32],
-                                               int m, int n, int split) {
-  if (p.epilogue == B2_EPI_PARTIAL_F32) {
-    float* dst = p.partial + ((size_t)split * p.M + m) * p.N + n;
-#pragma unroll
-    for (int j = 0; j < 32; j += 4)
-      *reinterpret_cast<float4*>(dst + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
-                                                        __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
-    return;
-  }
-  float f[32];
-#pragma unroll
-  for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-  if (p.bias != nullptr) {
-#pragma unroll
-    for (int j = 0; j < 32; j += 8) {
-      const uint4 b = ldg16(p.bias + n + j);
-      f[j + 0] += bf16_lo(b.x); f[j + 1] += bf16_hi(b.x);
-      f[j + 2] += bf16_lo(b.y); f[j + 3] += bf16_hi(b.y);
-      f[j + 4] += bf16_lo(b.z); f[j + 5] += bf16_hi(b.z);
-      f[j + 6] += bf16_lo(b.w); f[j + 7] += bf16_hi(b.w);
-    }
-  }
-  if (p.epilogue == B2_EPI_BIAS_GELU) {
-    // keep the pre-activation (bf16) for the backward pass, emit gelu(pre-activation)
-    __nv_bfloat16* u = p.aux_out + (size_t)m * p.ld_aux_out + n;
-#pragma unroll
-    for (int j = 0; j < 32; j += 8) {
-      uint4 o;
-      o.x = pack_bf16(f[j], f[j + 1]); o.y = pack_bf16(f[j + 2], f[j + 3]);
-      o.z = pack_bf16(f[j + 4], f[j + 5]); o.w = pack_bf16(f[j + 6], f[j + 7]);
-      stg16(u + j, o);
-    }
-#pragma unroll
-    for (int j = 0; j < 32; ++j) f[j] = gelu_erf(bf16_round(f[j]));
-  } else if (p.epilogue == B2_EPI_BIAS_DROPOUT_RESIDUAL) {
-    const __nv_bfloat16* r = p.aux_in + (size_t)m * p.ld_aux_in + n;
-#pragma unroll
-    for (int j = 0; j < 32; j += 8) {
-      const uint32_t keep = dropout_keep8(drop, (unsigned long long)m * p.N + n + j);
-      const uint4 rr = ldg16(r + j);
-      const float res[8] = {bf16_lo(rr.x), bf16_hi(rr.x), bf16_lo(rr.y), bf16_hi(rr.y),
-                            bf16_lo(rr.z), bf16_hi(rr.z), bf16_lo(rr.w), bf16_hi(rr.w)};
-#pragma unroll
-      for (int i = 0; i < 8; ++i) f[j + i] = (((keep >> i) & 1u) ? f[j + i] * drop.scale : 0.f) + res[i];
-    }
-  } else if (p.epilogue == B2_EPI_RESIDUAL) {
-    const __nv_bfloat16* r = p.aux_in + (size_t)m * p.ld_aux_in + n;
-#pragma unroll
-    for (int j = 0; j < 32; j += 8) {
-      const uint4 rr = ldg16(r + j);
-      f[j + 0] += bf16_lo(rr.x); f[j + 1] += bf16_hi(rr.x);
-      f[j + 2] += bf16_lo(rr.y); f[j + 3] += bf16_hi(rr.y);
-      f[j + 4] += bf16_lo(rr.z); f[j + 5] += bf16_hi(rr.z);
-      f[j + 6] += bf16_lo(rr.w); f[j + 7] += bf16_hi(rr.w);
-    }
-  } else if (p.epilogue == B2_EPI_GELU_BWD) {
-    const __nv_bfloat16* u = p.aux_in + (size_t)m * p.ld_aux_in + n;
-#pragma unroll
-    for (int j = 0; j < 32; j += 8) {
-      const uint4 uu = ldg16(u + j);
-      f[j + 0] *= gelu_erf_grad(bf16_lo(uu.x)); f[j + 1] *= gelu_erf_grad(bf16_hi(uu.x));
-      f[j + 2] *= gelu_erf_grad(bf16_lo(uu.y)); f[j + 3] *= gelu_erf_grad(bf16_hi(uu.y));
-      f[j + 4] *= gelu_erf_grad(bf16_lo(uu.z)); f[j + 5] *= gelu_erf_grad(bf16_hi(uu.z));
-      f[j + 6] *= gelu_erf_grad(bf16_lo(uu.w)); f[j + 7] *= gelu_erf_grad(bf16_hi(uu.w));
-    }
-  }
-  __nv_bfloat16* d = p.D + (size_t)m * p.ldd + n;
-#pragma unroll
-  for (int j = 0; j < 32; j += 8) {
-    uint4 o;
-    o.x = pack_bf16(f[j], f[j + 1]); o.y = pack_bf16(f[j + 2], f[j + 3]);
-    o.z = pack_bf16(f[j + 4], f[j + 5]); o.w = pack_bf16(f[j + 6], f[j + 7]);
-    stg16(d + j, o);
-  }
-}
-
-// 8 epilogue warps drain one [128 rows x BN cols] accumulator: warp -> (TMEM lane quarter, column half)
-template <int BN>
-__device__ __forceinline__ void epilogue_tile(const GemmKernelParams& p, const DropCtx& drop, uint32_t tmem_acc,
-                                              int warp, int lane, int m_base, int n0, int split) {
-  const int quarter = warp & 3;           // TMEM lane quarter this warp may touch
-  const int colhalf = (warp - 4) >> 2;    // which half of the BN columns
-  constexpr int kColsPerWarp = BN / 2;
-  constexpr int kChunks = kColsPerWarp / 32;
-  const int m = m_base + quarter * 32 + lane;
-  const bool row_ok = m < p.M;
-#pragma unroll 1
-  for (int c = 0; c < kChunks; ++c) {
-    const int n = n0 + colhalf * kColsPerWarp + c * 32;
-    uint32_t v[32];
-    tmem_ld32(tmem_acc + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(colhalf * kColsPerWarp + c * 32), v);
-    tmem_ld_wait();
-    if (n < p.N && row_ok) epilogue_chunk(p, drop, v, m, n, split);
-    __syncwarp();
-  }
-}
-
 // ------------------------------------------------------------------------------------------------------------
 // single-CTA kernel
 // ------------------------------------------------------------------------------------------------------------
 template <int BN>
 struct GemmCfg {
-  static constexpr int kStages = (BN == 256) ? 4 : (BN == 192 ? 5 : 6);
+  static constexpr int kStages = (BN == 256) ? 4 : 5;
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kAccStride = (BN <= 128) ? 128 : 256;  // TMEM columns between the 2 accumulators
   static constexpr int kTmemCols = 2 * kAccStride;            // 256 or 512 (power of two)
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int kPipeBytes = kStages * kStageBytes;
+  static constexpr int kSmemBytes = kPipeBytes + NUM_EPI_WARPS * kEpiStageBytes + 1024 /*align*/ + 256 /*barriers*/;
 };
 
 template <int BN, bool A_MN, bool B_MN>
@@ -165,7 +55,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   using Cfg = GemmCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint8_t* epi_stage = smem + Cfg::kPipeBytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_stage + NUM_EPI_WARPS * kEpiStageBytes);
   uint64_t* empty_bar = full_bar + Cfg::kStages;
   uint64_t* tmem_full = empty_bar + Cfg::kStages;
   uint64_t* tmem_empty = tmem_full + 2;
@@ -273,7 +164,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       const int m0 = (tile / p.tiles_n) * BM, n0 = (tile % p.tiles_n) * BN;
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      epilogue_tile<BN>(p, drop, tmem_base + acc * Cfg::kAccStride, warp, lane, m0, n0, split);
+      epilogue_tile<BN>(p, drop, tmem_base + acc * Cfg::kAccStride, warp, lane, m0, n0, split,
+                        epi_stage + (warp - 4) * kEpiStageBytes);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
@@ -356,10 +248,11 @@ struct Gemm2Cfg {
   static constexpr int kABytes = BM * BK * 2;            // this CTA's 128 A rows
   static constexpr int kBBytes = (BN / 2) * BK * 2;      // this CTA's half of the B tile
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (BN == 256) ? 6 : 8;
+  static constexpr int kStages = (BN == 256) ? 5 : 7;
   static constexpr int kAccStride = (BN <= 128) ? 128 : 256;
   static constexpr int kTmemCols = 2 * kAccStride;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
+  static constexpr int kPipeBytes = kStages * kStageBytes;
+  static constexpr int kSmemBytes = kPipeBytes + NUM_EPI_WARPS * kEpiStageBytes + 1024 + 256;
 };
 
 template <int BN, bool A_MN, bool B_MN>
@@ -369,7 +262,8 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   using Cfg = Gemm2Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint8_t* epi_stage = smem + Cfg::kPipeBytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_stage + NUM_EPI_WARPS * kEpiStageBytes);
   uint64_t* empty_bar = full_bar + Cfg::kStages;
   uint64_t* tmem_full = empty_bar + Cfg::kStages;
   uint64_t* tmem_empty = tmem_full + 2;
@@ -483,7 +377,8 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       const int n0 = (tile % p.tiles_n) * BN;
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      epilogue_tile<BN>(p, drop, tmem_base + acc * Cfg::kAccStride, warp, lane, m0, n0, split);
+      epilogue_tile<BN>(p, drop, tmem_base + acc * Cfg::kAccStride, warp, lane, m0, n0, split,
+                        epi_stage + (warp - 4) * kEpiStageBytes);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
@@ -626,10 +521,9 @@ static Choice choose_config(const b2_gemm_args_t& a) {
   Choice c{0, 128, 1};
   const double l2_bytes_per_cycle = 5500.0;   // ~10 TB/s at ~1.85 GHz, shared by the busy SMs
   for (int pair = 0; pair <= 1; ++pair) {
-    const int bns[3] = {256, 192, 128};
-    for (int bi = 0; bi < 3; ++bi) {
+    const int bns[2] = {256, 128};
+    for (int bi = 0; bi < 2; ++bi) {
       const int bn = bns[bi];
-      if (pair && bn == 192) continue;                       // half tiles of 96 columns break the 64-wide MN chunks
       if (a.N % bn != 0 && (pair || bn != 128)) continue;
       const int tile_m = pair ? 256 : 128;
       const int tiles = (int)((a.M + tile_m - 1) / tile_m) * (int)((a.N + bn - 1) / bn);
@@ -664,17 +558,17 @@ extern "C" int32_t b2_gemm_bf16(const b2_gemm_args_t* a, void* stream_) {
   B2_REQUIRE(a->M > 0 && a->N > 0 && a->K > 0, "b2_gemm_bf16: empty problem M=%lld N=%lld K=%lld",
              (long long)a->M, (long long)a->N, (long long)a->K);
   B2_REQUIRE(a->A && a->B && a->D, "b2_gemm_bf16: null operand pointer");
-  B2_REQUIRE(a->N % 32 == 0, "b2_gemm_bf16: N=%lld must be a multiple of 32", (long long)a->N);
+  B2_REQUIRE(a->N % 64 == 0, "b2_gemm_bf16: N=%lld must be a multiple of 64", (long long)a->N);
   B2_REQUIRE(a->K % 8 == 0 && a->lda % 8 == 0 && a->ldb % 8 == 0 && a->ldd % 8 == 0,
              "b2_gemm_bf16: K and leading dimensions must be multiples of 8 elements (16 B)");
   B2_REQUIRE(((uintptr_t)a->A % 16 == 0) && ((uintptr_t)a->B % 16 == 0) && ((uintptr_t)a->D % 16 == 0),
              "b2_gemm_bf16: operands must be 16-byte aligned");
-  B2_REQUIRE(a->epilogue >= B2_EPI_NONE && a->epilogue <= B2_EPI_GELU_BWD, "b2_gemm_bf16: bad epilogue %d",
+  B2_REQUIRE(a->epilogue >= B2_EPI_NONE && a->epilogue <= B2_EPI_RESIDUAL_F32, "b2_gemm_bf16: bad epilogue %d",
              a->epilogue);
   if (a->epilogue == B2_EPI_BIAS || a->epilogue == B2_EPI_BIAS_GELU || a->epilogue == B2_EPI_BIAS_DROPOUT_RESIDUAL)
     B2_REQUIRE(a->bias != nullptr, "b2_gemm_bf16: epilogue %d needs a bias", a->epilogue);
   if (a->epilogue == B2_EPI_BIAS_DROPOUT_RESIDUAL || a->epilogue == B2_EPI_RESIDUAL ||
-      a->epilogue == B2_EPI_GELU_BWD)
+      a->epilogue == B2_EPI_GELU_BWD || a->epilogue == B2_EPI_RESIDUAL_F32)
     B2_REQUIRE(a->aux_in != nullptr && a->ld_aux_in % 8 == 0, "b2_gemm_bf16: epilogue %d needs aux_in",
                a->epilogue);
   if (a->epilogue == B2_EPI_BIAS_GELU)
@@ -686,12 +580,11 @@ extern "C" int32_t b2_gemm_bf16(const b2_gemm_args_t* a, void* stream_) {
   Choice c = choose_config(*a);
   if (a->force_kernel == 1) c.pair = 0;
   if (a->force_kernel == 2) c.pair = 1;
-  if (a->force_bn == 128 || a->force_bn == 192 || a->force_bn == 256) {
+  if (a->force_bn == 128 || a->force_bn == 256) {
     B2_REQUIRE(a->N % a->force_bn == 0 || (a->force_bn == 128 && !c.pair), "b2_gemm_bf16: force_bn does not divide N");
     c.bn = a->force_bn;
   }
   if (c.pair) {
-    if (c.bn == 192) c.bn = (a->N % 256 == 0) ? 256 : 128;
     B2_REQUIRE(a->N % c.bn == 0, "b2_gemm_bf16: the CTA-pair kernel needs N %% %d == 0 (N=%lld)", c.bn,
                (long long)a->N);
   } else if (a->N % c.bn != 0 && c.bn != 128) {
@@ -718,7 +611,6 @@ extern "C" int32_t b2_gemm_bf16(const b2_gemm_args_t* a, void* stream_) {
     B2_DISPATCH(launch_gemm2, 256)
   } else {
     B2_DISPATCH(launch_gemm, 128)
-    B2_DISPATCH(launch_gemm, 192)
     B2_DISPATCH(launch_gemm, 256)
   }
 #undef B2_DISPATCH

@@ -1,0 +1,188 @@
+// GEMM epilogue: TMEM accumulator -> registers -> fused element-wise math -> HBM, with COALESCED global traffic.
+//
+// tcgen05.ld (32x32b) hands every thread one accumulator ROW.  Storing rows straight from registers makes each
+// warp-wide 16-byte store touch 32 different 128-byte lines (one per row): the first profiles showed the epilogue,
+// not the tensor pipe, bounding every K=768 GEMM (~8k store wavefronts per 128x256 bf16 tile vs 6.1k MMA cycles).
+// Here each epilogue warp owns a 4 KB shared-memory staging tile (32 rows x 128 B, 16-byte chunks XOR-swizzled by
+// row & 7 so both access patterns are bank-conflict free).  Rows go registers -> staging -> global with every
+// warp-wide access covering 4 rows x 128 contiguous bytes (4 full lines); auxiliary inputs (residual, saved
+// pre-activation) take the same path in reverse.
+#pragma once
+#include "common.cuh"
+#include "../../include/b2_ddp_bert.h"
+
+namespace b2 {
+
+struct GemmKernelParams {
+  int M, N, K;
+  int tiles_m, tiles_n, splits, kblocks_per_split, kblocks_total;
+  int epilogue;
+  __nv_bfloat16* D; long long ldd;
+  const __nv_bfloat16* bias;
+  const __nv_bfloat16* aux_in; long long ld_aux_in;
+  __nv_bfloat16* aux_out; long long ld_aux_out;
+  float* partial;  // split-K fp32 partials [splits][M][N]
+  float dropout_p; const unsigned long long* rng; unsigned rng_site;
+};
+
+constexpr int kEpiStageBytes = 32 * 128;   // per epilogue warp
+
+#ifdef __CUDACC__
+__device__ __forceinline__ uint4* stage_ptr(uint8_t* stage, int row, int chunk) {
+  return reinterpret_cast<uint4*>(stage + row * 128 + ((chunk ^ (row & 7)) << 4));
+}
+// coalesced copy of a [32 rows x 128 bytes] tile between global memory (row pitch in bytes) and the staging tile;
+// lane l of step k handles row 4k + l/8, 16-byte chunk l%8.  Rows >= rows_valid are skipped (zero-filled on load).
+__device__ __forceinline__ void tile_g2s(uint8_t* stage, const uint8_t* g, long long pitch, int lane, int rows_valid) {
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int r = 4 * k + (lane >> 3), c = lane & 7;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (r < rows_valid) v = __ldg(reinterpret_cast<const uint4*>(g + (size_t)r * pitch + c * 16));
+    *stage_ptr(stage, r, c) = v;
+  }
+}
+__device__ __forceinline__ void tile_s2g(uint8_t* stage, uint8_t* g, long long pitch, int lane, int rows_valid) {
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int r = 4 * k + (lane >> 3), c = lane & 7;
+    const uint4 v = *stage_ptr(stage, r, c);
+    if (r < rows_valid) *reinterpret_cast<uint4*>(g + (size_t)r * pitch + c * 16) = v;
+  }
+}
+// this thread's own row (row == lane) of the staging tile: 8 chunks of 16 bytes
+__device__ __forceinline__ void row_write_bf16(uint8_t* stage, int lane, const float (&f)[64]) {
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    uint4 o;
+    o.x = pack_bf16(f[8 * c + 0], f[8 * c + 1]); o.y = pack_bf16(f[8 * c + 2], f[8 * c + 3]);
+    o.z = pack_bf16(f[8 * c + 4], f[8 * c + 5]); o.w = pack_bf16(f[8 * c + 6], f[8 * c + 7]);
+    *stage_ptr(stage, lane, c) = o;
+  }
+}
+__device__ __forceinline__ void row_read_bf16(uint8_t* stage, int lane, float (&r)[64]) {
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const uint4 t = *stage_ptr(stage, lane, c);
+    r[8 * c + 0] = bf16_lo(t.x); r[8 * c + 1] = bf16_hi(t.x); r[8 * c + 2] = bf16_lo(t.y); r[8 * c + 3] = bf16_hi(t.y);
+    r[8 * c + 4] = bf16_lo(t.z); r[8 * c + 5] = bf16_hi(t.z); r[8 * c + 6] = bf16_lo(t.w); r[8 * c + 7] = bf16_hi(t.w);
+  }
+}
+
+// 8 epilogue warps drain one [128 rows x BN cols] accumulator: warp -> (TMEM lane quarter, column half)
+template <int BN>
+__device__ __forceinline__ void epilogue_tile(const GemmKernelParams& p, const DropCtx& drop, uint32_t tmem_acc,
+                                              int warp, int lane, int m_base, int n0, int split, uint8_t* stage) {
+  static_assert(BN == 128 || BN == 256, "epilogue works on 64-column groups per warp half");
+  const int quarter = warp & 3;           // TMEM lane quarter this warp may touch
+  const int colhalf = (warp - 4) >> 2;    // which half of the BN columns
+  constexpr int kColsPerWarp = BN / 2;
+  const int row0 = m_base + quarter * 32;
+  const int rows_valid = p.M - row0;      // <= 0: nothing to write; >= 32: full tile
+  const int m = row0 + lane;
+  const uint32_t taddr = tmem_acc + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(colhalf * kColsPerWarp);
+
+  if (p.epilogue == B2_EPI_PARTIAL_F32 || p.epilogue == B2_EPI_RESIDUAL_F32) {
+    // ---- fp32 outputs: 32 columns (128 bytes) per group ----
+    const bool partial = p.epilogue == B2_EPI_PARTIAL_F32;
+    float* dst_base = partial ? p.partial + (size_t)split * p.M * p.N : reinterpret_cast<float*>(p.D);
+    const long long dst_ld = partial ? (long long)p.N : p.ldd;
+#pragma unroll 1
+    for (int c = 0; c < kColsPerWarp / 32; ++c) {
+      const int n = n0 + colhalf * kColsPerWarp + c * 32;
+      uint32_t v[32];
+      tmem_ld32(taddr + c * 32, v);
+      tmem_ld_wait();
+      if (n < p.N && rows_valid > 0) {
+        if (!partial) {
+          const float* aux = reinterpret_cast<const float*>(p.aux_in) + (size_t)row0 * p.ld_aux_in + n;
+          tile_g2s(stage, reinterpret_cast<const uint8_t*>(aux), p.ld_aux_in * 4, lane, rows_valid);
+          __syncwarp();
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const uint4 t = *stage_ptr(stage, lane, k);
+            v[4 * k + 0] = __float_as_uint(__uint_as_float(v[4 * k + 0]) + __uint_as_float(t.x));
+            v[4 * k + 1] = __float_as_uint(__uint_as_float(v[4 * k + 1]) + __uint_as_float(t.y));
+            v[4 * k + 2] = __float_as_uint(__uint_as_float(v[4 * k + 2]) + __uint_as_float(t.z));
+            v[4 * k + 3] = __float_as_uint(__uint_as_float(v[4 * k + 3]) + __uint_as_float(t.w));
+          }
+          __syncwarp();
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          *stage_ptr(stage, lane, k) = make_uint4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+        __syncwarp();
+        tile_s2g(stage, reinterpret_cast<uint8_t*>(dst_base + (size_t)row0 * dst_ld + n), dst_ld * 4, lane, rows_valid);
+      }
+      __syncwarp();
+    }
+    return;
+  }
+
+  // ---- bf16 outputs: 64 columns (128 bytes) per group ----
+#pragma unroll 1
+  for (int g = 0; g < kColsPerWarp / 64; ++g) {
+    const int n = n0 + colhalf * kColsPerWarp + g * 64;
+    float f[64];
+    {
+      uint32_t v0[32], v1[32];
+      tmem_ld32(taddr + g * 64, v0);
+      tmem_ld32(taddr + g * 64 + 32, v1);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        f[j] = __uint_as_float(v0[j]);
+        f[32 + j] = __uint_as_float(v1[j]);
+      }
+    }
+    if (n < p.N && rows_valid > 0) {
+      if (p.bias != nullptr) {
+#pragma unroll
+        for (int j = 0; j < 64; j += 8) {
+          const uint4 b = ldg16(p.bias + n + j);
+          f[j + 0] += bf16_lo(b.x); f[j + 1] += bf16_hi(b.x); f[j + 2] += bf16_lo(b.y); f[j + 3] += bf16_hi(b.y);
+          f[j + 4] += bf16_lo(b.z); f[j + 5] += bf16_hi(b.z); f[j + 6] += bf16_lo(b.w); f[j + 7] += bf16_hi(b.w);
+        }
+      }
+      if (p.epilogue == B2_EPI_BIAS_GELU) {
+        // keep the pre-activation (bf16) for the backward pass, emit gelu(pre-activation)
+        row_write_bf16(stage, lane, f);
+        __syncwarp();
+        tile_s2g(stage, reinterpret_cast<uint8_t*>(p.aux_out + (size_t)row0 * p.ld_aux_out + n), p.ld_aux_out * 2, lane,
+                 rows_valid);
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 64; ++j) f[j] = gelu_erf(bf16_round(f[j]));
+      } else if (p.epilogue == B2_EPI_BIAS_DROPOUT_RESIDUAL || p.epilogue == B2_EPI_RESIDUAL ||
+                 p.epilogue == B2_EPI_GELU_BWD) {
+        tile_g2s(stage, reinterpret_cast<const uint8_t*>(p.aux_in + (size_t)row0 * p.ld_aux_in + n), p.ld_aux_in * 2,
+                 lane, rows_valid);
+        __syncwarp();
+        float r[64];
+        row_read_bf16(stage, lane, r);
+        __syncwarp();
+        if (p.epilogue == B2_EPI_BIAS_DROPOUT_RESIDUAL) {
+#pragma unroll
+          for (int j = 0; j < 64; j += 8) {
+            const uint32_t keep = dropout_keep8(drop, (unsigned long long)m * p.N + n + j);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) f[j + i] = (((keep >> i) & 1u) ? f[j + i] * drop.scale : 0.f) + r[j + i];
+          }
+        } else if (p.epilogue == B2_EPI_RESIDUAL) {
+#pragma unroll
+          for (int j = 0; j < 64; ++j) f[j] += r[j];
+        } else {
+#pragma unroll
+          for (int j = 0; j < 64; ++j) f[j] *= gelu_erf_grad(r[j]);
+        }
+      }
+      row_write_bf16(stage, lane, f);
+      __syncwarp();
+      tile_s2g(stage, reinterpret_cast<uint8_t*>(p.D + (size_t)row0 * p.ldd + n), p.ldd * 2, lane, rows_valid);
+    }
+    __syncwarp();
+  }
+}
+#endif  // __CUDACC__
+
+}  // namespace b2

@@ -171,7 +171,7 @@ __global__ void head_bwd_k2(const float* __restrict__ d_pre, const __nv_bfloat16
 //     grid = (batch, H/64), 8 warps: warp w sums its eighth of the j range for 64 columns (2 per lane), smem reduce
 __global__ void __launch_bounds__(256) head_bwd_k3(const float* __restrict__ d_pre,
                                                   const __nv_bfloat16* __restrict__ Wp, int seq, int H,
-                                                  __nv_bfloat16* __restrict__ d_hidden) {
+                                                  void* __restrict__ d_hidden, int out_f32) {
   __shared__ float red[8][64];
   const int b = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -191,7 +191,9 @@ __global__ void __launch_bounds__(256) head_bwd_k3(const float* __restrict__ d_p
     float s = 0.f;
 #pragma unroll
     for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
-    d_hidden[(size_t)b * seq * H + blockIdx.y * 64 + threadIdx.x] = __float2bfloat16_rn(s);
+    const size_t o = (size_t)b * seq * H + blockIdx.y * 64 + threadIdx.x;
+    if (out_f32) reinterpret_cast<float*>(d_hidden)[o] = s;
+    else reinterpret_cast<__nv_bfloat16*>(d_hidden)[o] = __float2bfloat16_rn(s);
   }
 }
 
@@ -235,8 +237,8 @@ extern "C" int32_t b2_ce_fwd_bwd(const float* logits, const int64_t* labels, int
 extern "C" int32_t b2_head_bwd(const float* dlogits, const void* hidden_states, const void* pooled, int64_t batch,
                                int64_t seq, int64_t hidden, const void* pool_w, const void* cls_w, int64_t num_labels,
                                float dropout_p, const void* rng_state, uint32_t rng_site, void* d_pool_w,
-                               void* d_pool_b, void* d_cls_w, void* d_cls_b, void* d_hidden, float* scratch,
-                               void* stream_) {
+                               void* d_pool_b, void* d_cls_w, void* d_cls_b, void* d_hidden, int32_t d_hidden_fp32,
+                               float* scratch, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   B2_REQUIRE(dlogits && hidden_states && pooled && pool_w && cls_w && d_pool_w && d_pool_b && d_cls_w && d_cls_b &&
                  d_hidden && scratch,
@@ -244,7 +246,7 @@ extern "C" int32_t b2_head_bwd(const float* dlogits, const void* hidden_states, 
   B2_REQUIRE(batch > 0 && seq > 0, "head_bwd: empty batch");
   B2_REQUIRE(hidden % 256 == 0 && hidden / 8 <= 1024, "head_bwd: hidden=%lld unsupported", (long long)hidden);
   B2_REQUIRE(num_labels <= 64, "head_bwd: num_labels=%lld > 64", (long long)num_labels);
-  B2_CUDA(cudaMemsetAsync(d_hidden, 0, (size_t)batch * seq * hidden * 2, stream));
+  B2_CUDA(cudaMemsetAsync(d_hidden, 0, (size_t)batch * seq * hidden * (d_hidden_fp32 ? 4 : 2), stream));
   head_bwd_k1<<<(unsigned)((hidden + 255) / 256), 256, 0, stream>>>(
       dlogits, (const __nv_bfloat16*)pooled, (int)batch, (int)hidden, (const __nv_bfloat16*)cls_w, (int)num_labels,
       dropout_p, (const unsigned long long*)rng_state, rng_site, scratch, (__nv_bfloat16*)d_cls_w,
@@ -257,7 +259,7 @@ extern "C" int32_t b2_head_bwd(const float* dlogits, const void* hidden_states, 
   B2_CUDA(cudaGetLastError());
   count_launches(1);
   head_bwd_k3<<<dim3((unsigned)batch, (unsigned)(hidden / 64)), 256, 0, stream>>>(scratch, (const __nv_bfloat16*)pool_w, (int)seq,
-                                                                      (int)hidden, (__nv_bfloat16*)d_hidden);
+                                                                      (int)hidden, d_hidden, d_hidden_fp32 ? 1 : 0);
   B2_CUDA(cudaGetLastError());
   count_launches(1);
   return 0;

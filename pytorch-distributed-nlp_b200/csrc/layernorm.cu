@@ -31,12 +31,14 @@ __global__ void __launch_bounds__(128) layernorm_fwd_kernel(const __nv_bfloat16*
 
 // mode 0: dropout mask (if any) applies to the LN *input* branch -> emit dx_drop = dx*mask*scale (encoder LNs)
 // mode 1: dropout mask applies to the LN *output* (embeddings: y = dropout(LN(x))) -> dy is masked on load
-template <int VPL>
+// DY_F32 / DX_F32: the gradient flowing along the residual stream (dy in, dx out) is fp32 in the training engine so
+// that 12 layers of residual additions do not each round it to bf16; dx_drop (what the tensor cores read) is bf16.
+template <int VPL, bool DY_F32, bool DX_F32>
 __global__ void __launch_bounds__(256) layernorm_bwd_kernel(
-    const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ dy_add,
+    const void* __restrict__ dy_, const void* __restrict__ dy_add_,
     const __nv_bfloat16* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ rstd,
     const __nv_bfloat16* __restrict__ gamma, int rows, float dropout_p, const unsigned long long* rng,
-    unsigned rng_site, int mode, __nv_bfloat16* __restrict__ dx, __nv_bfloat16* __restrict__ dx_drop,
+    unsigned rng_site, int mode, void* __restrict__ dx_, __nv_bfloat16* __restrict__ dx_drop,
     float* __restrict__ partials /* [gridDim.x][3][H] */) {
   constexpr int H = VPL * 256;
   constexpr int WARPS = 8;
@@ -51,10 +53,12 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(
 
   for (int row = blockIdx.x * WARPS + warp; row < rows; row += gridDim.x * WARPS) {
     float dyv[VPL * 8], xv[VPL * 8];
-    load_row<VPL>(dy + (size_t)row * H, lane, dyv);
-    if (dy_add != nullptr) {
+    if (DY_F32) load_row_f32<VPL>(reinterpret_cast<const float*>(dy_) + (size_t)row * H, lane, dyv);
+    else load_row<VPL>(reinterpret_cast<const __nv_bfloat16*>(dy_) + (size_t)row * H, lane, dyv);
+    if (dy_add_ != nullptr) {
       float t[VPL * 8];
-      load_row<VPL>(dy_add + (size_t)row * H, lane, t);
+      if (DY_F32) load_row_f32<VPL>(reinterpret_cast<const float*>(dy_add_) + (size_t)row * H, lane, t);
+      else load_row<VPL>(reinterpret_cast<const __nv_bfloat16*>(dy_add_) + (size_t)row * H, lane, t);
 #pragma unroll
       for (int i = 0; i < VPL * 8; ++i) dyv[i] += t[i];
     }
@@ -83,7 +87,8 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(
     float dxv[VPL * 8];
 #pragma unroll
     for (int i = 0; i < VPL * 8; ++i) dxv[i] = rs * (dyv[i] * g[i] - s1 - xv[i] * s2);
-    store_row<VPL>(dx + (size_t)row * H, lane, dxv);
+    if (DX_F32) store_row_f32<VPL>(reinterpret_cast<float*>(dx_) + (size_t)row * H, lane, dxv);
+    else store_row<VPL>(reinterpret_cast<__nv_bfloat16*>(dx_) + (size_t)row * H, lane, dxv);
     if (mode == 0) {
       if (dx_drop != nullptr) {
 #pragma unroll
@@ -209,8 +214,8 @@ int32_t launch_colsum(const void* x, int64_t rows, int64_t cols, int64_t ldx, co
 
 int32_t launch_layernorm_bwd(const void* dy, const void* dy_add, const void* x, const float* mean, const float* rstd,
                              const void* gamma, int64_t rows, int64_t hidden, float dropout_p, const void* rng,
-                             uint32_t site, int mode, void* dx, void* dx_drop, void* d_gamma, void* d_beta,
-                             void* d_bias, float* scratch, int64_t scratch_bytes, cudaStream_t stream) {
+                             uint32_t site, int mode, int dy_f32, int dx_f32, void* dx, void* dx_drop, void* d_gamma,
+                             void* d_beta, void* d_bias, float* scratch, int64_t scratch_bytes, cudaStream_t stream) {
   B2_REQUIRE(hidden % 256 == 0 && hidden >= 256 && hidden <= 1024, "layernorm: hidden=%lld unsupported",
              (long long)hidden);
   int nblocks = (int)(scratch_bytes / (3 * hidden * 4));
@@ -219,17 +224,21 @@ int32_t launch_layernorm_bwd(const void* dy, const void* dy_add, const void* x, 
   const int max_useful = (int)((rows + 7) / 8);
   if (nblocks > max_useful) nblocks = max_useful;
   B2_REQUIRE(nblocks >= 1, "layernorm_bwd: scratch too small");
-#define B2_LN_BWD(VPL_)                                                                                        \
-  case VPL_:                                                                                                   \
-    layernorm_bwd_kernel<VPL_><<<nblocks, 256, 0, stream>>>(                                                   \
-        (const __nv_bfloat16*)dy, (const __nv_bfloat16*)dy_add, (const __nv_bfloat16*)x, mean, rstd,           \
-        (const __nv_bfloat16*)gamma, (int)rows, dropout_p, (const unsigned long long*)rng, site, mode,         \
-        (__nv_bfloat16*)dx, (__nv_bfloat16*)dx_drop, scratch);                                                 \
+#define B2_LN_ARGS                                                                                           \
+  dy, dy_add, (const __nv_bfloat16*)x, mean, rstd, (const __nv_bfloat16*)gamma, (int)rows, dropout_p,        \
+      (const unsigned long long*)rng, site, mode, dx, (__nv_bfloat16*)dx_drop, scratch
+#define B2_LN_BWD(VPL_)                                                                                      \
+  case VPL_:                                                                                                 \
+    if (dy_f32 && dx_f32) layernorm_bwd_kernel<VPL_, true, true><<<nblocks, 256, 0, stream>>>(B2_LN_ARGS);   \
+    else if (dy_f32) layernorm_bwd_kernel<VPL_, true, false><<<nblocks, 256, 0, stream>>>(B2_LN_ARGS);       \
+    else layernorm_bwd_kernel<VPL_, false, false><<<nblocks, 256, 0, stream>>>(B2_LN_ARGS);                  \
     break;
+  B2_REQUIRE(dy_f32 || !dx_f32, "layernorm_bwd: fp32 dx with bf16 dy is not on the path");
   switch ((int)(hidden / 256)) {
     B2_LN_BWD(1) B2_LN_BWD(2) B2_LN_BWD(3) B2_LN_BWD(4)
   }
 #undef B2_LN_BWD
+#undef B2_LN_ARGS
   B2_CUDA(cudaGetLastError());
   count_launches(1);
   colsum_finish_kernel<<<(unsigned)((3 * hidden + 31) / 32), 256, 0, stream>>>(
@@ -268,16 +277,18 @@ extern "C" int32_t b2_layernorm_fwd(const void* x, const void* gamma, const void
 
 extern "C" int32_t b2_layernorm_bwd(const void* dy, const void* dy_add, const void* x, const float* mean,
                                     const float* rstd, const void* gamma, int64_t rows, int64_t hidden,
-                                    float dropout_p, const void* rng_state, uint32_t rng_site, void* dx,
-                                    void* dx_drop, void* d_gamma, void* d_beta, void* d_bias,
+                                    float dropout_p, const void* rng_state, uint32_t rng_site, int32_t grad_fp32,
+                                    void* dx, void* dx_drop, void* d_gamma, void* d_beta, void* d_bias,
                                     float* scratch_partials, int64_t scratch_partials_bytes, void* stream_) {
   B2_REQUIRE(dy && x && mean && rstd && gamma && dx && d_gamma && d_beta && scratch_partials,
              "layernorm_bwd: null pointer");
   B2_REQUIRE(rows > 0, "layernorm_bwd: rows=%lld", (long long)rows);
   B2_REQUIRE(!(dropout_p > 0.f) || (rng_state && dx_drop), "layernorm_bwd: dropout needs rng_state and dx_drop");
-  return launch_layernorm_bwd(dy, dy_add, x, mean, rstd, gamma, rows, hidden, dropout_p, rng_state, rng_site, 0, dx,
-                              dropout_p > 0.f ? dx_drop : nullptr, d_gamma, d_beta, d_bias, scratch_partials,
-                              scratch_partials_bytes, (cudaStream_t)stream_);
+  B2_REQUIRE(!grad_fp32 || dx_drop, "layernorm_bwd: the fp32 gradient stream needs dx_drop (the bf16 GEMM operand)");
+  return launch_layernorm_bwd(dy, dy_add, x, mean, rstd, gamma, rows, hidden, dropout_p, rng_state, rng_site, 0,
+                              grad_fp32 ? 1 : 0, grad_fp32 ? 1 : 0, dx,
+                              (dropout_p > 0.f || grad_fp32) ? dx_drop : nullptr, d_gamma, d_beta, d_bias,
+                              scratch_partials, scratch_partials_bytes, (cudaStream_t)stream_);
 }
 
 extern "C" int32_t b2_colsum(const void* x, int64_t rows, int64_t cols, int64_t ldx, void* out,

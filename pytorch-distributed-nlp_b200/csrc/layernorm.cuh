@@ -27,6 +27,26 @@ __device__ __forceinline__ void store_row(__nv_bfloat16* __restrict__ row, int l
     stg16(row + (vv * 32 + lane) * 8, o);
   }
 }
+template <int VPL>
+__device__ __forceinline__ void load_row_f32(const float* __restrict__ row, int lane, float (&v)[VPL * 8]) {
+#pragma unroll
+  for (int vv = 0; vv < VPL; ++vv) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(row + (vv * 32 + lane) * 8));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(row + (vv * 32 + lane) * 8 + 4));
+    v[vv * 8 + 0] = a.x; v[vv * 8 + 1] = a.y; v[vv * 8 + 2] = a.z; v[vv * 8 + 3] = a.w;
+    v[vv * 8 + 4] = b.x; v[vv * 8 + 5] = b.y; v[vv * 8 + 6] = b.z; v[vv * 8 + 7] = b.w;
+  }
+}
+template <int VPL>
+__device__ __forceinline__ void store_row_f32(float* __restrict__ row, int lane, const float (&v)[VPL * 8]) {
+#pragma unroll
+  for (int vv = 0; vv < VPL; ++vv) {
+    *reinterpret_cast<float4*>(row + (vv * 32 + lane) * 8) =
+        make_float4(v[vv * 8 + 0], v[vv * 8 + 1], v[vv * 8 + 2], v[vv * 8 + 3]);
+    *reinterpret_cast<float4*>(row + (vv * 32 + lane) * 8 + 4) =
+        make_float4(v[vv * 8 + 4], v[vv * 8 + 5], v[vv * 8 + 6], v[vv * 8 + 7]);
+  }
+}
 // two-pass mean / variance in registers (biased variance, like torch.nn.LayerNorm)
 template <int VPL>
 __device__ __forceinline__ void row_stats(const float (&v)[VPL * 8], float eps, float& mean, float& rstd) {
@@ -68,7 +88,7 @@ int32_t launch_colsum(const void* x, int64_t rows, int64_t cols, int64_t ldx, co
                       void* out, float* scratch, int64_t scratch_bytes, cudaStream_t stream);
 int32_t launch_layernorm_bwd(const void* dy, const void* dy_add, const void* x, const float* mean, const float* rstd,
                              const void* gamma, int64_t rows, int64_t hidden, float dropout_p, const void* rng,
-                             uint32_t site, int mode, void* dx, void* dx_drop, void* d_gamma, void* d_beta,
-                             void* d_bias, float* scratch, int64_t scratch_bytes, cudaStream_t stream);
+                             uint32_t site, int mode, int dy_f32, int dx_f32, void* dx, void* dx_drop, void* d_gamma,
+                             void* d_beta, void* d_bias, float* scratch, int64_t scratch_bytes, cudaStream_t stream);
 
 }  // namespace b2

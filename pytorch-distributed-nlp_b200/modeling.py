@@ -449,7 +449,10 @@ class _Engine:
                 for _ in range(nl)],
             "pooled": e(B, H), "logits": e(B, self.C, dtype=f32), "loss": e((), dtype=f32),
             "dlogits": e(B, self.C, dtype=f32), "dloss_logits": e(B, self.C, dtype=f32),
-            "dxA": e(M, H), "dxB": e(M, H), "dz": e(M, H), "dzd": e(M, H), "dz1": e(M, H), "dz1d": e(M, H),
+            # gradient of the residual stream: fp32 (12 layers of residual adds would otherwise each round it to bf16);
+            # dzd / dz1d are the bf16 (dropout-masked) copies the tensor cores consume
+            "dxA": e(M, H, dtype=f32), "dxB": e(M, H, dtype=f32), "dz": e(M, H, dtype=f32), "dzd": e(M, H),
+            "dz1": e(M, H, dtype=f32), "dz1d": e(M, H), "emb_dx": e(M, H),
             "dU": e(M, I), "dctx": e(M, H), "dqkv": e(M, 3 * H), "head_scratch": e(B, H, dtype=f32),
             "dq_accum": e(M, H, dtype=f32) if S > 128 else None,
             "zeros_tt": torch.zeros(B, S, dtype=torch.int64, device=dev),
@@ -594,7 +597,7 @@ class _Engine:
         L.call("b2_head_bwd", dl.data_ptr(), x_last.data_ptr(), ws["pooled"].data_ptr(), B, S, H,
                w("bert.pooler.dense.weight"), w("classifier.weight"), self.C, p_c, rng, 1 + 3 * self.nl,
                g("bert.pooler.dense.weight"), g("bert.pooler.dense.bias"), g("classifier.weight"),
-               g("classifier.bias"), ws["dxA"].data_ptr(), ws["head_scratch"].data_ptr(), s)
+               g("classifier.bias"), ws["dxA"].data_ptr(), 1, ws["head_scratch"].data_ptr(), s)
         if hooks is not None:
             hooks._bucket_ready(len(self.lay.buckets) - 1)
         dx, dx_other = ws["dxA"], ws["dxB"]
@@ -604,10 +607,10 @@ class _Engine:
             pre = "bert.encoder.layer.%d." % l
             # --- BertOutput: LN2 backward (+ dropout mask, bias grad), FFN2 wgrad/dgrad(+GELU')
             L.call("b2_layernorm_bwd", dx.data_ptr(), None, a["z2"].data_ptr(), a["mean2"].data_ptr(),
-                   a["rstd2"].data_ptr(), w(pre + "output.LayerNorm.weight"), M, H, p_h, rng, 3 + 3 * l,
+                   a["rstd2"].data_ptr(), w(pre + "output.LayerNorm.weight"), M, H, p_h, rng, 3 + 3 * l, 1,
                    ws["dz"].data_ptr(), ws["dzd"].data_ptr(), g(pre + "output.LayerNorm.weight"),
                    g(pre + "output.LayerNorm.bias"), g(pre + "output.dense.bias"), scratch, scratch_bytes, s)
-            dy2 = ws["dzd"] if p_h > 0 else ws["dz"]
+            dy2 = ws["dzd"]
             self.gemm(H, I, M, dy2.data_ptr(), H, MN, a["h"].data_ptr(), I, MN, g(pre + "output.dense.weight"), I,
                       split=True)
             self.gemm(M, I, H, dy2.data_ptr(), H, KM, w(pre + "output.dense.weight"), I, MN, ws["dU"].data_ptr(), I,
@@ -618,14 +621,14 @@ class _Engine:
             self.gemm(I, H, M, ws["dU"].data_ptr(), I, MN, a["x1"].data_ptr(), H, MN,
                       g(pre + "intermediate.dense.weight"), H, split=True)
             self.gemm(M, H, I, ws["dU"].data_ptr(), I, KM, w(pre + "intermediate.dense.weight"), H, MN,
-                      dx_other.data_ptr(), H, L.EPI_RESIDUAL, aux_in=ws["dz"].data_ptr(), ld_aux_in=H)
+                      dx_other.data_ptr(), H, L.EPI_RESIDUAL_F32, aux_in=ws["dz"].data_ptr(), ld_aux_in=H)
             # --- BertSelfOutput
             L.call("b2_layernorm_bwd", dx_other.data_ptr(), None, a["z1"].data_ptr(), a["mean1"].data_ptr(),
-                   a["rstd1"].data_ptr(), w(pre + "attention.output.LayerNorm.weight"), M, H, p_h, rng, 2 + 3 * l,
+                   a["rstd1"].data_ptr(), w(pre + "attention.output.LayerNorm.weight"), M, H, p_h, rng, 2 + 3 * l, 1,
                    ws["dz1"].data_ptr(), ws["dz1d"].data_ptr(), g(pre + "attention.output.LayerNorm.weight"),
                    g(pre + "attention.output.LayerNorm.bias"), g(pre + "attention.output.dense.bias"), scratch,
                    scratch_bytes, s)
-            dy1 = ws["dz1d"] if p_h > 0 else ws["dz1"]
+            dy1 = ws["dz1d"]
             self.gemm(H, H, M, dy1.data_ptr(), H, MN, a["ctx"].data_ptr(), H, MN,
                       g(pre + "attention.output.dense.weight"), H, split=True)
             self.gemm(M, H, H, dy1.data_ptr(), H, KM, w(pre + "attention.output.dense.weight"), H, MN,
@@ -639,16 +642,16 @@ class _Engine:
             self.gemm(3 * H, H, M, ws["dqkv"].data_ptr(), 3 * H, MN, x_in.data_ptr(), H, MN,
                       g(pre + "attention.self.query.weight"), H, split=True)
             self.gemm(M, H, 3 * H, ws["dqkv"].data_ptr(), 3 * H, KM, w(pre + "attention.self.query.weight"), H, MN,
-                      dx.data_ptr(), H, L.EPI_RESIDUAL, aux_in=ws["dz1"].data_ptr(), ld_aux_in=H)
+                      dx.data_ptr(), H, L.EPI_RESIDUAL_F32, aux_in=ws["dz1"].data_ptr(), ld_aux_in=H)
             if hooks is not None:
                 hooks._bucket_ready(1 + l)
-        L.call("b2_embed_bwd", dx.data_ptr(), ws["emb_pre"].data_ptr(), ws["emb_mean"].data_ptr(),
+        L.call("b2_embed_bwd", dx.data_ptr(), 1, ws["emb_pre"].data_ptr(), ws["emb_mean"].data_ptr(),
                ws["emb_rstd"].data_ptr(), w("bert.embeddings.LayerNorm.weight"), ws["ids32"].data_ptr(),
                ws["tt32"].data_ptr(), B, S, H, cfg.vocab_size, cfg.type_vocab_size,
                -1 if getattr(cfg, "pad_token_id", None) is None else int(cfg.pad_token_id), p_h, rng, 0,
                g("bert.embeddings.word_embeddings.weight"), g("bert.embeddings.position_embeddings.weight"),
                g("bert.embeddings.token_type_embeddings.weight"), g("bert.embeddings.LayerNorm.weight"),
-               g("bert.embeddings.LayerNorm.bias"), ws["dxB"].data_ptr(), scratch, scratch_bytes,
+               g("bert.embeddings.LayerNorm.bias"), ws["emb_dx"].data_ptr(), scratch, scratch_bytes,
                self.owner.data_ptr(), s)
         if hooks is not None:
             hooks._bucket_ready(0)

@@ -49,9 +49,20 @@ def test_layernorm_fwd_bwd(cuda_dev, H):
         scratch = torch.empty(4 << 20, dtype=torch.uint8, device=dev)
         rs = rng_state(dev)
         L.call("b2_layernorm_bwd", dy.data_ptr(), None, x.data_ptr(), mean.data_ptr(), rstd.data_ptr(), g.data_ptr(),
-               rows, H, p, rs.data_ptr(), 11, dx.data_ptr(), dxd.data_ptr(), dg.data_ptr(), db.data_ptr(),
+               rows, H, p, rs.data_ptr(), 11, 0, dx.data_ptr(), dxd.data_ptr(), dg.data_ptr(), db.data_ptr(),
                dbias.data_ptr(), scratch.data_ptr(), scratch.numel(), S())
+        # fp32 gradient stream variant: fp32 dy in, fp32 dx out, bf16 dx_drop always written
+        dy32, dx32, dxd32 = dy.float(), torch.empty(rows, H, device=dev), torch.empty_like(x)
+        dg2, db2, dbias2 = (torch.empty(H, dtype=bf, device=dev) for _ in range(3))
+        L.call("b2_layernorm_bwd", dy32.data_ptr(), None, x.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+               g.data_ptr(), rows, H, p, rs.data_ptr(), 11, 1, dx32.data_ptr(), dxd32.data_ptr(), dg2.data_ptr(),
+               db2.data_ptr(), dbias2.data_ptr(), scratch.data_ptr(), scratch.numel(), S())
         torch.cuda.synchronize()
+        assert rel_l2(dx32, dx.float()) < 5e-3 and rel_l2(dg2.float(), dg.float()) < 1e-2
+        if p > 0:
+            assert torch.equal(dxd32, dxd)
+        else:
+            assert torch.equal(dxd32, dx32.to(bf))
         for t in (xr, gr, br):
             t.grad = None
         yr = F.layer_norm(xr, (H,), gr, br, 1e-12)
@@ -118,7 +129,7 @@ def test_embed_fwd_bwd(cuda_dev, p):
     L.call("b2_embed_owner_init", owner.data_ptr(), V, S())
     for _ in range(2):  # twice: the owner table must re-arm itself
         d_word.zero_()
-        L.call("b2_embed_bwd", dy.data_ptr(), pre.data_ptr(), mean.data_ptr(), rstd.data_ptr(), gam.data_ptr(),
+        L.call("b2_embed_bwd", dy.data_ptr(), 0, pre.data_ptr(), mean.data_ptr(), rstd.data_ptr(), gam.data_ptr(),
                ids32.data_ptr(), tt32.data_ptr(), B, Sq, H, V, T, 0, p, rs.data_ptr(), 0, d_word.data_ptr(),
                d_pos.data_ptr(), d_typ.data_ptr(), d_g.data_ptr(), d_b.data_ptr(), scratch_dx.data_ptr(),
                scratch.data_ptr(), scratch.numel(), owner.data_ptr(), S())
@@ -230,7 +241,7 @@ def test_head_and_ce(cuda_dev, p):
     scratch = torch.empty(B, H, dtype=torch.float32, device=dev)
     L.call("b2_head_bwd", dlog.data_ptr(), hs.data_ptr(), pooled.data_ptr(), B, Sq, H, Wp.data_ptr(), Wc.data_ptr(),
            C, p, rs.data_ptr(), 37, grads["Wp"].data_ptr(), grads["bp"].data_ptr(), grads["Wc"].data_ptr(),
-           grads["bc"].data_ptr(), d_hidden.data_ptr(), scratch.data_ptr(), S())
+           grads["bc"].data_ptr(), d_hidden.data_ptr(), 0, scratch.data_ptr(), S())
     torch.cuda.synchronize()
     lr.backward()
     assert rel_l2(grads["Wc"].float(), Wcr.grad) < 2e-2
