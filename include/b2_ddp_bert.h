@@ -28,7 +28,7 @@ extern "C" {
 /* ------------------------------------------------------------------------------------------------------ */
 const char* b2_last_error(void);
 int32_t b2_abi_version(void);             /* bumped when a struct below changes */
-#define B2_ABI_VERSION 3
+#define B2_ABI_VERSION 4
 int64_t b2_launch_count(void);            /* kernels launched by this library so far (process-wide) */
 
 /* ------------------------------------------------------------------------------------------------------ */
@@ -73,6 +73,7 @@ typedef struct b2_gemm_args {
   int32_t force_bn;       /* 0 = auto, else 128 / 192 / 256 (tests, tuning)                                  */
   int32_t force_splits;   /* 0 = auto, else >= 1                                                             */
   int32_t force_kernel;   /* 0 = auto, 1 = single-CTA 128xBN kernel, 2 = CTA-pair (cta_group::2) 256xBN kernel        */
+  void* debug_timing;     /* NULL, or device int64[grid][8]: clock64 stamps of the CTA-pair kernel's phases          */
 } b2_gemm_args_t;
 
 int32_t b2_gemm_bf16(const b2_gemm_args_t* args, void* stream);

@@ -274,6 +274,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
   const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  if (threadIdx.x == 0) stamp(p, 0);                                  // kernel entry
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
@@ -295,6 +296,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   cluster_sync_all();   // barrier inits + TMEM allocation visible pair-wide before any remote arrive / TMA credit
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
+  if (threadIdx.x == 0) stamp(p, 1);                                  // setup done
 
   const int num_work = p.tiles_m * p.tiles_n * p.splits;   // tiles_m counts 256-row tiles here
 
@@ -351,6 +353,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         const uint32_t d_tmem = tmem_base + acc * Cfg::kAccStride;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
+          if (w == pair && kb == kb0) stamp(p, 2);                    // first operands landed
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
           const uint32_t sb = sa + Cfg::kABytes;
@@ -364,6 +367,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
         }
         umma_commit_2sm(&tmem_full[acc]);
+        if (w + npairs >= num_work) stamp(p, 3);                      // last MMA of the last tile issued
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -376,11 +380,13 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       const int m0 = (tile / p.tiles_n) * (2 * BM) + (int)rank * BM;
       const int n0 = (tile % p.tiles_n) * BN;
       mbar_wait(&tmem_full[acc], acc_phase);
+      if (warp == 4 && lane == 0 && w + npairs >= num_work) stamp(p, 4);   // last accumulator complete
       tc_fence_after();
       epilogue_tile<BN>(p, drop, tmem_base + acc * Cfg::kAccStride, warp, lane, m0, n0, split,
                         epi_stage + (warp - 4) * kEpiStageBytes);
       tc_fence_before();
       __syncwarp();
+      if (warp == 4 && lane == 0 && w + npairs >= num_work) stamp(p, 5);   // last epilogue done (warp 4)
       if (lane == 0) {
         if (leader) mbar_arrive(&tmem_empty[acc]);
         else mbar_arrive_remote(mapa_u32(smem_u32(&tmem_empty[acc]), 0));
@@ -392,6 +398,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   // no CTA may exit (or free TMEM) while its partner can still multicast-commit into it or read its smem
   tc_fence_before();
   cluster_sync_all();
+  if (threadIdx.x == 0) stamp(p, 6);                                  // pair done
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc_2sm(tmem_base, Cfg::kTmemCols);
@@ -442,6 +449,7 @@ static void fill_params(GemmKernelParams& p, const b2_gemm_args_t& a, int tile_m
   p.aux_out = (__nv_bfloat16*)a.aux_out; p.ld_aux_out = a.ld_aux_out;
   p.partial = (float*)a.workspace;
   p.dropout_p = a.dropout_p; p.rng = (const unsigned long long*)a.rng_state; p.rng_site = a.rng_site;
+  p.timing = (long long*)a.debug_timing;
 }
 
 static int32_t launch_splitk_reduce(const b2_gemm_args_t& a, int splits, cudaStream_t stream) {

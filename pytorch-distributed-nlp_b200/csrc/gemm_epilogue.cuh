@@ -23,7 +23,14 @@ struct GemmKernelParams {
   __nv_bfloat16* aux_out; long long ld_aux_out;
   float* partial;  // split-K fp32 partials [splits][M][N]
   float dropout_p; const unsigned long long* rng; unsigned rng_site;
+  long long* timing;  // optional [gridDim.x][8] clock64 stamps (profiling aid, see tools/gemm_timeline.py)
 };
+
+#ifdef __CUDACC__
+__device__ __forceinline__ void stamp(const GemmKernelParams& p, int slot) {
+  if (p.timing != nullptr) p.timing[(size_t)blockIdx.x * 8 + slot] = clock64();
+}
+#endif
 
 constexpr int kEpiStageBytes = 32 * 128;   // per epilogue warp
 
