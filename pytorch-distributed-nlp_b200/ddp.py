@@ -106,7 +106,8 @@ class DistributedDataParallel(nn.Module):
         self._master_stale = False
         self._side = None
         self._pending = None
-        module._ddp = self
+        # plain attribute, NOT a registered submodule (model -> wrapper -> model would be a module cycle)
+        object.__setattr__(module, "_ddp", self)
         eng = module._engine
         if self.world > 1:
             if self.world > 8:
