@@ -69,6 +69,8 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_fwd_kernel(const __grid
     fence_mbar_init();
   }
   if (warp == 0) tmem_alloc(tmem_holder, 256);
+  pdl_wait();               // PDL: setup above overlapped the predecessor's tail; global reads start below
+  pdl_launch_dependents();
   for (int c = tid; c < p.seq; c += ATT_THREADS)
     s_bias[c] = (p.mask != nullptr && p.mask[(size_t)b * p.seq + c] == 0) ? kMaskBias : 0.f;
   tc_fence_before();
@@ -242,6 +244,8 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_bwd_kernel(const __grid
     fence_mbar_init();
   }
   if (warp == 0) tmem_alloc(tmem_holder, 512);
+  pdl_wait();               // PDL: setup above overlapped the predecessor's tail; global reads start below
+  pdl_launch_dependents();
   s_bias[tid] = (p.mask != nullptr && p.mask[(size_t)b * p.seq + jb * 128 + tid] == 0) ? kMaskBias : 0.f;
   tc_fence_before();
   __syncthreads();
@@ -430,6 +434,8 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_bwd_kernel(const __grid
 // fp32 dQ accumulator [tokens, hidden] -> the Q column block of d_qkv (bf16 [tokens, 3*hidden])
 __global__ void dq_convert_kernel(const float* __restrict__ acc, __nv_bfloat16* __restrict__ d_qkv, long long tokens,
                                   int hidden) {
+  pdl_wait();               // PDL: predecessors complete + visible before any global access
+  pdl_launch_dependents();  // let the next kernel in the stream begin launching
   const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (i >= tokens * hidden) return;
   const long long t = i / hidden;
@@ -482,7 +488,7 @@ extern "C" int32_t b2_attention_fwd(const void* qkv, const int64_t* attention_ma
     attr = true;
   }
   dim3 grid((unsigned)(seq / 128), (unsigned)heads, (unsigned)batch);
-  attention_fwd_kernel<<<grid, ATT_THREADS, kFwdSmem, stream>>>(tm, p);
+  B2_LAUNCH(attention_fwd_kernel, grid, ATT_THREADS, kFwdSmem, stream, tm, p);
   B2_CUDA(cudaGetLastError());
   count_launches(1);
   return 0;
@@ -520,12 +526,12 @@ extern "C" int32_t b2_attention_bwd(const void* qkv, const int64_t* attention_ma
     attr = true;
   }
   dim3 grid((unsigned)(seq / 128), (unsigned)heads, (unsigned)batch);
-  attention_bwd_kernel<<<grid, ATT_THREADS, kBwdSmem, stream>>>(tm_qkv, tm_do, p);
+  B2_LAUNCH(attention_bwd_kernel, grid, ATT_THREADS, kBwdSmem, stream, tm_qkv, tm_do, p);
   B2_CUDA(cudaGetLastError());
   count_launches(1);
   if (p.dq_accum) {
     const long long n4 = tokens * hidden / 4;
-    dq_convert_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, stream>>>(p.dq_accum, (__nv_bfloat16*)d_qkv, tokens,
+    B2_LAUNCH(dq_convert_kernel, (unsigned)((n4 + 255) / 256), 256, 0, stream, p.dq_accum, (__nv_bfloat16*)d_qkv, tokens,
                                                                         (int)hidden);
     B2_CUDA(cudaGetLastError());
   count_launches(1);

@@ -47,6 +47,8 @@ __device__ __forceinline__ void barrier_signal_wait(const PeerPtrs& flags, int w
 }
 
 __global__ void peer_barrier_kernel(PeerPtrs flags, int world, int rank, int slot, uint32_t* epoch_ctr) {
+  pdl_wait();               // PDL: predecessors complete + visible before any global access
+  pdl_launch_dependents();  // let the next kernel in the stream begin launching
   __shared__ uint32_t epoch;
   if (threadIdx.x == 0) {
     epoch = *epoch_ctr + 1;
@@ -60,6 +62,8 @@ __global__ void peer_barrier_kernel(PeerPtrs flags, int world, int rank, int slo
 // every rank stores `bytes` (multiple of 4) into slot `rank` of every peer's buffer, then barrier
 __global__ void allgather_rows_kernel(const uint32_t* __restrict__ src, long long words, PeerPtrs dst,
                                       PeerPtrs flags, int world, int rank, int slot, uint32_t* epoch_ctr) {
+  pdl_wait();               // PDL: predecessors complete + visible before any global access
+  pdl_launch_dependents();  // let the next kernel in the stream begin launching
   __shared__ uint32_t epoch;
   if (threadIdx.x == 0) {
     epoch = *epoch_ctr + 1;
@@ -77,6 +81,8 @@ __global__ void allgather_rows_kernel(const uint32_t* __restrict__ src, long lon
 // mean of one fp32 scalar over ranks; scratch is float[2][world] on every rank (double-buffered by epoch parity)
 __global__ void scalar_allreduce_mean_kernel(const float* __restrict__ src, float* __restrict__ dst, PeerPtrs scratch,
                                              PeerPtrs flags, int world, int rank, int slot, uint32_t* epoch_ctr) {
+  pdl_wait();               // PDL: predecessors complete + visible before any global access
+  pdl_launch_dependents();  // let the next kernel in the stream begin launching
   __shared__ uint32_t epoch;
   if (threadIdx.x == 0) {
     epoch = *epoch_ctr + 1;
@@ -153,7 +159,7 @@ extern "C" int32_t b2_peer_barrier(void* const* peer_flags, int32_t world, int32
   PeerPtrs f;
   int32_t st = fill_peers(&f, peer_flags, world, "peer_barrier");
   if (st) return st;
-  peer_barrier_kernel<<<1, 32, 0, (cudaStream_t)stream_>>>(f, world, rank, slot, epoch);
+  B2_LAUNCH(peer_barrier_kernel, 1, 32, 0, (cudaStream_t)stream_, f, world, rank, slot, epoch);
   B2_CUDA(cudaGetLastError());
   count_launches(1);
   return 0;
@@ -172,7 +178,7 @@ extern "C" int32_t b2_allgather_rows(const void* src, int64_t bytes, void* const
   if (st) return st;
   st = fill_peers(&f, peer_flags, world, "allgather_rows(flags)");
   if (st) return st;
-  allgather_rows_kernel<<<1, 256, 0, (cudaStream_t)stream_>>>((const uint32_t*)src, bytes / 4, d, f, world, rank, slot,
+  B2_LAUNCH(allgather_rows_kernel, 1, 256, 0, (cudaStream_t)stream_, (const uint32_t*)src, bytes / 4, d, f, world, rank, slot,
                                                               epoch);
   B2_CUDA(cudaGetLastError());
   count_launches(1);
@@ -191,7 +197,7 @@ extern "C" int32_t b2_scalar_allreduce_mean(const float* src, float* dst, float*
   if (st) return st;
   st = fill_peers(&f, peer_flags, world, "scalar_allreduce_mean(flags)");
   if (st) return st;
-  scalar_allreduce_mean_kernel<<<1, 32, 0, (cudaStream_t)stream_>>>(src, dst, s, f, world, rank, slot, epoch);
+  B2_LAUNCH(scalar_allreduce_mean_kernel, 1, 32, 0, (cudaStream_t)stream_, src, dst, s, f, world, rank, slot, epoch);
   B2_CUDA(cudaGetLastError());
   count_launches(1);
   return 0;

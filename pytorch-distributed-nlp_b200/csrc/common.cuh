@@ -40,6 +40,29 @@ int32_t get_tensor_map_2d(CUtensorMap* out, const void* base, uint64_t rows, uin
 
 #ifdef __CUDACC__
 // ----------------------------------------------------------------------------------------------
+// kernel launch: cudaLaunchKernelEx with the programmatic-stream-serialization attribute (PDL), so that back-to-back
+// kernels of a step (318 per step, captured in one CUDA graph) overlap launch latency with the predecessor's tail
+// ----------------------------------------------------------------------------------------------
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline void launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                          Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  (void)cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);   // errors surface via cudaGetLastError()
+}
+#define B2_LAUNCH(kernel, grid, block, smem, stream, ...) \
+  ::b2::launch_kernel(kernel, dim3(grid), dim3(block), (size_t)(smem), (cudaStream_t)(stream), ##__VA_ARGS__)
+
+// ----------------------------------------------------------------------------------------------
 // small device helpers
 // ----------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -277,6 +300,13 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(uint32_t M, uint32_t N, b
   return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
          ((N >> 3) << 17) | ((M >> 4) << 24);
 }
+
+// Programmatic dependent launch (PDL).  Every kernel of the library starts with pdl_wait(): it returns once all
+// kernels it depends on have completed and flushed, so whatever precedes it (nothing, by convention) may overlap the
+// predecessor's tail; pdl_launch_dependents() then allows the next kernel of the stream to start launching while
+// this one runs.  Both are no-ops for launches without the programmatic-serialization attribute.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 // vectorised global access helpers
 __device__ __forceinline__ uint4 ldg16(const void* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }

@@ -22,6 +22,8 @@ __global__ void __launch_bounds__(128) embed_fwd_kernel(
     const unsigned long long* rng, unsigned rng_site, __nv_bfloat16* __restrict__ y,
     __nv_bfloat16* __restrict__ pre_ln, float* __restrict__ mean_out, float* __restrict__ rstd_out,
     int* __restrict__ ids32, int* __restrict__ tt32) {
+  pdl_wait();               // PDL: predecessors complete + visible before any global access
+  pdl_launch_dependents();  // let the next kernel in the stream begin launching
   constexpr int H = VPL * 256;
   const int t = blockIdx.x * 4 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -64,6 +66,8 @@ __global__ void __launch_bounds__(128) embed_fwd_kernel(
 
 __global__ void embed_owner_kernel(const int* __restrict__ ids32, int tokens, int pad_id,
                                    int* __restrict__ owner) {
+  pdl_wait();               // PDL: predecessors complete + visible before any global access
+  pdl_launch_dependents();  // let the next kernel in the stream begin launching
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t < tokens && ids32[t] != pad_id) atomicMin(&owner[ids32[t]], t);
 }
@@ -72,6 +76,8 @@ __global__ void embed_owner_kernel(const int* __restrict__ ids32, int tokens, in
 __global__ void embed_word_scatter_kernel(const __nv_bfloat16* __restrict__ dx, const int* __restrict__ ids32,
                                           int tokens, int H, int pad_id, int* __restrict__ owner,
                                           __nv_bfloat16* __restrict__ d_word) {
+  pdl_wait();               // PDL: predecessors complete + visible before any global access
+  pdl_launch_dependents();  // let the next kernel in the stream begin launching
   const int t = blockIdx.x;
   const int id = ids32[t];
   // nn.Embedding(padding_idx=pad_token_id): the pad row never receives gradient (stays at the caller's zero fill)
@@ -115,6 +121,8 @@ __global__ void embed_word_scatter_kernel(const __nv_bfloat16* __restrict__ dx, 
 // d_pos[s] = sum_b dx[b*seq + s]  (rows >= seq get zero).  grid = max_pos rows, threads = H/8
 __global__ void embed_pos_kernel(const __nv_bfloat16* __restrict__ dx, int batch, int seq, int H,
                                  __nv_bfloat16* __restrict__ d_pos) {
+  pdl_wait();               // PDL: predecessors complete + visible before any global access
+  pdl_launch_dependents();  // let the next kernel in the stream begin launching
   const int s = blockIdx.x;
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   if (s < seq) {
@@ -131,6 +139,8 @@ __global__ void embed_pos_kernel(const __nv_bfloat16* __restrict__ dx, int batch
 }
 
 __global__ void fill_int_kernel(int* p, int n, int v) {
+  pdl_wait();               // PDL: predecessors complete + visible before any global access
+  pdl_launch_dependents();  // let the next kernel in the stream begin launching
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = v;
 }
@@ -156,7 +166,7 @@ extern "C" int32_t b2_embed_fwd(const int64_t* input_ids, const int64_t* token_t
   const unsigned grid = (unsigned)((tokens + 3) / 4);
 #define B2_EMB(VPL_)                                                                                              \
   case VPL_:                                                                                                      \
-    embed_fwd_kernel<VPL_><<<grid, 128, 0, stream>>>(                                                             \
+    B2_LAUNCH((embed_fwd_kernel<VPL_>), grid, 128, 0, stream,                                                              \
         (const long long*)input_ids, (const long long*)token_type_ids, tokens, (int)seq,                          \
         (const __nv_bfloat16*)word_emb, (const __nv_bfloat16*)pos_emb, (const __nv_bfloat16*)type_emb,            \
         (const __nv_bfloat16*)gamma, (const __nv_bfloat16*)beta, (int)vocab, (int)type_vocab, eps, dropout_p,     \
@@ -191,16 +201,16 @@ extern "C" int32_t b2_embed_bwd(const void* dy, int32_t dy_fp32, const void* pre
                                     scratch_partials, scratch_partials_bytes, stream);
   if (st) return st;
   // 2. word rows (d_word pre-zeroed by the caller)
-  embed_owner_kernel<<<(tokens + 255) / 256, 256, 0, stream>>>(ids32, tokens, (int)pad_token_id, owner);
+  B2_LAUNCH(embed_owner_kernel, (tokens + 255) / 256, 256, 0, stream, ids32, tokens, (int)pad_token_id, owner);
   B2_CUDA(cudaGetLastError());
   count_launches(1);
-  embed_word_scatter_kernel<<<tokens, 128, 0, stream>>>((const __nv_bfloat16*)scratch_dx, ids32, tokens, (int)hidden,
+  B2_LAUNCH(embed_word_scatter_kernel, tokens, 128, 0, stream, (const __nv_bfloat16*)scratch_dx, ids32, tokens, (int)hidden,
                                                         (int)pad_token_id, owner, (__nv_bfloat16*)d_word);
   B2_CUDA(cudaGetLastError());
   count_launches(1);
   // 3. position rows: the table has `max_pos` rows but only the first `seq` receive gradient; the caller passes
   //    d_pos sized [seq rows used]; rows beyond are zeroed by the caller's bucket memset
-  embed_pos_kernel<<<(unsigned)seq, (unsigned)(hidden / 8), 0, stream>>>((const __nv_bfloat16*)scratch_dx, (int)batch,
+  B2_LAUNCH(embed_pos_kernel, (unsigned)seq, (unsigned)(hidden / 8), 0, stream, (const __nv_bfloat16*)scratch_dx, (int)batch,
                                                                          (int)seq, (int)hidden, (__nv_bfloat16*)d_pos);
   B2_CUDA(cudaGetLastError());
   count_launches(1);
@@ -216,7 +226,7 @@ extern "C" int32_t b2_embed_bwd(const void* dy, int32_t dy_fp32, const void* pre
 // arms the owner table (INT_MAX) once; the scatter kernel re-arms what it touched
 extern "C" int32_t b2_embed_owner_init(int32_t* owner, int64_t vocab, void* stream_) {
   B2_REQUIRE(owner && vocab > 0, "embed_owner_init: bad args");
-  fill_int_kernel<<<(unsigned)((vocab + 255) / 256), 256, 0, (cudaStream_t)stream_>>>(owner, (int)vocab, INT_MAX);
+  B2_LAUNCH(fill_int_kernel, (unsigned)((vocab + 255) / 256), 256, 0, (cudaStream_t)stream_, owner, (int)vocab, INT_MAX);
   B2_CUDA(cudaGetLastError());
   count_launches(1);
   return 0;

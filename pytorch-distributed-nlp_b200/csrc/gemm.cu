@@ -85,6 +85,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
+  // PDL: everything above (barrier init, TMEM allocation, descriptor prefetch) touches no global data and may overlap
+  // the predecessor's tail; from here on operands / auxiliary tensors written by earlier kernels are read
+  pdl_wait();
+  pdl_launch_dependents();
 
   const int num_work = p.tiles_m * p.tiles_n * p.splits;
 
@@ -297,6 +301,10 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
   if (threadIdx.x == 0) stamp(p, 1);                                  // setup done
+  // PDL: everything above (barrier init, TMEM allocation, descriptor prefetch) touches no global data and may overlap
+  // the predecessor's tail; from here on operands / auxiliary tensors written by earlier kernels are read
+  pdl_wait();
+  pdl_launch_dependents();
 
   const int num_work = p.tiles_m * p.tiles_n * p.splits;   // tiles_m counts 256-row tiles here
 
@@ -408,6 +416,8 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 // sums split-K partials [splits][M][N] fp32 -> bf16 D
 __global__ void splitk_reduce_kernel(const float* __restrict__ partial, __nv_bfloat16* __restrict__ D,
                                      long long ldd, int M, int N, int splits) {
+  pdl_wait();               // PDL: predecessors complete + visible before any global access
+  pdl_launch_dependents();  // let the next kernel in the stream begin launching
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // one float4 (4 columns) each
   const long long total = (long long)M * N / 4;
   if (idx >= total) return;
@@ -454,7 +464,7 @@ static void fill_params(GemmKernelParams& p, const b2_gemm_args_t& a, int tile_m
 
 static int32_t launch_splitk_reduce(const b2_gemm_args_t& a, int splits, cudaStream_t stream) {
   const long long total = (long long)a.M * a.N / 4;
-  splitk_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(
+  B2_LAUNCH(splitk_reduce_kernel, (unsigned)((total + 255) / 256), 256, 0, stream, 
       (const float*)a.workspace, (__nv_bfloat16*)a.D, a.ldd, (int)a.M, (int)a.N, splits);
   B2_CUDA(cudaGetLastError());
   count_launches(1);
@@ -482,7 +492,7 @@ static int32_t launch_gemm(const b2_gemm_args_t& a, int splits, cudaStream_t str
   }
   const int work = p.tiles_m * p.tiles_n * p.splits;
   const int grid = work < num_sms() ? work : num_sms();
-  kern<<<grid, GEMM_THREADS, Cfg::kSmemBytes, stream>>>(ta, tb, p);
+  B2_LAUNCH(kern, grid, GEMM_THREADS, Cfg::kSmemBytes, stream, ta, tb, p);
   B2_CUDA(cudaGetLastError());
   count_launches(1);
   if (splits > 1) return launch_splitk_reduce(a, splits, stream);
@@ -511,7 +521,7 @@ static int32_t launch_gemm2(const b2_gemm_args_t& a, int splits, cudaStream_t st
   const int work = p.tiles_m * p.tiles_n * p.splits;
   const int max_pairs = num_sms() / 2;
   const int pairs = work < max_pairs ? work : max_pairs;
-  kern<<<2 * pairs, GEMM_THREADS, Cfg::kSmemBytes, stream>>>(ta, tb, p);
+  B2_LAUNCH(kern, 2 * pairs, GEMM_THREADS, Cfg::kSmemBytes, stream, ta, tb, p);
   B2_CUDA(cudaGetLastError());
   count_launches(1);
   if (splits > 1) return launch_splitk_reduce(a, splits, stream);

@@ -26,6 +26,8 @@ __global__ void __launch_bounds__(256) pooler_fwd_kernel(const __nv_bfloat16* __
                                                         int H, const __nv_bfloat16* __restrict__ Wp,
                                                         const __nv_bfloat16* __restrict__ bp,
                                                         __nv_bfloat16* __restrict__ pooled) {
+  pdl_wait();               // PDL: predecessors complete + visible before any global access
+  pdl_launch_dependents();  // let the next kernel in the stream begin launching
   const int j = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   const int b0 = blockIdx.y * 8;
@@ -58,6 +60,8 @@ __global__ void __launch_bounds__(256) classifier_fwd_kernel(const __nv_bfloat16
                                                             const __nv_bfloat16* __restrict__ bc, int C,
                                                             float dropout_p, const unsigned long long* rng,
                                                             unsigned site, float* __restrict__ logits) {
+  pdl_wait();               // PDL: predecessors complete + visible before any global access
+  pdl_launch_dependents();  // let the next kernel in the stream begin launching
   const int o = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (o >= batch * C) return;
@@ -82,6 +86,8 @@ __global__ void __launch_bounds__(256) classifier_fwd_kernel(const __nv_bfloat16
 __global__ void __launch_bounds__(256) ce_fwd_bwd_kernel(const float* __restrict__ logits,
                                                         const long long* __restrict__ labels, int batch, int C,
                                                         float* __restrict__ loss, float* __restrict__ dlogits) {
+  pdl_wait();               // PDL: predecessors complete + visible before any global access
+  pdl_launch_dependents();  // let the next kernel in the stream begin launching
   __shared__ float red[256];
   float local = 0.f;
   for (int b = threadIdx.x; b < batch; b += blockDim.x) {
@@ -119,6 +125,8 @@ __global__ void __launch_bounds__(256) head_bwd_k1(const float* __restrict__ dlo
                                                   const unsigned long long* rng, unsigned site,
                                                   float* __restrict__ d_pre, __nv_bfloat16* __restrict__ d_cls_w,
                                                   __nv_bfloat16* __restrict__ d_cls_b) {
+  pdl_wait();               // PDL: predecessors complete + visible before any global access
+  pdl_launch_dependents();  // let the next kernel in the stream begin launching
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j < C && blockIdx.x == 0) {  // class bias grads (C <= blockDim.x)
     float s = 0.f;
@@ -149,6 +157,8 @@ __global__ void __launch_bounds__(256) head_bwd_k1(const float* __restrict__ dlo
 //     grid = H rows (j), threads = H/8 (each 8 consecutive k)
 __global__ void head_bwd_k2(const float* __restrict__ d_pre, const __nv_bfloat16* __restrict__ h, int batch, int seq,
                             int H, __nv_bfloat16* __restrict__ d_pool_w, __nv_bfloat16* __restrict__ d_pool_b) {
+  pdl_wait();               // PDL: predecessors complete + visible before any global access
+  pdl_launch_dependents();  // let the next kernel in the stream begin launching
   const int j = blockIdx.x;
   const int k = threadIdx.x * 8;
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -172,6 +182,8 @@ __global__ void head_bwd_k2(const float* __restrict__ d_pre, const __nv_bfloat16
 __global__ void __launch_bounds__(256) head_bwd_k3(const float* __restrict__ d_pre,
                                                   const __nv_bfloat16* __restrict__ Wp, int seq, int H,
                                                   void* __restrict__ d_hidden, int out_f32) {
+  pdl_wait();               // PDL: predecessors complete + visible before any global access
+  pdl_launch_dependents();  // let the next kernel in the stream begin launching
   __shared__ float red[8][64];
   const int b = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -210,12 +222,12 @@ extern "C" int32_t b2_head_fwd(const void* hidden_states, int64_t batch, int64_t
   B2_REQUIRE(batch > 0 && seq > 0 && num_labels > 0, "head_fwd: empty problem");
   B2_REQUIRE(hidden % 256 == 0, "head_fwd: hidden=%lld must be a multiple of 256", (long long)hidden);
   B2_REQUIRE(!(dropout_p > 0.f) || rng_state, "head_fwd: dropout needs rng_state");
-  pooler_fwd_kernel<<<dim3((unsigned)((hidden + 7) / 8), (unsigned)((batch + 7) / 8)), 256, 0, stream>>>(
+  B2_LAUNCH(pooler_fwd_kernel, dim3((unsigned)((hidden + 7) / 8), (unsigned)((batch + 7) / 8)), 256, 0, stream, 
       (const __nv_bfloat16*)hidden_states, (int)batch, (int)seq, (int)hidden, (const __nv_bfloat16*)pool_w,
       (const __nv_bfloat16*)pool_b, (__nv_bfloat16*)pooled);
   B2_CUDA(cudaGetLastError());
   count_launches(1);
-  classifier_fwd_kernel<<<(unsigned)((batch * num_labels + 7) / 8), 256, 0, stream>>>(
+  B2_LAUNCH(classifier_fwd_kernel, (unsigned)((batch * num_labels + 7) / 8), 256, 0, stream, 
       (const __nv_bfloat16*)pooled, (int)batch, (int)hidden, (const __nv_bfloat16*)cls_w, (const __nv_bfloat16*)cls_b,
       (int)num_labels, dropout_p, (const unsigned long long*)rng_state, rng_site, logits);
   B2_CUDA(cudaGetLastError());
@@ -227,7 +239,7 @@ extern "C" int32_t b2_ce_fwd_bwd(const float* logits, const int64_t* labels, int
                                  float* loss, float* dlogits, void* stream_) {
   B2_REQUIRE(logits && labels && loss, "ce_fwd_bwd: null pointer");
   B2_REQUIRE(batch > 0 && num_labels > 0, "ce_fwd_bwd: empty batch");
-  ce_fwd_bwd_kernel<<<1, 256, 0, (cudaStream_t)stream_>>>(logits, (const long long*)labels, (int)batch,
+  B2_LAUNCH(ce_fwd_bwd_kernel, 1, 256, 0, (cudaStream_t)stream_, logits, (const long long*)labels, (int)batch,
                                                           (int)num_labels, loss, dlogits);
   B2_CUDA(cudaGetLastError());
   count_launches(1);
@@ -247,18 +259,18 @@ extern "C" int32_t b2_head_bwd(const float* dlogits, const void* hidden_states, 
   B2_REQUIRE(hidden % 256 == 0 && hidden / 8 <= 1024, "head_bwd: hidden=%lld unsupported", (long long)hidden);
   B2_REQUIRE(num_labels <= 64, "head_bwd: num_labels=%lld > 64", (long long)num_labels);
   B2_CUDA(cudaMemsetAsync(d_hidden, 0, (size_t)batch * seq * hidden * (d_hidden_fp32 ? 4 : 2), stream));
-  head_bwd_k1<<<(unsigned)((hidden + 255) / 256), 256, 0, stream>>>(
+  B2_LAUNCH(head_bwd_k1, (unsigned)((hidden + 255) / 256), 256, 0, stream, 
       dlogits, (const __nv_bfloat16*)pooled, (int)batch, (int)hidden, (const __nv_bfloat16*)cls_w, (int)num_labels,
       dropout_p, (const unsigned long long*)rng_state, rng_site, scratch, (__nv_bfloat16*)d_cls_w,
       (__nv_bfloat16*)d_cls_b);
   B2_CUDA(cudaGetLastError());
   count_launches(1);
-  head_bwd_k2<<<(unsigned)hidden, (unsigned)(hidden / 8), 0, stream>>>(
+  B2_LAUNCH(head_bwd_k2, (unsigned)hidden, (unsigned)(hidden / 8), 0, stream, 
       scratch, (const __nv_bfloat16*)hidden_states, (int)batch, (int)seq, (int)hidden, (__nv_bfloat16*)d_pool_w,
       (__nv_bfloat16*)d_pool_b);
   B2_CUDA(cudaGetLastError());
   count_launches(1);
-  head_bwd_k3<<<dim3((unsigned)batch, (unsigned)(hidden / 64)), 256, 0, stream>>>(scratch, (const __nv_bfloat16*)pool_w, (int)seq,
+  B2_LAUNCH(head_bwd_k3, dim3((unsigned)batch, (unsigned)(hidden / 64)), 256, 0, stream, scratch, (const __nv_bfloat16*)pool_w, (int)seq,
                                                                       (int)hidden, d_hidden, d_hidden_fp32 ? 1 : 0);
   B2_CUDA(cudaGetLastError());
   count_launches(1);

@@ -14,6 +14,8 @@ __global__ void __launch_bounds__(128) layernorm_fwd_kernel(const __nv_bfloat16*
                                                            const __nv_bfloat16* __restrict__ beta, int rows, float eps,
                                                            __nv_bfloat16* __restrict__ y, float* __restrict__ mean_out,
                                                            float* __restrict__ rstd_out) {
+  pdl_wait();               // PDL: predecessors complete + visible before any global access
+  pdl_launch_dependents();  // let the next kernel in the stream begin launching
   constexpr int H = VPL * 256;
   const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -40,6 +42,8 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(
     const __nv_bfloat16* __restrict__ gamma, int rows, float dropout_p, const unsigned long long* rng,
     unsigned rng_site, int mode, void* __restrict__ dx_, __nv_bfloat16* __restrict__ dx_drop,
     float* __restrict__ partials /* [gridDim.x][3][H] */) {
+  pdl_wait();               // PDL: predecessors complete + visible before any global access
+  pdl_launch_dependents();  // let the next kernel in the stream begin launching
   constexpr int H = VPL * 256;
   constexpr int WARPS = 8;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -137,6 +141,8 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(
 __global__ void __launch_bounds__(256) colsum_finish_kernel(const float* __restrict__ partials, int nparts, int nsets,
                                                            int cols, __nv_bfloat16* o0, __nv_bfloat16* o1,
                                                            __nv_bfloat16* o2) {
+  pdl_wait();               // PDL: predecessors complete + visible before any global access
+  pdl_launch_dependents();  // let the next kernel in the stream begin launching
   __shared__ float red[8][33];
   const int c = threadIdx.x & 31, pl = threadIdx.x >> 5;
   const int idx = blockIdx.x * 32 + c;
@@ -169,6 +175,8 @@ __global__ void __launch_bounds__(256) colsum_finish_kernel(const float* __restr
 __global__ void __launch_bounds__(256) colsum_partial_kernel(const __nv_bfloat16* __restrict__ x, int rows, int cols,
                                                             long long ldx, const int* __restrict__ filter,
                                                             int filter_value, float* __restrict__ partials) {
+  pdl_wait();               // PDL: predecessors complete + visible before any global access
+  pdl_launch_dependents();  // let the next kernel in the stream begin launching
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int col = blockIdx.x * 256 + lane * 8;
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -201,11 +209,11 @@ int32_t launch_colsum(const void* x, int64_t rows, int64_t cols, int64_t ldx, co
   B2_REQUIRE(nparts >= 1, "colsum: scratch too small (%lld bytes for %lld columns)", (long long)scratch_bytes,
              (long long)cols);
   dim3 grid((unsigned)((cols + 255) / 256), (unsigned)nparts);
-  colsum_partial_kernel<<<grid, 256, 0, stream>>>((const __nv_bfloat16*)x, (int)rows, (int)cols, ldx, filter,
+  B2_LAUNCH(colsum_partial_kernel, grid, 256, 0, stream, (const __nv_bfloat16*)x, (int)rows, (int)cols, ldx, filter,
                                                   filter_value, scratch);
   B2_CUDA(cudaGetLastError());
   count_launches(1);
-  colsum_finish_kernel<<<(unsigned)((cols + 31) / 32), 256, 0, stream>>>(scratch, nparts, 1, (int)cols,
+  B2_LAUNCH(colsum_finish_kernel, (unsigned)((cols + 31) / 32), 256, 0, stream, scratch, nparts, 1, (int)cols,
                                                                            (__nv_bfloat16*)out, nullptr, nullptr);
   B2_CUDA(cudaGetLastError());
   count_launches(1);
@@ -229,9 +237,9 @@ int32_t launch_layernorm_bwd(const void* dy, const void* dy_add, const void* x, 
       (const unsigned long long*)rng, site, mode, dx, (__nv_bfloat16*)dx_drop, scratch
 #define B2_LN_BWD(VPL_)                                                                                      \
   case VPL_:                                                                                                 \
-    if (dy_f32 && dx_f32) layernorm_bwd_kernel<VPL_, true, true><<<nblocks, 256, 0, stream>>>(B2_LN_ARGS);   \
-    else if (dy_f32) layernorm_bwd_kernel<VPL_, true, false><<<nblocks, 256, 0, stream>>>(B2_LN_ARGS);       \
-    else layernorm_bwd_kernel<VPL_, false, false><<<nblocks, 256, 0, stream>>>(B2_LN_ARGS);                  \
+    if (dy_f32 && dx_f32) B2_LAUNCH((layernorm_bwd_kernel<VPL_, true, true>), nblocks, 256, 0, stream, B2_LN_ARGS);   \
+    else if (dy_f32) B2_LAUNCH((layernorm_bwd_kernel<VPL_, true, false>), nblocks, 256, 0, stream, B2_LN_ARGS);       \
+    else B2_LAUNCH((layernorm_bwd_kernel<VPL_, false, false>), nblocks, 256, 0, stream, B2_LN_ARGS);                  \
     break;
   B2_REQUIRE(dy_f32 || !dx_f32, "layernorm_bwd: fp32 dx with bf16 dy is not on the path");
   switch ((int)(hidden / 256)) {
@@ -241,7 +249,7 @@ int32_t launch_layernorm_bwd(const void* dy, const void* dy_add, const void* x, 
 #undef B2_LN_ARGS
   B2_CUDA(cudaGetLastError());
   count_launches(1);
-  colsum_finish_kernel<<<(unsigned)((3 * hidden + 31) / 32), 256, 0, stream>>>(
+  B2_LAUNCH(colsum_finish_kernel, (unsigned)((3 * hidden + 31) / 32), 256, 0, stream, 
       scratch, nblocks, 3, (int)hidden, (__nv_bfloat16*)d_gamma, (__nv_bfloat16*)d_beta, (__nv_bfloat16*)d_bias);
   B2_CUDA(cudaGetLastError());
   count_launches(1);
@@ -262,7 +270,7 @@ extern "C" int32_t b2_layernorm_fwd(const void* x, const void* gamma, const void
   const unsigned grid = (unsigned)((rows + 3) / 4);
 #define B2_LN_FWD(VPL_)                                                                                       \
   case VPL_:                                                                                                  \
-    layernorm_fwd_kernel<VPL_><<<grid, 128, 0, stream>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)gamma, \
+    B2_LAUNCH((layernorm_fwd_kernel<VPL_>), grid, 128, 0, stream, (const __nv_bfloat16*)x, (const __nv_bfloat16*)gamma, \
                                                          (const __nv_bfloat16*)beta, (int)rows, eps,           \
                                                          (__nv_bfloat16*)y, mean, rstd);                       \
     break;

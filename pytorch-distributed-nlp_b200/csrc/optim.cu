@@ -31,6 +31,8 @@ struct ReduceAdamWParams {
 };
 
 __global__ void __launch_bounds__(256) reduce_adamw_kernel(const ReduceAdamWParams p) {
+  pdl_wait();               // PDL: predecessors complete + visible before any global access
+  pdl_launch_dependents();  // let the next kernel in the stream begin launching
   // HF AdamW bias correction: step_size = lr * sqrt(1 - b2^t) / (1 - b1^t), t = steps taken including this one
   const long long t = *p.step_counter + 1;
   float step_size = p.lr;
@@ -86,12 +88,16 @@ __global__ void __launch_bounds__(256) reduce_adamw_kernel(const ReduceAdamWPara
 }
 
 __global__ void step_advance_kernel(long long* step, unsigned long long* rng) {
+  pdl_wait();               // PDL: predecessors complete + visible before any global access
+  pdl_launch_dependents();  // let the next kernel in the stream begin launching
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     if (step) *step += 1;
     if (rng) rng[1] += 1;
   }
 }
 __global__ void rng_seed_kernel(unsigned long long* rng, unsigned long long seed, unsigned long long step) {
+  pdl_wait();               // PDL: predecessors complete + visible before any global access
+  pdl_launch_dependents();  // let the next kernel in the stream begin launching
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     rng[0] = seed;
     rng[1] = step;
@@ -99,6 +105,8 @@ __global__ void rng_seed_kernel(unsigned long long* rng, unsigned long long seed
 }
 
 __global__ void cast_f32_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long n) {
+  pdl_wait();               // PDL: predecessors complete + visible before any global access
+  pdl_launch_dependents();  // let the next kernel in the stream begin launching
   const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8;
   if (i + 8 <= n) {
     const float4 a = *reinterpret_cast<const float4*>(src + i), b = *reinterpret_cast<const float4*>(src + i + 4);
@@ -110,6 +118,8 @@ __global__ void cast_f32_bf16_kernel(const float* __restrict__ src, __nv_bfloat1
   }
 }
 __global__ void cast_bf16_f32_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ dst, long long n) {
+  pdl_wait();               // PDL: predecessors complete + visible before any global access
+  pdl_launch_dependents();  // let the next kernel in the stream begin launching
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) dst[i] = __bfloat162float(src[i]);
 }
@@ -148,14 +158,14 @@ extern "C" int32_t b2_bucket_reduce_adamw(const void* const* peer_grads, void* c
   long long blocks = (nvec + 255) / 256;
   const long long cap = 148 * 8;
   if (blocks > cap) blocks = cap;
-  reduce_adamw_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream_>>>(p);
+  B2_LAUNCH(reduce_adamw_kernel, (unsigned)blocks, 256, 0, (cudaStream_t)stream_, p);
   B2_CUDA(cudaGetLastError());
   count_launches(1);
   return 0;
 }
 
 extern "C" int32_t b2_step_advance(int64_t* step_counter, void* rng_state, void* stream_) {
-  step_advance_kernel<<<1, 32, 0, (cudaStream_t)stream_>>>((long long*)step_counter, (unsigned long long*)rng_state);
+  B2_LAUNCH(step_advance_kernel, 1, 32, 0, (cudaStream_t)stream_, (long long*)step_counter, (unsigned long long*)rng_state);
   B2_CUDA(cudaGetLastError());
   count_launches(1);
   return 0;
@@ -163,7 +173,7 @@ extern "C" int32_t b2_step_advance(int64_t* step_counter, void* rng_state, void*
 
 extern "C" int32_t b2_rng_seed(void* rng_state, uint64_t seed, uint64_t step, void* stream_) {
   B2_REQUIRE(rng_state, "rng_seed: null pointer");
-  rng_seed_kernel<<<1, 32, 0, (cudaStream_t)stream_>>>((unsigned long long*)rng_state, seed, step);
+  B2_LAUNCH(rng_seed_kernel, 1, 32, 0, (cudaStream_t)stream_, (unsigned long long*)rng_state, seed, step);
   B2_CUDA(cudaGetLastError());
   count_launches(1);
   return 0;
@@ -174,7 +184,7 @@ extern "C" int32_t b2_cast_f32_to_bf16(const float* src, void* dst, int64_t n, v
   B2_REQUIRE(((uintptr_t)src % 16 == 0) && ((uintptr_t)dst % 16 == 0), "cast_f32_to_bf16: 16-byte alignment required");
   if (n == 0) return 0;
   const long long nv = (n + 7) / 8;
-  cast_f32_bf16_kernel<<<(unsigned)((nv + 255) / 256), 256, 0, (cudaStream_t)stream_>>>(src, (__nv_bfloat16*)dst, n);
+  B2_LAUNCH(cast_f32_bf16_kernel, (unsigned)((nv + 255) / 256), 256, 0, (cudaStream_t)stream_, src, (__nv_bfloat16*)dst, n);
   B2_CUDA(cudaGetLastError());
   count_launches(1);
   return 0;
@@ -183,7 +193,7 @@ extern "C" int32_t b2_cast_f32_to_bf16(const float* src, void* dst, int64_t n, v
 extern "C" int32_t b2_cast_bf16_to_f32(const void* src, float* dst, int64_t n, void* stream_) {
   B2_REQUIRE(src && dst && n >= 0, "cast_bf16_to_f32: bad args");
   if (n == 0) return 0;
-  cast_bf16_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream_>>>((const __nv_bfloat16*)src, dst,
+  B2_LAUNCH(cast_bf16_f32_kernel, (unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream_, (const __nv_bfloat16*)src, dst,
                                                                                        n);
   B2_CUDA(cudaGetLastError());
   count_launches(1);
