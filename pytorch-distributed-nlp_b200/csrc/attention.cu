@@ -5,7 +5,9 @@
 // plus its autograd backward.  The [B,12,S,S] probability tensor never exists in HBM: the
 // backward recomputes it from Q, K and the saved log-sum-exp.
 //
-// One CTA = 128 threads = 128 query (fwd) or key (bwd) rows = the 128 TMEM lanes; thread r owns row r.
+// One CTA = 256 threads = 128 query (fwd) or key (bwd) rows = the 128 TMEM lanes, TWO threads per row: warps 0-3
+// take key columns 0-63 of a 128-wide score block, warps 4-7 columns 64-127 (a warp may touch TMEM lanes
+// 32*(warp%4)..+31, any columns), which halves the per-row softmax / dS work that bounded the 128-thread version.
 // Tiles move HBM->smem by TMA straight out of the packed [tokens, 3*hidden] QKV activation (128B swizzle);
 // the same smem tile serves as a K-major operand for one product and as an MN-major operand for another
 // (e.g. dO is A of dP = dO V^T and B of dV = P^T dO), so nothing is ever transposed in memory.
@@ -14,7 +16,7 @@
 
 namespace b2 {
 
-constexpr int ATT_THREADS = 128;
+constexpr int ATT_THREADS = 256;
 constexpr int TILE_BYTES = 128 * 64 * 2;  // one [128 x 64] bf16 tile = 16 KB
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
@@ -55,9 +57,12 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_fwd_kernel(const __grid
   uint64_t* bar_s = &bars[1];
   uint64_t* bar_o = &bars[2];
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(&bars[4]);
-  float* s_bias = reinterpret_cast<float*>(smem + 5 * TILE_BYTES + 64);  // [seq]
+  float* s_bias = reinterpret_cast<float*>(smem + 5 * TILE_BYTES + 64);  // [seq <= 512]
+  float* s_red = s_bias + 512;                                           // [2][128] row exchange between halves
 
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int row = (warp & 3) * 32 + lane;   // TMEM lane == query row of this thread
+  const int half = warp >> 2;               // which 64 of the 128 key columns (and which 32 of the 64 output dims)
   const int qb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int nkv = p.seq / 128;
 
@@ -78,18 +83,18 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_fwd_kernel(const __grid
   tc_fence_after();
   const uint32_t tmem = *tmem_holder;
   const uint32_t tmem_s = tmem, tmem_o = tmem + 128;
-  const uint32_t lane_base = ((uint32_t)(warp * 32)) << 16;
+  const uint32_t lane_base = ((uint32_t)((warp & 3) * 32)) << 16;
 
   const int row0 = b * p.seq;           // first token row of this sequence
-  const int q_row = qb * 128 + tid;     // query index inside the sequence
+  const int q_row = qb * 128 + row;     // query index inside the sequence
   const int col_q = h * 64, col_k = p.hidden + h * 64, col_v = 2 * p.hidden + h * 64;
   const DropCtx drop = make_drop_ctx(p.rng, p.rng_site, p.dropout_p);
   const float c2 = p.scale * kLog2e;
 
-  float o_acc[64];
+  float o_acc[32];
 #pragma unroll
-  for (int i = 0; i < 64; ++i) o_acc[i] = 0.f;
-  float m_run = -INFINITY, l_run = 0.f;
+  for (int i = 0; i < 32; ++i) o_acc[i] = 0.f;
+  float m_run = -INFINITY, l_run = 0.f;   // l_run: this thread's half of the row sum
   uint32_t ph_load = 0, ph_s = 0, ph_o = 0;
 
   constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, false, false);
@@ -116,35 +121,38 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_fwd_kernel(const __grid
     ph_s ^= 1;
     tc_fence_after();
 
-    // pass 1: row maximum of the scaled + masked scores (log2 domain)
-    float m_new = m_run;
+    // pass 1: maximum of this thread's 64 scaled + masked scores (log2 domain), then across the two halves
+    float m_loc = -INFINITY;
 #pragma unroll 1
-    for (int c = 0; c < 4; ++c) {
+    for (int c = 0; c < 2; ++c) {
       uint32_t v[32];
-      tmem_ld32(tmem_s + lane_base + c * 32, v);
+      tmem_ld32(tmem_s + lane_base + half * 64 + c * 32, v);
       tmem_ld_wait();
 #pragma unroll
       for (int i = 0; i < 32; ++i)
-        m_new = fmaxf(m_new, __uint_as_float(v[i]) * c2 + s_bias[j * 128 + c * 32 + i]);
+        m_loc = fmaxf(m_loc, __uint_as_float(v[i]) * c2 + s_bias[j * 128 + half * 64 + c * 32 + i]);
     }
+    s_red[half * 128 + row] = m_loc;
+    __syncthreads();
+    const float m_new = fmaxf(m_run, fmaxf(s_red[row], s_red[128 + row]));
     const float alpha = exp2f(m_run - m_new);  // first block: exp2(-inf) = 0
     float l_blk = 0.f;
     // pass 2: probabilities -> (dropout) -> bf16 P tile in smem
 #pragma unroll 1
-    for (int c = 0; c < 4; ++c) {
+    for (int c = 0; c < 2; ++c) {
       uint32_t v[32];
-      tmem_ld32(tmem_s + lane_base + c * 32, v);
+      tmem_ld32(tmem_s + lane_base + half * 64 + c * 32, v);
       tmem_ld_wait();
       float pr[32];
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
-        pr[i] = exp2f(__uint_as_float(v[i]) * c2 + s_bias[j * 128 + c * 32 + i] - m_new);
+        pr[i] = exp2f(__uint_as_float(v[i]) * c2 + s_bias[j * 128 + half * 64 + c * 32 + i] - m_new);
         l_blk += pr[i];
       }
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
-        const unsigned long long idx =
-            (((unsigned long long)(b * p.heads + h) * p.seq + q_row) * p.seq) + j * 128 + c * 32 + g * 8;
+        const unsigned long long idx = (((unsigned long long)(b * p.heads + h) * p.seq + q_row) * p.seq) + j * 128 +
+                                       half * 64 + c * 32 + g * 8;
         const uint32_t keep = dropout_keep8(drop, idx);
         float q8[8];
 #pragma unroll
@@ -152,7 +160,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_fwd_kernel(const __grid
         uint4 o;
         o.x = pack_bf16(q8[0], q8[1]); o.y = pack_bf16(q8[2], q8[3]);
         o.z = pack_bf16(q8[4], q8[5]); o.w = pack_bf16(q8[6], q8[7]);
-        st_tile_chunk(sP, tid, c * 4 + g, o);
+        st_tile_chunk(sP, row, half * 8 + c * 4 + g, o);
       }
     }
     l_run = l_run * alpha + l_blk;
@@ -174,23 +182,26 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_fwd_kernel(const __grid
     mbar_wait(bar_o, ph_o);
     ph_o ^= 1;
     tc_fence_after();
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
+    {
       uint32_t v[32];
-      tmem_ld32(tmem_o + lane_base + c * 32, v);
+      tmem_ld32(tmem_o + lane_base + half * 32, v);
       tmem_ld_wait();
 #pragma unroll
-      for (int i = 0; i < 32; ++i) o_acc[c * 32 + i] = o_acc[c * 32 + i] * alpha + __uint_as_float(v[i]);
+      for (int i = 0; i < 32; ++i) o_acc[i] = o_acc[i] * alpha + __uint_as_float(v[i]);
     }
     // all TMEM reads of this iteration must retire before thread 0 issues the next QK^T / PV
     tc_fence_before();
     __syncthreads();
   }
 
-  const float inv_l = 1.0f / l_run;
-  __nv_bfloat16* out = p.ctx + (size_t)(row0 + q_row) * p.hidden + h * 64;
+  // total row sum = the two halves' partial sums
+  s_red[half * 128 + row] = l_run;
+  __syncthreads();
+  const float l_tot = s_red[row] + s_red[128 + row];
+  const float inv_l = 1.0f / l_tot;
+  __nv_bfloat16* out = p.ctx + (size_t)(row0 + q_row) * p.hidden + h * 64 + half * 32;
 #pragma unroll
-  for (int i = 0; i < 64; i += 8) {
+  for (int i = 0; i < 32; i += 8) {
     uint4 o;
     o.x = pack_bf16(o_acc[i] * inv_l, o_acc[i + 1] * inv_l);
     o.y = pack_bf16(o_acc[i + 2] * inv_l, o_acc[i + 3] * inv_l);
@@ -198,7 +209,8 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_fwd_kernel(const __grid
     o.w = pack_bf16(o_acc[i + 6] * inv_l, o_acc[i + 7] * inv_l);
     stg16(out + i, o);
   }
-  if (p.lse != nullptr) p.lse[((size_t)b * p.heads + h) * p.seq + q_row] = (m_run + log2f(l_run)) * kLn2;
+  if (p.lse != nullptr && half == 0)
+    p.lse[((size_t)b * p.heads + h) * p.seq + q_row] = (m_run + log2f(l_tot)) * kLn2;
 
   tc_fence_before();
   __syncthreads();
@@ -230,7 +242,9 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_bwd_kernel(const __grid
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(&bars[4]);
   float* s_bias = reinterpret_cast<float*>(smem + 8 * TILE_BYTES + 64);  // [128] keys of this block
 
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int row = (warp & 3) * 32 + lane;   // TMEM lane: query row inside the S/dP/dQ tiles, key row for dK/dV
+  const int half = warp >> 2;               // key-column half in the dS pass, output-dim half in the drains
   const int jb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int nq = p.seq / 128;
 
@@ -246,13 +260,14 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_bwd_kernel(const __grid
   if (warp == 0) tmem_alloc(tmem_holder, 512);
   pdl_wait();               // PDL: setup above overlapped the predecessor's tail; global reads start below
   pdl_launch_dependents();
-  s_bias[tid] = (p.mask != nullptr && p.mask[(size_t)b * p.seq + jb * 128 + tid] == 0) ? kMaskBias : 0.f;
+  if (tid < 128)
+    s_bias[tid] = (p.mask != nullptr && p.mask[(size_t)b * p.seq + jb * 128 + tid] == 0) ? kMaskBias : 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_holder;
   const uint32_t tm_s = tmem, tm_dp = tmem + 128, tm_dv = tmem + 256, tm_dk = tmem + 320, tm_dq = tmem + 384;
-  const uint32_t lane_base = ((uint32_t)(warp * 32)) << 16;
+  const uint32_t lane_base = ((uint32_t)((warp & 3) * 32)) << 16;
 
   const int row0 = b * p.seq;
   const int col_q = h * 64, col_k = p.hidden + h * 64, col_v = 2 * p.hidden + h * 64;
@@ -271,7 +286,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_bwd_kernel(const __grid
   uint32_t ph_q = 0, ph_s = 0, ph_mma = 0;
 
   for (int i = 0; i < nq; ++i) {
-    const int q_row = i * 128 + tid;  // this thread's query row in the sequence
+    const int q_row = i * 128 + row;  // this thread's query row in the sequence
     if (tid == 0) {
       mbar_expect_tx(bar_q, 2 * TILE_BYTES);
       tma_load_2d(sQ, &tmap_qkv, bar_q, col_q, row0 + i * 128);
@@ -293,7 +308,8 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_bwd_kernel(const __grid
     ph_q ^= 1;
     __syncwarp();
 
-    // delta = rowsum(dO * O) and the row's log-sum-exp, straight from HBM while the MMAs run
+    // delta = rowsum(dO * O) and the row's log-sum-exp, straight from HBM while the MMAs run (both threads of a row
+    // compute the same value; 16 loads each)
     float delta = 0.f;
     {
       const __nv_bfloat16* o_row = p.ctx_in + (size_t)(row0 + q_row) * p.hidden + h * 64;
@@ -312,21 +328,22 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_bwd_kernel(const __grid
     ph_s ^= 1;
     tc_fence_after();
 #pragma unroll 1
-    for (int c = 0; c < 4; ++c) {
+    for (int c = 0; c < 2; ++c) {
+      const int cb = half * 64 + c * 32;   // first key column of this chunk inside the 128-key block
       uint32_t vs[32], vd[32];
-      tmem_ld32(tm_s + lane_base + c * 32, vs);
-      tmem_ld32(tm_dp + lane_base + c * 32, vd);
+      tmem_ld32(tm_s + lane_base + cb, vs);
+      tmem_ld32(tm_dp + lane_base + cb, vd);
       tmem_ld_wait();
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
         const unsigned long long idx =
-            (((unsigned long long)(b * p.heads + h) * p.seq + q_row) * p.seq) + jb * 128 + c * 32 + g * 8;
+            (((unsigned long long)(b * p.heads + h) * p.seq + q_row) * p.seq) + jb * 128 + cb + g * 8;
         const uint32_t keep = dropout_keep8(drop, idx);
         float pd[8], ds[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
           const int cc = g * 8 + e;
-          const float pr = exp2f(__uint_as_float(vs[cc]) * c2 + s_bias[c * 32 + cc] - lse2);
+          const float pr = exp2f(__uint_as_float(vs[cc]) * c2 + s_bias[cb + cc] - lse2);
           const bool kp = (keep >> e) & 1u;
           pd[e] = kp ? pr * drop.scale : 0.f;
           const float dp = kp ? __uint_as_float(vd[cc]) * drop.scale : 0.f;
@@ -335,10 +352,10 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_bwd_kernel(const __grid
         uint4 o;
         o.x = pack_bf16(pd[0], pd[1]); o.y = pack_bf16(pd[2], pd[3]);
         o.z = pack_bf16(pd[4], pd[5]); o.w = pack_bf16(pd[6], pd[7]);
-        st_tile_chunk(sP, tid, c * 4 + g, o);
+        st_tile_chunk(sP, row, half * 8 + c * 4 + g, o);
         o.x = pack_bf16(ds[0], ds[1]); o.y = pack_bf16(ds[2], ds[3]);
         o.z = pack_bf16(ds[4], ds[5]); o.w = pack_bf16(ds[6], ds[7]);
-        st_tile_chunk(sdS, tid, c * 4 + g, o);
+        st_tile_chunk(sdS, row, half * 8 + c * 4 + g, o);
       }
     }
     fence_proxy_async_smem();
@@ -369,13 +386,12 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_bwd_kernel(const __grid
     mbar_wait(bar_mma, ph_mma);
     ph_mma ^= 1;
     tc_fence_after();
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
+    {
       uint32_t v[32];
-      tmem_ld32(tm_dq + lane_base + c * 32, v);
+      tmem_ld32(tm_dq + lane_base + half * 32, v);
       tmem_ld_wait();
       if (p.dq_accum == nullptr) {
-        __nv_bfloat16* dst = p.d_qkv + (size_t)(row0 + q_row) * (3 * p.hidden) + col_q + c * 32;
+        __nv_bfloat16* dst = p.d_qkv + (size_t)(row0 + q_row) * (3 * p.hidden) + col_q + half * 32;
 #pragma unroll
         for (int e = 0; e < 32; e += 8) {
           uint4 o;
@@ -386,7 +402,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_bwd_kernel(const __grid
           stg16(dst + e, o);
         }
       } else {
-        float* dst = p.dq_accum + (size_t)(row0 + q_row) * p.hidden + h * 64 + c * 32;
+        float* dst = p.dq_accum + (size_t)(row0 + q_row) * p.hidden + h * 64 + half * 32;
 #pragma unroll
         for (int e = 0; e < 32; ++e) atomicAdd(dst + e, __uint_as_float(v[e]));
       }
@@ -395,32 +411,29 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_bwd_kernel(const __grid
     __syncthreads();
   }
 
-  // dK, dV for this thread's key row
+  // dK, dV for this thread's key row (32 of the 64 head dims each)
   {
-    const int k_row = jb * 128 + tid;
-    __nv_bfloat16* dk = p.d_qkv + (size_t)(row0 + k_row) * (3 * p.hidden) + col_k;
-    __nv_bfloat16* dv = p.d_qkv + (size_t)(row0 + k_row) * (3 * p.hidden) + col_v;
+    const int k_row = jb * 128 + row;
+    __nv_bfloat16* dk = p.d_qkv + (size_t)(row0 + k_row) * (3 * p.hidden) + col_k + half * 32;
+    __nv_bfloat16* dv = p.d_qkv + (size_t)(row0 + k_row) * (3 * p.hidden) + col_v + half * 32;
     tc_fence_after();
+    uint32_t v[32], w[32];
+    tmem_ld32(tm_dk + lane_base + half * 32, v);
+    tmem_ld32(tm_dv + lane_base + half * 32, w);
+    tmem_ld_wait();
 #pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      uint32_t v[32], w[32];
-      tmem_ld32(tm_dk + lane_base + c * 32, v);
-      tmem_ld32(tm_dv + lane_base + c * 32, w);
-      tmem_ld_wait();
-#pragma unroll
-      for (int e = 0; e < 32; e += 8) {
-        uint4 o;
-        o.x = pack_bf16(__uint_as_float(v[e]), __uint_as_float(v[e + 1]));
-        o.y = pack_bf16(__uint_as_float(v[e + 2]), __uint_as_float(v[e + 3]));
-        o.z = pack_bf16(__uint_as_float(v[e + 4]), __uint_as_float(v[e + 5]));
-        o.w = pack_bf16(__uint_as_float(v[e + 6]), __uint_as_float(v[e + 7]));
-        stg16(dk + c * 32 + e, o);
-        o.x = pack_bf16(__uint_as_float(w[e]), __uint_as_float(w[e + 1]));
-        o.y = pack_bf16(__uint_as_float(w[e + 2]), __uint_as_float(w[e + 3]));
-        o.z = pack_bf16(__uint_as_float(w[e + 4]), __uint_as_float(w[e + 5]));
-        o.w = pack_bf16(__uint_as_float(w[e + 6]), __uint_as_float(w[e + 7]));
-        stg16(dv + c * 32 + e, o);
-      }
+    for (int e = 0; e < 32; e += 8) {
+      uint4 o;
+      o.x = pack_bf16(__uint_as_float(v[e]), __uint_as_float(v[e + 1]));
+      o.y = pack_bf16(__uint_as_float(v[e + 2]), __uint_as_float(v[e + 3]));
+      o.z = pack_bf16(__uint_as_float(v[e + 4]), __uint_as_float(v[e + 5]));
+      o.w = pack_bf16(__uint_as_float(v[e + 6]), __uint_as_float(v[e + 7]));
+      stg16(dk + e, o);
+      o.x = pack_bf16(__uint_as_float(w[e]), __uint_as_float(w[e + 1]));
+      o.y = pack_bf16(__uint_as_float(w[e + 2]), __uint_as_float(w[e + 3]));
+      o.z = pack_bf16(__uint_as_float(w[e + 4]), __uint_as_float(w[e + 5]));
+      o.w = pack_bf16(__uint_as_float(w[e + 6]), __uint_as_float(w[e + 7]));
+      stg16(dv + e, o);
     }
   }
   tc_fence_before();
@@ -434,8 +447,8 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_bwd_kernel(const __grid
 // fp32 dQ accumulator [tokens, hidden] -> the Q column block of d_qkv (bf16 [tokens, 3*hidden])
 __global__ void dq_convert_kernel(const float* __restrict__ acc, __nv_bfloat16* __restrict__ d_qkv, long long tokens,
                                   int hidden) {
-  pdl_wait();               // PDL: predecessors complete + visible before any global access
-  pdl_launch_dependents();  // let the next kernel in the stream begin launching
+  pdl_wait();
+  pdl_launch_dependents();
   const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (i >= tokens * hidden) return;
   const long long t = i / hidden;
@@ -447,7 +460,7 @@ __global__ void dq_convert_kernel(const float* __restrict__ acc, __nv_bfloat16* 
   *reinterpret_cast<uint2*>(d_qkv + t * 3 * hidden + c) = o;
 }
 
-constexpr int kFwdSmem = 5 * TILE_BYTES + 64 + 512 * 4 + 1024;
+constexpr int kFwdSmem = 5 * TILE_BYTES + 64 + 512 * 4 + 256 * 4 + 1024;
 constexpr int kBwdSmem = 8 * TILE_BYTES + 64 + 128 * 4 + 1024;
 
 static int32_t check_attn_shapes(const char* who, int64_t batch, int64_t seq, int64_t heads, int64_t head_dim) {
@@ -531,10 +544,10 @@ extern "C" int32_t b2_attention_bwd(const void* qkv, const int64_t* attention_ma
   count_launches(1);
   if (p.dq_accum) {
     const long long n4 = tokens * hidden / 4;
-    B2_LAUNCH(dq_convert_kernel, (unsigned)((n4 + 255) / 256), 256, 0, stream, p.dq_accum, (__nv_bfloat16*)d_qkv, tokens,
-                                                                        (int)hidden);
+    B2_LAUNCH(dq_convert_kernel, (unsigned)((n4 + 255) / 256), 256, 0, stream, p.dq_accum, (__nv_bfloat16*)d_qkv,
+              tokens, (int)hidden);
     B2_CUDA(cudaGetLastError());
-  count_launches(1);
+    count_launches(1);
   }
   return 0;
 }
