@@ -28,7 +28,7 @@ extern "C" {
 /* ------------------------------------------------------------------------------------------------------ */
 const char* b2_last_error(void);
 int32_t b2_abi_version(void);             /* bumped when a struct below changes */
-#define B2_ABI_VERSION 4
+#define B2_ABI_VERSION 5
 int64_t b2_launch_count(void);            /* kernels launched by this library so far (process-wide) */
 
 /* ------------------------------------------------------------------------------------------------------ */
@@ -74,6 +74,7 @@ typedef struct b2_gemm_args {
   int32_t force_splits;   /* 0 = auto, else >= 1                                                             */
   int32_t force_kernel;   /* 0 = auto, 1 = single-CTA 128xBN kernel, 2 = CTA-pair (cta_group::2) 256xBN kernel        */
   void* debug_timing;     /* NULL, or device int64[grid][8]: clock64 stamps of the CTA-pair kernel's phases          */
+  float* colsum_out;      /* NULL, or fp32 [N]: += column sums of the (bf16-rounded) output D, by atomic add        */
 } b2_gemm_args_t;
 
 int32_t b2_gemm_bf16(const b2_gemm_args_t* args, void* stream);
@@ -136,7 +137,9 @@ int32_t b2_attention_fwd(const void* qkv, const int64_t* attention_mask, int64_t
 int32_t b2_attention_bwd(const void* qkv, const int64_t* attention_mask, const void* ctx, const void* d_ctx,
                          const float* lse, int64_t batch, int64_t seq, int64_t heads, int64_t head_dim,
                          float dropout_p, const void* rng_state, uint32_t rng_site, void* d_qkv,
-                         float* dq_accum /* fp32 [batch*seq, hidden], only for seq > 128 */, void* stream);
+                         float* dq_accum /* fp32 [batch*seq, hidden], only for seq > 128 */,
+                         float* dbias_accum /* NULL, or fp32 [3*hidden]: += column sums of d_qkv (QKV bias grad) */,
+                         void* stream);
 
 /* ------------------------------------------------------------------------------------------------------ */
 /* head: BertPooler (modeling_bert.py:462-468) + dropout + classifier (:1123-1124) + CrossEntropyLoss       */
@@ -183,6 +186,12 @@ int32_t b2_bucket_reduce_adamw(const void* const* peer_grads, void* const* peer_
 /* ++step (AdamW t) and ++rng step (dropout stream) on the device: keeps CUDA-graph replays stateful        */
 int32_t b2_step_advance(int64_t* step_counter, void* rng_state, void* stream);
 int32_t b2_rng_seed(void* rng_state, uint64_t seed, uint64_t step, void* stream);
+
+/* segments[i] = {src element offset in `src` (fp32), dst element offset in `dst` (bf16), count}: dst <- bf16(src), then
+ * src <- 0.  One launch turns the per-step fp32 bias-gradient accumulators (filled by atomics from the GEMM and
+ * attention-backward epilogues) into bf16 gradients and re-arms them.                                           */
+int32_t b2_accum_finish(float* src, void* dst, const int64_t* segments /* device [n][3] */, int64_t n_segments,
+                        int64_t max_count, void* stream);
 
 /* bf16 <- fp32 cast of a flat range (initial shadow weights, load_state_dict) and zero fill                 */
 int32_t b2_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream);

@@ -8,7 +8,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libb2ddpbert.so")
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 MAJOR_K, MAJOR_MN = 0, 1
 EPI_NONE, EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_DROPOUT_RESIDUAL, EPI_RESIDUAL, EPI_GELU_BWD = 0, 1, 2, 3, 4, 5
@@ -27,7 +27,7 @@ class GemmArgs(C.Structure):
         ("D", vp), ("ldd", i64), ("epilogue", i32),
         ("bias", vp), ("aux_in", vp), ("ld_aux_in", i64), ("aux_out", vp), ("ld_aux_out", i64),
         ("dropout_p", f32), ("rng_state", vp), ("rng_site", u32),
-        ("workspace", vp), ("workspace_bytes", i64), ("force_bn", i32), ("force_splits", i32), ("force_kernel", i32), ("debug_timing", vp),
+        ("workspace", vp), ("workspace_bytes", i64), ("force_bn", i32), ("force_splits", i32), ("force_kernel", i32), ("debug_timing", vp), ("colsum_out", vp),
     ]
 
 
@@ -48,7 +48,8 @@ _SIGNATURES = {
     "b2_layernorm_bwd": [vp, vp, vp, vp, vp, vp, i64, i64, f32, vp, u32, i32, vp, vp, vp, vp, vp, vp, i64, vp],
     "b2_colsum": [vp, i64, i64, i64, vp, vp, i64, vp],
     "b2_attention_fwd": [vp, vp, i64, i64, i64, i64, f32, vp, u32, vp, vp, vp],
-    "b2_attention_bwd": [vp, vp, vp, vp, vp, i64, i64, i64, i64, f32, vp, u32, vp, vp, vp],
+    "b2_attention_bwd": [vp, vp, vp, vp, vp, i64, i64, i64, i64, f32, vp, u32, vp, vp, vp, vp],
+    "b2_accum_finish": [vp, vp, vp, i64, i64, vp],
     "b2_head_fwd": [vp, i64, i64, i64, vp, vp, vp, vp, i64, f32, vp, u32, vp, vp, vp],
     "b2_ce_fwd_bwd": [vp, vp, i64, i64, vp, vp, vp],
     "b2_head_bwd": [vp, vp, vp, i64, i64, i64, vp, vp, i64, f32, vp, u32, vp, vp, vp, vp, vp, i32, vp, vp],

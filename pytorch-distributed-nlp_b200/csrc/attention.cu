@@ -39,7 +39,23 @@ struct AttnParams {
   // backward
   const __nv_bfloat16* ctx_in; const __nv_bfloat16* d_ctx;
   __nv_bfloat16* d_qkv; float* dq_accum;
+  float* dbias;                   // optional fp32 [3*hidden]: += column sums of d_qkv (QKV bias gradient)
 };
+
+// Sum v[j] over the 32 lanes for every j: 31 shuffles (butterfly with halving); lane l returns the total of column l.
+__device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool upper = (lane & off) != 0;
+#pragma unroll
+    for (int j = 0; j < off; ++j) {
+      const float send = upper ? v[j] : v[j + off];
+      const float keep = upper ? v[j + off] : v[j];
+      v[j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return v[0];
+}
 
 // ------------------------------------------------------------------------------------------------------------
 // forward: grid (seq/128, heads, batch)
@@ -401,6 +417,13 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_bwd_kernel(const __grid
           o.w = pack_bf16(__uint_as_float(v[e + 6]), __uint_as_float(v[e + 7]));
           stg16(dst + e, o);
         }
+        if (p.dbias != nullptr) {
+          float f[32];
+#pragma unroll
+          for (int e = 0; e < 32; ++e) f[e] = bf16_round(__uint_as_float(v[e]));
+          const float t = warp_colsum32(f, lane);
+          atomicAdd(p.dbias + col_q + half * 32 + lane, t);
+        }
       } else {
         float* dst = p.dq_accum + (size_t)(row0 + q_row) * p.hidden + h * 64 + half * 32;
 #pragma unroll
@@ -434,6 +457,17 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_bwd_kernel(const __grid
       o.z = pack_bf16(__uint_as_float(w[e + 4]), __uint_as_float(w[e + 5]));
       o.w = pack_bf16(__uint_as_float(w[e + 6]), __uint_as_float(w[e + 7]));
       stg16(dv + e, o);
+    }
+    if (p.dbias != nullptr) {
+      float f[32], g[32];
+#pragma unroll
+      for (int e = 0; e < 32; ++e) {
+        f[e] = bf16_round(__uint_as_float(v[e]));
+        g[e] = bf16_round(__uint_as_float(w[e]));
+      }
+      const float tk = warp_colsum32(f, lane), tv = warp_colsum32(g, lane);
+      atomicAdd(p.dbias + col_k + half * 32 + lane, tk);
+      atomicAdd(p.dbias + col_v + half * 32 + lane, tv);
     }
   }
   tc_fence_before();
@@ -510,7 +544,7 @@ extern "C" int32_t b2_attention_fwd(const void* qkv, const int64_t* attention_ma
 extern "C" int32_t b2_attention_bwd(const void* qkv, const int64_t* attention_mask, const void* ctx, const void* d_ctx,
                                     const float* lse, int64_t batch, int64_t seq, int64_t heads, int64_t head_dim,
                                     float dropout_p, const void* rng_state, uint32_t rng_site, void* d_qkv,
-                                    float* dq_accum, void* stream_) {
+                                    float* dq_accum, float* dbias_accum, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   B2_REQUIRE(qkv && ctx && d_ctx && lse && d_qkv, "attention_bwd: null pointer");
   int32_t st = check_attn_shapes("attention_bwd", batch, seq, heads, head_dim);
@@ -532,6 +566,9 @@ extern "C" int32_t b2_attention_bwd(const void* qkv, const int64_t* attention_ma
   p.ctx_in = (const __nv_bfloat16*)ctx; p.d_ctx = (const __nv_bfloat16*)d_ctx;
   p.d_qkv = (__nv_bfloat16*)d_qkv;
   p.dq_accum = seq > 128 ? dq_accum : nullptr;
+  B2_REQUIRE(dbias_accum == nullptr || seq == 128,
+             "attention_bwd: the fused QKV bias gradient covers seq == 128 (longer sequences: use b2_colsum)");
+  p.dbias = dbias_accum;
   if (p.dq_accum) B2_CUDA(cudaMemsetAsync(p.dq_accum, 0, (size_t)tokens * hidden * 4, stream));
   static bool attr = false;
   if (!attr) {

@@ -460,6 +460,7 @@ static void fill_params(GemmKernelParams& p, const b2_gemm_args_t& a, int tile_m
   p.partial = (float*)a.workspace;
   p.dropout_p = a.dropout_p; p.rng = (const unsigned long long*)a.rng_state; p.rng_site = a.rng_site;
   p.timing = (long long*)a.debug_timing;
+  p.colsum = a.colsum_out;
 }
 
 static int32_t launch_splitk_reduce(const b2_gemm_args_t& a, int splits, cudaStream_t stream) {

@@ -24,6 +24,7 @@ struct GemmKernelParams {
   float* partial;  // split-K fp32 partials [splits][M][N]
   float dropout_p; const unsigned long long* rng; unsigned rng_site;
   long long* timing;  // optional [gridDim.x][8] clock64 stamps (profiling aid, see tools/gemm_timeline.py)
+  float* colsum;      // optional fp32 [N]: += column sums of the bf16 output (bias gradient of the producing layer)
 };
 
 #ifdef __CUDACC__
@@ -185,6 +186,20 @@ __device__ __forceinline__ void epilogue_tile(const GemmKernelParams& p, const D
       }
       row_write_bf16(stage, lane, f);
       __syncwarp();
+      if (p.colsum != nullptr) {
+        // bias gradient of the layer that produced this tensor: column sums of what was just rounded to bf16; lane l
+        // owns columns 2l, 2l+1 of the 64-wide group and walks the 32 staged rows (conflict-free 4-byte reads)
+        float s0 = 0.f, s1 = 0.f;
+        const int nr = rows_valid < 32 ? rows_valid : 32;
+        for (int r = 0; r < nr; ++r) {
+          const uint32_t w = *reinterpret_cast<const uint32_t*>(stage + r * 128 + (((lane >> 2) ^ (r & 7)) << 4) +
+                                                                (lane & 3) * 4);
+          s0 += bf16_lo(w);
+          s1 += bf16_hi(w);
+        }
+        atomicAdd(p.colsum + n + 2 * lane, s0);
+        atomicAdd(p.colsum + n + 2 * lane + 1, s1);
+      }
       tile_s2g(stage, reinterpret_cast<uint8_t*>(p.D + (size_t)row0 * p.ldd + n), p.ldd * 2, lane, rows_valid);
     }
     __syncwarp();

@@ -124,9 +124,32 @@ __global__ void cast_bf16_f32_kernel(const __nv_bfloat16* __restrict__ src, floa
   if (i < n) dst[i] = __bfloat162float(src[i]);
 }
 
+// segments [n][3] = {src offset, dst offset, count}: dst(bf16) <- src(fp32); src <- 0.  grid = (ceil(max_count/256), n)
+__global__ void accum_finish_kernel(float* __restrict__ src, __nv_bfloat16* __restrict__ dst,
+                                    const long long* __restrict__ seg) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const long long so = seg[blockIdx.y * 3], d0 = seg[blockIdx.y * 3 + 1], cnt = seg[blockIdx.y * 3 + 2];
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < cnt) {
+    dst[d0 + i] = __float2bfloat16_rn(src[so + i]);
+    src[so + i] = 0.f;
+  }
+}
+
 }  // namespace b2
 
 using namespace b2;
+
+extern "C" int32_t b2_accum_finish(float* src, void* dst, const int64_t* segments, int64_t n_segments,
+                                   int64_t max_count, void* stream_) {
+  B2_REQUIRE(src && dst && segments && n_segments > 0 && max_count > 0, "accum_finish: bad args");
+  dim3 grid((unsigned)((max_count + 255) / 256), (unsigned)n_segments);
+  B2_LAUNCH(accum_finish_kernel, grid, 256, 0, stream_, src, (__nv_bfloat16*)dst, (const long long*)segments);
+  B2_CUDA(cudaGetLastError());
+  count_launches(1);
+  return 0;
+}
 
 extern "C" int32_t b2_bucket_reduce_adamw(const void* const* peer_grads, void* const* peer_shadow, int32_t world,
                                           int32_t rank, float* master, float* exp_avg, float* exp_avg_sq,

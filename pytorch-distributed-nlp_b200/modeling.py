@@ -401,6 +401,17 @@ class _Engine:
         self.partials = torch.empty(8 << 20, dtype=torch.uint8, device=self.dev)
         self._ws = {}
         self._saved = None
+        # fp32 accumulators for the bias gradients that kernels produce as a side effect of their epilogues (QKV bias
+        # from attention backward, intermediate bias from the GELU' dgrad): per layer [3H | I]; one finishing launch
+        # per step turns them into bf16 gradients and re-zeroes them
+        per = 3 * self.H + self.I
+        self.bias_acc = torch.zeros(max(1, self.nl * per), dtype=torch.float32, device=self.dev)
+        segs = []
+        for l in range(self.nl):
+            pre = "bert.encoder.layer.%d." % l
+            segs.append([l * per, self.lay.off(pre + "attention.self.query.bias"), 3 * self.H])
+            segs.append([l * per + 3 * self.H, self.lay.off(pre + "intermediate.dense.bias"), self.I])
+        self.bias_segs = torch.tensor(segs if segs else [[0, 0, 0]], dtype=torch.int64, device=self.dev)
         s = self.stream()
         L.call("b2_embed_owner_init", L.ptr(self.owner), cfg.vocab_size, s)
         L.call("b2_rng_seed", L.ptr(self.rng), int(torch.initial_seed()) & ((1 << 63) - 1), 0, s)
@@ -461,7 +472,7 @@ class _Engine:
         return ws
 
     def gemm(self, M, N, K, A, lda, a_major, Bm, ldb, b_major, D, ldd, epi=L.EPI_NONE, bias=None, aux_in=None,
-             ld_aux_in=0, aux_out=None, ld_aux_out=0, p=0.0, site=0, split=False, stream=None):
+             ld_aux_in=0, aux_out=None, ld_aux_out=0, p=0.0, site=0, split=False, stream=None, colsum=None):
         a = L.GemmArgs()
         a.M, a.N, a.K = M, N, K
         a.A, a.lda, a.a_major = A, lda, a_major
@@ -476,6 +487,8 @@ class _Engine:
         a.force_bn = int(os.environ.get("B2_FORCE_BN", "0"))
         a.force_splits = 0
         a.force_kernel = int(os.environ.get("B2_FORCE_KERNEL", "0"))
+        a.debug_timing = None
+        a.colsum_out = colsum
         L.call("b2_gemm_bf16", a, stream if stream is not None else self.stream())
 
     # ---- forward --------------------------------------------------------------------------------------------------------
@@ -613,11 +626,11 @@ class _Engine:
             dy2 = ws["dzd"]
             self.gemm(H, I, M, dy2.data_ptr(), H, MN, a["h"].data_ptr(), I, MN, g(pre + "output.dense.weight"), I,
                       split=True)
+            acc_l = self.bias_acc.data_ptr() + 4 * l * (3 * H + I)
+            # dU = (dY2 W2) * gelu'(u); its column sums (= intermediate bias gradient) accumulate in the same epilogue
             self.gemm(M, I, H, dy2.data_ptr(), H, KM, w(pre + "output.dense.weight"), I, MN, ws["dU"].data_ptr(), I,
-                      L.EPI_GELU_BWD, aux_in=a["u"].data_ptr(), ld_aux_in=I)
+                      L.EPI_GELU_BWD, aux_in=a["u"].data_ptr(), ld_aux_in=I, colsum=acc_l + 4 * 3 * H)
             # --- BertIntermediate
-            L.call("b2_colsum", ws["dU"].data_ptr(), M, I, I, g(pre + "intermediate.dense.bias"), scratch,
-                   scratch_bytes, s)
             self.gemm(I, H, M, ws["dU"].data_ptr(), I, MN, a["x1"].data_ptr(), H, MN,
                       g(pre + "intermediate.dense.weight"), H, split=True)
             self.gemm(M, H, I, ws["dU"].data_ptr(), I, KM, w(pre + "intermediate.dense.weight"), H, MN,
@@ -636,13 +649,19 @@ class _Engine:
             # --- BertSelfAttention
             L.call("b2_attention_bwd", a["qkv"].data_ptr(), L.ptr(mask), a["ctx"].data_ptr(), ws["dctx"].data_ptr(),
                    a["lse"].data_ptr(), B, S, self.heads, 64, p_a, rng, 1 + 3 * l, ws["dqkv"].data_ptr(),
-                   L.ptr(ws["dq_accum"]), s)
-            L.call("b2_colsum", ws["dqkv"].data_ptr(), M, 3 * H, 3 * H, g(pre + "attention.self.query.bias"), scratch,
-                   scratch_bytes, s)
+                   L.ptr(ws["dq_accum"]), acc_l if S == 128 else None, s)
+            if S != 128:   # long-sequence parity configs: separate column-sum pass into the same accumulator slot
+                L.call("b2_colsum", ws["dqkv"].data_ptr(), M, 3 * H, 3 * H, g(pre + "attention.self.query.bias"),
+                       scratch, scratch_bytes, s)
             self.gemm(3 * H, H, M, ws["dqkv"].data_ptr(), 3 * H, MN, x_in.data_ptr(), H, MN,
                       g(pre + "attention.self.query.weight"), H, split=True)
             self.gemm(M, H, 3 * H, ws["dqkv"].data_ptr(), 3 * H, KM, w(pre + "attention.self.query.weight"), H, MN,
                       dx.data_ptr(), H, L.EPI_RESIDUAL_F32, aux_in=ws["dz1"].data_ptr(), ld_aux_in=H)
+            # fp32 accumulators -> bf16 bias gradients of this layer (and re-arm them); for S != 128 the QKV segment's
+            # accumulator is unused (zero) and must not overwrite the colsum result: finish only the intermediate one
+            seg0 = 2 * l if S == 128 else 2 * l + 1
+            L.call("b2_accum_finish", self.bias_acc.data_ptr(), self.grads.data_ptr(),
+                   self.bias_segs.data_ptr() + 24 * seg0, (2 * l + 2) - seg0, I, s)
             if hooks is not None:
                 hooks._bucket_ready(1 + l)
         L.call("b2_embed_bwd", dx.data_ptr(), 1, ws["emb_pre"].data_ptr(), ws["emb_mean"].data_ptr(),

@@ -13,7 +13,7 @@ def _rng_state(dev, seed=77, step=3):
 
 
 def _call(M, N, K, A, lda, a_major, B, ldb, b_major, D, epi=L.EPI_NONE, bias=None, aux_in=None, aux_out=None,
-          p=0.0, rng=None, site=0, ws=None, bn=0, splits=0, kernel=0):
+          p=0.0, rng=None, site=0, ws=None, bn=0, splits=0, kernel=0, colsum=None):
     a = L.GemmArgs()
     a.M, a.N, a.K = M, N, K
     a.A, a.lda, a.a_major = A.data_ptr(), lda, a_major
@@ -25,6 +25,7 @@ def _call(M, N, K, A, lda, a_major, B, ldb, b_major, D, epi=L.EPI_NONE, bias=Non
     a.dropout_p, a.rng_state, a.rng_site = p, L.ptr(rng), site
     a.workspace, a.workspace_bytes = L.ptr(ws), (ws.numel() if ws is not None else 0)
     a.force_bn, a.force_splits, a.force_kernel = bn, splits, kernel
+    a.colsum_out = L.ptr(colsum)
     L.call("b2_gemm_bf16", a, torch.cuda.current_stream().cuda_stream)
     torch.cuda.synchronize()
 
@@ -152,10 +153,14 @@ def test_residual_and_gelu_bwd(cuda_dev):
     _call(M, N, K, A, K, L.MAJOR_K, B, N, L.MAJOR_MN, D, L.EPI_RESIDUAL, aux_in=R)
     _check(D, A.float() @ B.float() + R.float())
     U = _rand((M, N), cuda_dev)
-    _call(M, N, K, A, K, L.MAJOR_K, B, N, L.MAJOR_MN, D, L.EPI_GELU_BWD, aux_in=U)
+    cs = torch.zeros(N, dtype=torch.float32, device=cuda_dev)
+    _call(M, N, K, A, K, L.MAJOR_K, B, N, L.MAJOR_MN, D, L.EPI_GELU_BWD, aux_in=U, colsum=cs)
     u = U.float().requires_grad_(True)
     torch.nn.functional.gelu(u).sum().backward()
     _check(D, (A.float() @ B.float()) * u.grad)
+    # fused bias gradient: column sums of the bf16 output, accumulated by the epilogue
+    ref = D.float().sum(0)
+    assert (cs - ref).abs().max().item() <= 1e-3 * ref.abs().max().item() + 1e-3
 
 
 def test_linearity_full_size(cuda_dev):

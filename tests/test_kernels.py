@@ -185,9 +185,12 @@ def test_attention_fwd_bwd(cuda_dev, Sq, masked, p):
     dctx = rnd((M, H), dev)
     dqkv = torch.zeros(M, 3 * H, dtype=bf, device=dev)
     dq_acc = torch.empty(M, H, dtype=torch.float32, device=dev) if Sq > 128 else None
+    dbias = torch.zeros(3 * H, dtype=torch.float32, device=dev) if Sq == 128 else None
     L.call("b2_attention_bwd", qkv.data_ptr(), L.ptr(mask), ctx.data_ptr(), dctx.data_ptr(), lse.data_ptr(), B, Sq,
-           nh, 64, p, rs.data_ptr(), 4, dqkv.data_ptr(), L.ptr(dq_acc), S())
+           nh, 64, p, rs.data_ptr(), 4, dqkv.data_ptr(), L.ptr(dq_acc), L.ptr(dbias), S())
     torch.cuda.synchronize()
+    if dbias is not None:   # fused QKV bias gradient == column sums of what was written
+        assert rel_l2(dbias, dqkv.float().sum(0)) < 1e-4
     ref.backward(dctx.float())
     for i, nm in enumerate("qkv"):
         e = rel_l2(dqkv[:, i * H:(i + 1) * H].float(), qr.grad[:, i * H:(i + 1) * H])
