@@ -661,7 +661,7 @@ class _Engine:
             # accumulator is unused (zero) and must not overwrite the colsum result: finish only the intermediate one
             seg0 = 2 * l if S == 128 else 2 * l + 1
             L.call("b2_accum_finish", self.bias_acc.data_ptr(), self.grads.data_ptr(),
-                   self.bias_segs.data_ptr() + 24 * seg0, (2 * l + 2) - seg0, I, s)
+                   self.bias_segs.data_ptr() + 24 * seg0, (2 * l + 2) - seg0, max(3 * H, I), s)
             if hooks is not None:
                 hooks._bucket_ready(1 + l)
         L.call("b2_embed_bwd", dx.data_ptr(), 1, ws["emb_pre"].data_ptr(), ws["emb_mean"].data_ptr(),

@@ -104,10 +104,12 @@ def test_tiny_trajectory_eager_and_fused(cuda_dev):
         losses2.append(step.loss_to_host())
     assert step.graph is not None
     for a, c in zip(losses, losses2):   # ulp-level dlogits differences (torch CE vs our CE kernel) grow over the steps
-        assert abs(a - c) <= 1e-4, (losses, losses2)
+        assert abs(a - c) <= 5e-4, (losses, losses2)
     sd2 = model2.state_dict()
-    for k in sd:   # same kernels, same order; only d(loss)/d(logits) comes from torch in one case, our CE kernel in the other
-        assert float((sd[k].double() - sd2[k].double()).abs().max()) <= 5e-6, k
+    # same kernels, same order; d(loss)/d(logits) comes from torch in one case and from our CE kernel in the other, and
+    # the fused bias-gradient sums use fp32 atomics (order not fixed): ulp-level differences, amplified over 5 steps
+    for k in sd:
+        assert float((sd[k].double() - sd2[k].double()).abs().max()) <= 2e-5, k
 
 
 def test_state_dict_round_trip_and_hf_loadable(cuda_dev):
