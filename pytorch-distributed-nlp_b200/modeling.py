@@ -401,6 +401,8 @@ class _Engine:
         self.partials = torch.empty(8 << 20, dtype=torch.uint8, device=self.dev)
         self._ws = {}
         self._saved = None
+        self.wgrad_stream = torch.cuda.Stream(device=self.dev)
+        self.use_wgrad_stream = os.environ.get("B2_WGRAD_STREAM", "1") != "0"
         # fp32 accumulators for the bias gradients that kernels produce as a side effect of their epilogues (QKV bias
         # from attention backward, intermediate bias from the GELU' dgrad): per layer [3H | I]; one finishing launch
         # per step turns them into bf16 gradients and re-zeroes them
@@ -462,9 +464,11 @@ class _Engine:
             "dlogits": e(B, self.C, dtype=f32), "dloss_logits": e(B, self.C, dtype=f32),
             # gradient of the residual stream: fp32 (12 layers of residual adds would otherwise each round it to bf16);
             # dzd / dz1d are the bf16 (dropout-masked) copies the tensor cores consume
-            "dxA": e(M, H, dtype=f32), "dxB": e(M, H, dtype=f32), "dz": e(M, H, dtype=f32), "dzd": e(M, H),
-            "dz1": e(M, H, dtype=f32), "dz1d": e(M, H), "emb_dx": e(M, H),
-            "dU": e(M, I), "dctx": e(M, H), "dqkv": e(M, 3 * H), "head_scratch": e(B, H, dtype=f32),
+            "dxA": e(M, H, dtype=f32), "dxB": e(M, H, dtype=f32), "dz": e(M, H, dtype=f32),
+            "dz1": e(M, H, dtype=f32), "emb_dx": e(M, H), "dctx": e(M, H), "head_scratch": e(B, H, dtype=f32),
+            # operands of the weight-gradient GEMMs, double-buffered by layer parity (see _backward_from_dlogits)
+            "dzd": [e(M, H), e(M, H)], "dz1d": [e(M, H), e(M, H)], "dU": [e(M, I), e(M, I)],
+            "dqkv": [e(M, 3 * H), e(M, 3 * H)],
             "dq_accum": e(M, H, dtype=f32) if S > 128 else None,
             "zeros_tt": torch.zeros(B, S, dtype=torch.int64, device=dev),
         }
@@ -614,48 +618,72 @@ class _Engine:
         if hooks is not None:
             hooks._bucket_ready(len(self.lay.buckets) - 1)
         dx, dx_other = ws["dxA"], ws["dxB"]
+        # Weight gradients are off the critical path (only the optimizer consumes them): they run on a second stream,
+        # overlapping the dgrad / LayerNorm / attention chain of the main stream.  Their A operands (dzd, dU, dz1d,
+        # dqkv) are double-buffered by layer parity; the main stream may reuse a buffer set only after the weight
+        # gradients of the layer two steps earlier have drained (done[l + 2]).
+        main = torch.cuda.current_stream(self.dev)
+        side = self.wgrad_stream if self.use_wgrad_stream else main
+        ss = side.cuda_stream
+        done = {}
+
+        def fork():
+            if side is not main:
+                ev = torch.cuda.Event()
+                ev.record(main)
+                side.wait_event(ev)
+
         for l in reversed(range(self.nl)):
             a = ws["layers"][l]
             x_in = ws["layers"][l - 1]["x2"] if l > 0 else ws["emb_out"]
             pre = "bert.encoder.layer.%d." % l
+            st = l & 1
+            dzd, dU, dz1d, dqkv = ws["dzd"][st], ws["dU"][st], ws["dz1d"][st], ws["dqkv"][st]
+            if side is not main and (l + 2) in done:
+                main.wait_event(done[l + 2])
             # --- BertOutput: LN2 backward (+ dropout mask, bias grad), FFN2 wgrad/dgrad(+GELU')
             L.call("b2_layernorm_bwd", dx.data_ptr(), None, a["z2"].data_ptr(), a["mean2"].data_ptr(),
                    a["rstd2"].data_ptr(), w(pre + "output.LayerNorm.weight"), M, H, p_h, rng, 3 + 3 * l, 1,
-                   ws["dz"].data_ptr(), ws["dzd"].data_ptr(), g(pre + "output.LayerNorm.weight"),
+                   ws["dz"].data_ptr(), dzd.data_ptr(), g(pre + "output.LayerNorm.weight"),
                    g(pre + "output.LayerNorm.bias"), g(pre + "output.dense.bias"), scratch, scratch_bytes, s)
-            dy2 = ws["dzd"]
-            self.gemm(H, I, M, dy2.data_ptr(), H, MN, a["h"].data_ptr(), I, MN, g(pre + "output.dense.weight"), I,
-                      split=True)
+            fork()
+            self.gemm(H, I, M, dzd.data_ptr(), H, MN, a["h"].data_ptr(), I, MN, g(pre + "output.dense.weight"), I,
+                      split=True, stream=ss)
             acc_l = self.bias_acc.data_ptr() + 4 * l * (3 * H + I)
             # dU = (dY2 W2) * gelu'(u); its column sums (= intermediate bias gradient) accumulate in the same epilogue
-            self.gemm(M, I, H, dy2.data_ptr(), H, KM, w(pre + "output.dense.weight"), I, MN, ws["dU"].data_ptr(), I,
+            self.gemm(M, I, H, dzd.data_ptr(), H, KM, w(pre + "output.dense.weight"), I, MN, dU.data_ptr(), I,
                       L.EPI_GELU_BWD, aux_in=a["u"].data_ptr(), ld_aux_in=I, colsum=acc_l + 4 * 3 * H)
             # --- BertIntermediate
-            self.gemm(I, H, M, ws["dU"].data_ptr(), I, MN, a["x1"].data_ptr(), H, MN,
-                      g(pre + "intermediate.dense.weight"), H, split=True)
-            self.gemm(M, H, I, ws["dU"].data_ptr(), I, KM, w(pre + "intermediate.dense.weight"), H, MN,
+            fork()
+            self.gemm(I, H, M, dU.data_ptr(), I, MN, a["x1"].data_ptr(), H, MN,
+                      g(pre + "intermediate.dense.weight"), H, split=True, stream=ss)
+            self.gemm(M, H, I, dU.data_ptr(), I, KM, w(pre + "intermediate.dense.weight"), H, MN,
                       dx_other.data_ptr(), H, L.EPI_RESIDUAL_F32, aux_in=ws["dz"].data_ptr(), ld_aux_in=H)
             # --- BertSelfOutput
             L.call("b2_layernorm_bwd", dx_other.data_ptr(), None, a["z1"].data_ptr(), a["mean1"].data_ptr(),
                    a["rstd1"].data_ptr(), w(pre + "attention.output.LayerNorm.weight"), M, H, p_h, rng, 2 + 3 * l, 1,
-                   ws["dz1"].data_ptr(), ws["dz1d"].data_ptr(), g(pre + "attention.output.LayerNorm.weight"),
+                   ws["dz1"].data_ptr(), dz1d.data_ptr(), g(pre + "attention.output.LayerNorm.weight"),
                    g(pre + "attention.output.LayerNorm.bias"), g(pre + "attention.output.dense.bias"), scratch,
                    scratch_bytes, s)
-            dy1 = ws["dz1d"]
-            self.gemm(H, H, M, dy1.data_ptr(), H, MN, a["ctx"].data_ptr(), H, MN,
-                      g(pre + "attention.output.dense.weight"), H, split=True)
-            self.gemm(M, H, H, dy1.data_ptr(), H, KM, w(pre + "attention.output.dense.weight"), H, MN,
+            fork()
+            self.gemm(H, H, M, dz1d.data_ptr(), H, MN, a["ctx"].data_ptr(), H, MN,
+                      g(pre + "attention.output.dense.weight"), H, split=True, stream=ss)
+            self.gemm(M, H, H, dz1d.data_ptr(), H, KM, w(pre + "attention.output.dense.weight"), H, MN,
                       ws["dctx"].data_ptr(), H)
             # --- BertSelfAttention
             L.call("b2_attention_bwd", a["qkv"].data_ptr(), L.ptr(mask), a["ctx"].data_ptr(), ws["dctx"].data_ptr(),
-                   a["lse"].data_ptr(), B, S, self.heads, 64, p_a, rng, 1 + 3 * l, ws["dqkv"].data_ptr(),
+                   a["lse"].data_ptr(), B, S, self.heads, 64, p_a, rng, 1 + 3 * l, dqkv.data_ptr(),
                    L.ptr(ws["dq_accum"]), acc_l if S == 128 else None, s)
             if S != 128:   # long-sequence parity configs: separate column-sum pass into the same accumulator slot
-                L.call("b2_colsum", ws["dqkv"].data_ptr(), M, 3 * H, 3 * H, g(pre + "attention.self.query.bias"),
+                L.call("b2_colsum", dqkv.data_ptr(), M, 3 * H, 3 * H, g(pre + "attention.self.query.bias"),
                        scratch, scratch_bytes, s)
-            self.gemm(3 * H, H, M, ws["dqkv"].data_ptr(), 3 * H, MN, x_in.data_ptr(), H, MN,
-                      g(pre + "attention.self.query.weight"), H, split=True)
-            self.gemm(M, H, 3 * H, ws["dqkv"].data_ptr(), 3 * H, KM, w(pre + "attention.self.query.weight"), H, MN,
+            fork()
+            self.gemm(3 * H, H, M, dqkv.data_ptr(), 3 * H, MN, x_in.data_ptr(), H, MN,
+                      g(pre + "attention.self.query.weight"), H, split=True, stream=ss)
+            if side is not main:
+                done[l] = torch.cuda.Event()
+                done[l].record(side)
+            self.gemm(M, H, 3 * H, dqkv.data_ptr(), 3 * H, KM, w(pre + "attention.self.query.weight"), H, MN,
                       dx.data_ptr(), H, L.EPI_RESIDUAL_F32, aux_in=ws["dz1"].data_ptr(), ld_aux_in=H)
             # fp32 accumulators -> bf16 bias gradients of this layer (and re-arm them); for S != 128 the QKV segment's
             # accumulator is unused (zero) and must not overwrite the colsum result: finish only the intermediate one
@@ -663,6 +691,8 @@ class _Engine:
             L.call("b2_accum_finish", self.bias_acc.data_ptr(), self.grads.data_ptr(),
                    self.bias_segs.data_ptr() + 24 * seg0, (2 * l + 2) - seg0, max(3 * H, I), s)
             if hooks is not None:
+                if side is not main:
+                    main.wait_event(done[l])   # the bucket is complete only with this layer's weight gradients
                 hooks._bucket_ready(1 + l)
         L.call("b2_embed_bwd", dx.data_ptr(), 1, ws["emb_pre"].data_ptr(), ws["emb_mean"].data_ptr(),
                ws["emb_rstd"].data_ptr(), w("bert.embeddings.LayerNorm.weight"), ws["ids32"].data_ptr(),
@@ -672,5 +702,8 @@ class _Engine:
                g("bert.embeddings.token_type_embeddings.weight"), g("bert.embeddings.LayerNorm.weight"),
                g("bert.embeddings.LayerNorm.bias"), ws["emb_dx"].data_ptr(), scratch, scratch_bytes,
                self.owner.data_ptr(), s)
+        if side is not main and hooks is None:
+            for l in sorted(done)[:2]:       # the last two layers processed (0 and 1) may still be in flight
+                main.wait_event(done[l])
         if hooks is not None:
             hooks._bucket_ready(0)
