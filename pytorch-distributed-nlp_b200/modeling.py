@@ -402,6 +402,7 @@ class _Engine:
         self._ws = {}
         self._saved = None
         self.wgrad_stream = torch.cuda.Stream(device=self.dev)
+        self.opt_stream = torch.cuda.Stream(device=self.dev)
         self.use_wgrad_stream = os.environ.get("B2_WGRAD_STREAM", "1") != "0"
         # fp32 accumulators for the bias gradients that kernels produce as a side effect of their epilogues (QKV bias
         # from attention backward, intermediate bias from the GELU' dgrad): per layer [3H | I]; one finishing launch
@@ -615,8 +616,6 @@ class _Engine:
                w("bert.pooler.dense.weight"), w("classifier.weight"), self.C, p_c, rng, 1 + 3 * self.nl,
                g("bert.pooler.dense.weight"), g("bert.pooler.dense.bias"), g("classifier.weight"),
                g("classifier.bias"), ws["dxA"].data_ptr(), 1, ws["head_scratch"].data_ptr(), s)
-        if hooks is not None:
-            hooks._bucket_ready(len(self.lay.buckets) - 1)
         dx, dx_other = ws["dxA"], ws["dxB"]
         # Weight gradients are off the critical path (only the optimizer consumes them): they run on a second stream,
         # overlapping the dgrad / LayerNorm / attention chain of the main stream.  Their A operands (dzd, dU, dz1d,
@@ -633,6 +632,30 @@ class _Engine:
                 ev.record(main)
                 side.wait_event(ev)
 
+        # (head bucket is announced right after these helpers are defined)
+        opt = self.model._optimizer
+        overlap_opt = hooks is None and opt is not None and getattr(opt, "_armed", False)
+
+        def bucket_ready(idx, wg_event=None):
+            """bucket `idx` holds its final gradients once the main stream reaches this point (and `wg_event`,
+            the weight-gradient stream's marker for the layer, has fired)"""
+            if hooks is not None:
+                if wg_event is not None:
+                    main.wait_event(wg_event)
+                hooks._bucket_ready(idx)
+            elif overlap_opt:
+                # single GPU: the HBM-bound AdamW of this bucket runs on its own stream under the rest of backward
+                ev = torch.cuda.Event()
+                ev.record(main)
+                self.opt_stream.wait_event(ev)
+                if wg_event is not None:
+                    self.opt_stream.wait_event(wg_event)
+                b0, e0, _lbl = self.lay.buckets[idx]
+                opt.update_range(b0, e0, 1, 0, [self.grads.data_ptr()], [self.shadow.data_ptr()],
+                                 self.opt_stream.cuda_stream)
+                opt._pending.add(idx)
+
+        bucket_ready(len(self.lay.buckets) - 1)
         for l in reversed(range(self.nl)):
             a = ws["layers"][l]
             x_in = ws["layers"][l - 1]["x2"] if l > 0 else ws["emb_out"]
@@ -690,10 +713,7 @@ class _Engine:
             seg0 = 2 * l if S == 128 else 2 * l + 1
             L.call("b2_accum_finish", self.bias_acc.data_ptr(), self.grads.data_ptr(),
                    self.bias_segs.data_ptr() + 24 * seg0, (2 * l + 2) - seg0, max(3 * H, I), s)
-            if hooks is not None:
-                if side is not main:
-                    main.wait_event(done[l])   # the bucket is complete only with this layer's weight gradients
-                hooks._bucket_ready(1 + l)
+            bucket_ready(1 + l, done.get(l))   # complete only with this layer's weight gradients
         L.call("b2_embed_bwd", dx.data_ptr(), 1, ws["emb_pre"].data_ptr(), ws["emb_mean"].data_ptr(),
                ws["emb_rstd"].data_ptr(), w("bert.embeddings.LayerNorm.weight"), ws["ids32"].data_ptr(),
                ws["tt32"].data_ptr(), B, S, H, cfg.vocab_size, cfg.type_vocab_size,
@@ -705,5 +725,4 @@ class _Engine:
         if side is not main and hooks is None:
             for l in sorted(done)[:2]:       # the last two layers processed (0 and 1) may still be in flight
                 main.wait_event(done[l])
-        if hooks is not None:
-            hooks._bucket_ready(0)
+        bucket_ready(0)

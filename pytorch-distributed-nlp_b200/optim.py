@@ -53,6 +53,8 @@ class AdamW(torch.optim.Optimizer):
                              % (len(covered), len(lay.entries)))
         self._decay_flags_cpu = flags
         self._dev_state = None
+        self._armed = False      # set by FusedTrainStep: per-bucket updates may start during backward
+        self._pending = set()    # buckets already updated (on the engine's optimizer stream) in this step
         self._model._optimizer = self
 
     # -- device state (fp32 moments, step counter) ------------------------------------------------------------------
@@ -107,8 +109,19 @@ class AdamW(torch.optim.Optimizer):
         if model._ddp is not None and model._ddp.world > 1:
             model._ddp._optimizer_step(self)
         else:
-            s = eng.stream()
-            self.update_range(0, model._layout.total, 1, 0, [eng.grads.data_ptr()], [eng.shadow.data_ptr()], s)
+            main = torch.cuda.current_stream(eng.dev)
+            s = main.cuda_stream
+            if self._pending:
+                ev = torch.cuda.Event()
+                ev.record(eng.opt_stream)
+                main.wait_event(ev)
+            if len(self._pending) == 0:
+                self.update_range(0, model._layout.total, 1, 0, [eng.grads.data_ptr()], [eng.shadow.data_ptr()], s)
+            else:
+                for idx, (b0, e0, _lbl) in enumerate(model._layout.buckets):
+                    if idx not in self._pending:
+                        self.update_range(b0, e0, 1, 0, [eng.grads.data_ptr()], [eng.shadow.data_ptr()], s)
+            self._pending = set()
             self.advance(s)
         return loss
 

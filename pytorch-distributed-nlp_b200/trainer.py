@@ -65,6 +65,9 @@ class FusedTrainStep:
         self.loss_out = torch.zeros((), dtype=torch.float32, device=dev)
         self.h_loss = torch.zeros((), dtype=torch.float32).pin_memory()
         self.use_graph = use_graph
+        # the fused step owns backward + optimizer: per-bucket AdamW (and, under DDP, the peer exchange) may start
+        # while backward is still running
+        optimizer._armed = True
         self.graph = None
         self.kernel_launches = None
         self._warm = 0
