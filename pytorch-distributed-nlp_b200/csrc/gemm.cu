@@ -166,10 +166,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
       const int tile = w / p.splits, split = w % p.splits;
       const int m0 = (tile / p.tiles_n) * BM, n0 = (tile % p.tiles_n) * BN;
-      mbar_wait(&tmem_full[acc], acc_phase);
-      tc_fence_after();
       epilogue_tile<BN>(p, drop, tmem_base + acc * Cfg::kAccStride, warp, lane, m0, n0, split,
-                        epi_stage + (warp - 4) * kEpiStageBytes);
+                        epi_stage + (warp - 4) * kEpiStageBytes, &tmem_full[acc], acc_phase);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
@@ -387,11 +385,8 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       const int tile = w / p.splits, split = w % p.splits;
       const int m0 = (tile / p.tiles_n) * (2 * BM) + (int)rank * BM;
       const int n0 = (tile % p.tiles_n) * BN;
-      mbar_wait(&tmem_full[acc], acc_phase);
-      if (warp == 4 && lane == 0 && w + npairs >= num_work) stamp(p, 4);   // last accumulator complete
-      tc_fence_after();
       epilogue_tile<BN>(p, drop, tmem_base + acc * Cfg::kAccStride, warp, lane, m0, n0, split,
-                        epi_stage + (warp - 4) * kEpiStageBytes);
+                        epi_stage + (warp - 4) * kEpiStageBytes, &tmem_full[acc], acc_phase);
       tc_fence_before();
       __syncwarp();
       if (warp == 4 && lane == 0 && w + npairs >= num_work) stamp(p, 5);   // last epilogue done (warp 4)

@@ -58,6 +58,20 @@ __device__ __forceinline__ void tile_s2g(uint8_t* stage, uint8_t* g, long long p
     if (r < rows_valid) *reinterpret_cast<uint4*>(g + (size_t)r * pitch + c * 16) = v;
   }
 }
+// the same global->staging copy split in two so that the global loads can be issued long before their use:
+// tile_g2r puts the 8 chunks of this lane into registers, tile_r2s parks them in the staging tile
+__device__ __forceinline__ void tile_g2r(uint4 (&reg)[8], const uint8_t* g, long long pitch, int lane, int rows_valid) {
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int r = 4 * k + (lane >> 3), c = lane & 7;
+    reg[k] = make_uint4(0u, 0u, 0u, 0u);
+    if (r < rows_valid) reg[k] = __ldg(reinterpret_cast<const uint4*>(g + (size_t)r * pitch + c * 16));
+  }
+}
+__device__ __forceinline__ void tile_r2s(uint8_t* stage, const uint4 (&reg)[8], int lane) {
+#pragma unroll
+  for (int k = 0; k < 8; ++k) *stage_ptr(stage, 4 * k + (lane >> 3), lane & 7) = reg[k];
+}
 // this thread's own row (row == lane) of the staging tile: 8 chunks of 16 bytes
 __device__ __forceinline__ void row_write_bf16(uint8_t* stage, int lane, const float (&f)[64]) {
 #pragma unroll
@@ -80,7 +94,8 @@ __device__ __forceinline__ void row_read_bf16(uint8_t* stage, int lane, float (&
 // 8 epilogue warps drain one [128 rows x BN cols] accumulator: warp -> (TMEM lane quarter, column half)
 template <int BN>
 __device__ __forceinline__ void epilogue_tile(const GemmKernelParams& p, const DropCtx& drop, uint32_t tmem_acc,
-                                              int warp, int lane, int m_base, int n0, int split, uint8_t* stage) {
+                                              int warp, int lane, int m_base, int n0, int split, uint8_t* stage,
+                                              uint64_t* acc_bar, uint32_t acc_phase) {
   static_assert(BN == 128 || BN == 256, "epilogue works on 64-column groups per warp half");
   const int quarter = warp & 3;           // TMEM lane quarter this warp may touch
   const int colhalf = (warp - 4) >> 2;    // which half of the BN columns
@@ -95,6 +110,19 @@ __device__ __forceinline__ void epilogue_tile(const GemmKernelParams& p, const D
     const bool partial = p.epilogue == B2_EPI_PARTIAL_F32;
     float* dst_base = partial ? p.partial + (size_t)split * p.M * p.N : reinterpret_cast<float*>(p.D);
     const long long dst_ld = partial ? (long long)p.N : p.ldd;
+    // the auxiliary tile (fp32 residual) does not depend on the accumulator: fetch it before waiting for the MMAs,
+    // and the next group's while the current one is being combined and stored
+    uint4 pre[8];
+    auto prefetch = [&](int c) {
+      const int n = n0 + colhalf * kColsPerWarp + c * 32;
+      if (!partial && n < p.N && rows_valid > 0)
+        tile_g2r(pre, reinterpret_cast<const uint8_t*>(reinterpret_cast<const float*>(p.aux_in) +
+                                                        (size_t)row0 * p.ld_aux_in + n),
+                 p.ld_aux_in * 4, lane, rows_valid);
+    };
+    prefetch(0);
+    mbar_wait(acc_bar, acc_phase);
+    tc_fence_after();
 #pragma unroll 1
     for (int c = 0; c < kColsPerWarp / 32; ++c) {
       const int n = n0 + colhalf * kColsPerWarp + c * 32;
@@ -103,9 +131,9 @@ __device__ __forceinline__ void epilogue_tile(const GemmKernelParams& p, const D
       tmem_ld_wait();
       if (n < p.N && rows_valid > 0) {
         if (!partial) {
-          const float* aux = reinterpret_cast<const float*>(p.aux_in) + (size_t)row0 * p.ld_aux_in + n;
-          tile_g2s(stage, reinterpret_cast<const uint8_t*>(aux), p.ld_aux_in * 4, lane, rows_valid);
+          tile_r2s(stage, pre, lane);
           __syncwarp();
+          if (c + 1 < kColsPerWarp / 32) prefetch(c + 1);
 #pragma unroll
           for (int k = 0; k < 8; ++k) {
             const uint4 t = *stage_ptr(stage, lane, k);
@@ -128,6 +156,18 @@ __device__ __forceinline__ void epilogue_tile(const GemmKernelParams& p, const D
   }
 
   // ---- bf16 outputs: 64 columns (128 bytes) per group ----
+  const bool has_aux = p.epilogue == B2_EPI_BIAS_DROPOUT_RESIDUAL || p.epilogue == B2_EPI_RESIDUAL ||
+                       p.epilogue == B2_EPI_GELU_BWD;
+  uint4 pre[8];
+  auto prefetch = [&](int g) {
+    const int n = n0 + colhalf * kColsPerWarp + g * 64;
+    if (has_aux && n < p.N && rows_valid > 0)
+      tile_g2r(pre, reinterpret_cast<const uint8_t*>(p.aux_in + (size_t)row0 * p.ld_aux_in + n), p.ld_aux_in * 2, lane,
+               rows_valid);
+  };
+  prefetch(0);   // residual / saved pre-activation tile: independent of the accumulator, fetched under the mainloop
+  mbar_wait(acc_bar, acc_phase);
+  tc_fence_after();
 #pragma unroll 1
   for (int g = 0; g < kColsPerWarp / 64; ++g) {
     const int n = n0 + colhalf * kColsPerWarp + g * 64;
@@ -161,11 +201,10 @@ __device__ __forceinline__ void epilogue_tile(const GemmKernelParams& p, const D
         __syncwarp();
 #pragma unroll
         for (int j = 0; j < 64; ++j) f[j] = gelu_erf(bf16_round(f[j]));
-      } else if (p.epilogue == B2_EPI_BIAS_DROPOUT_RESIDUAL || p.epilogue == B2_EPI_RESIDUAL ||
-                 p.epilogue == B2_EPI_GELU_BWD) {
-        tile_g2s(stage, reinterpret_cast<const uint8_t*>(p.aux_in + (size_t)row0 * p.ld_aux_in + n), p.ld_aux_in * 2,
-                 lane, rows_valid);
+      } else if (has_aux) {
+        tile_r2s(stage, pre, lane);
         __syncwarp();
+        if (g + 1 < kColsPerWarp / 64) prefetch(g + 1);
         float r[64];
         row_read_bf16(stage, lane, r);
         __syncwarp();
