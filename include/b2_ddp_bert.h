@@ -28,7 +28,7 @@ extern "C" {
 /* ------------------------------------------------------------------------------------------------------ */
 const char* b2_last_error(void);
 int32_t b2_abi_version(void);             /* bumped when a struct below changes */
-#define B2_ABI_VERSION 5
+#define B2_ABI_VERSION 6
 int64_t b2_launch_count(void);            /* kernels launched by this library so far (process-wide) */
 
 /* ------------------------------------------------------------------------------------------------------ */
@@ -118,8 +118,18 @@ int32_t b2_layernorm_fwd(const void* x, const void* gamma, const void* beta, int
 int32_t b2_layernorm_bwd(const void* dy, const void* dy_add, const void* x, const float* mean, const float* rstd,
                          const void* gamma, int64_t rows, int64_t hidden, float dropout_p, const void* rng_state,
                          uint32_t rng_site, int32_t grad_fp32 /* 1: dy, dy_add, dx are fp32 (dx_drop stays bf16 and
-                         is then always written: it is what the GEMMs consume) */, void* dx, void* dx_drop, void* d_gamma, void* d_beta, void* d_bias,
-                         float* scratch_partials, int64_t scratch_partials_bytes, void* stream);
+                         is then always written: it is what the GEMMs consume) */,
+                         void* dx, void* dx_drop, void* d_gamma, void* d_beta, void* d_bias,
+                         float* scratch_partials, int64_t scratch_partials_bytes,
+                         int32_t* deferred_nparts /* host pointer or NULL.  NULL: d_gamma/d_beta/d_bias are final in
+                         stream order.  Else only the per-block partials are written, *deferred_nparts receives their
+                         count and the caller finishes with b2_colsum_finish (takes the reduction off the critical
+                         path, e.g. onto another stream) */,
+                         void* stream);
+
+/* partials [nparts][nsets][cols] fp32 -> up to three bf16 [cols] outputs (the second half of b2_layernorm_bwd) */
+int32_t b2_colsum_finish(const float* partials, int32_t nparts, int32_t nsets, int64_t cols, void* out0, void* out1,
+                         void* out2, void* stream);
 
 /* column sums of a bf16 [rows, cols] matrix -> bf16 [cols]   (bias gradients of QKV / intermediate dense)  */
 int32_t b2_colsum(const void* x, int64_t rows, int64_t cols, int64_t ldx, void* out, float* scratch_partials,

@@ -223,7 +223,8 @@ int32_t launch_colsum(const void* x, int64_t rows, int64_t cols, int64_t ldx, co
 int32_t launch_layernorm_bwd(const void* dy, const void* dy_add, const void* x, const float* mean, const float* rstd,
                              const void* gamma, int64_t rows, int64_t hidden, float dropout_p, const void* rng,
                              uint32_t site, int mode, int dy_f32, int dx_f32, void* dx, void* dx_drop, void* d_gamma,
-                             void* d_beta, void* d_bias, float* scratch, int64_t scratch_bytes, cudaStream_t stream) {
+                             void* d_beta, void* d_bias, float* scratch, int64_t scratch_bytes, cudaStream_t stream,
+                             int32_t* deferred_nparts) {
   B2_REQUIRE(hidden % 256 == 0 && hidden >= 256 && hidden <= 1024, "layernorm: hidden=%lld unsupported",
              (long long)hidden);
   int nblocks = (int)(scratch_bytes / (3 * hidden * 4));
@@ -249,6 +250,10 @@ int32_t launch_layernorm_bwd(const void* dy, const void* dy_add, const void* x, 
 #undef B2_LN_ARGS
   B2_CUDA(cudaGetLastError());
   count_launches(1);
+  if (deferred_nparts != nullptr) {   // the caller runs b2_colsum_finish itself (e.g. on another stream)
+    *deferred_nparts = nblocks;
+    return 0;
+  }
   B2_LAUNCH(colsum_finish_kernel, (unsigned)((3 * hidden + 31) / 32), 256, 0, stream, 
       scratch, nblocks, 3, (int)hidden, (__nv_bfloat16*)d_gamma, (__nv_bfloat16*)d_beta, (__nv_bfloat16*)d_bias);
   B2_CUDA(cudaGetLastError());
@@ -287,7 +292,8 @@ extern "C" int32_t b2_layernorm_bwd(const void* dy, const void* dy_add, const vo
                                     const float* rstd, const void* gamma, int64_t rows, int64_t hidden,
                                     float dropout_p, const void* rng_state, uint32_t rng_site, int32_t grad_fp32,
                                     void* dx, void* dx_drop, void* d_gamma, void* d_beta, void* d_bias,
-                                    float* scratch_partials, int64_t scratch_partials_bytes, void* stream_) {
+                                    float* scratch_partials, int64_t scratch_partials_bytes, int32_t* deferred_nparts,
+                                    void* stream_) {
   B2_REQUIRE(dy && x && mean && rstd && gamma && dx && d_gamma && d_beta && scratch_partials,
              "layernorm_bwd: null pointer");
   B2_REQUIRE(rows > 0, "layernorm_bwd: rows=%lld", (long long)rows);
@@ -296,7 +302,17 @@ extern "C" int32_t b2_layernorm_bwd(const void* dy, const void* dy_add, const vo
   return launch_layernorm_bwd(dy, dy_add, x, mean, rstd, gamma, rows, hidden, dropout_p, rng_state, rng_site, 0,
                               grad_fp32 ? 1 : 0, grad_fp32 ? 1 : 0, dx,
                               (dropout_p > 0.f || grad_fp32) ? dx_drop : nullptr, d_gamma, d_beta, d_bias,
-                              scratch_partials, scratch_partials_bytes, (cudaStream_t)stream_);
+                              scratch_partials, scratch_partials_bytes, (cudaStream_t)stream_, deferred_nparts);
+}
+
+extern "C" int32_t b2_colsum_finish(const float* partials, int32_t nparts, int32_t nsets, int64_t cols, void* out0,
+                                    void* out1, void* out2, void* stream_) {
+  B2_REQUIRE(partials && nparts > 0 && nsets >= 1 && nsets <= 3 && cols > 0, "colsum_finish: bad args");
+  B2_LAUNCH(colsum_finish_kernel, (unsigned)((nsets * cols + 31) / 32), 256, 0, stream_, partials, (int)nparts,
+            (int)nsets, (int)cols, (__nv_bfloat16*)out0, (__nv_bfloat16*)out1, (__nv_bfloat16*)out2);
+  B2_CUDA(cudaGetLastError());
+  count_launches(1);
+  return 0;
 }
 
 extern "C" int32_t b2_colsum(const void* x, int64_t rows, int64_t cols, int64_t ldx, void* out,

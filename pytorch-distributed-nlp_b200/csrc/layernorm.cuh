@@ -89,6 +89,7 @@ int32_t launch_colsum(const void* x, int64_t rows, int64_t cols, int64_t ldx, co
 int32_t launch_layernorm_bwd(const void* dy, const void* dy_add, const void* x, const float* mean, const float* rstd,
                              const void* gamma, int64_t rows, int64_t hidden, float dropout_p, const void* rng,
                              uint32_t site, int mode, int dy_f32, int dx_f32, void* dx, void* dx_drop, void* d_gamma,
-                             void* d_beta, void* d_bias, float* scratch, int64_t scratch_bytes, cudaStream_t stream);
+                             void* d_beta, void* d_bias, float* scratch, int64_t scratch_bytes, cudaStream_t stream,
+                             int32_t* deferred_nparts = nullptr);
 
 }  // namespace b2

@@ -11,6 +11,7 @@ The arithmetic follows HF ``BertForSequenceClassification`` (SP/transformers/mod
 1077-1154, eager attention) in bf16 with fp32 accumulation/statistics; fp32 master weights stay the parameters
 the user sees.  There is no PyTorch fallback: without the CUDA library every call raises.
 """
+import ctypes
 import math
 import os
 from collections import OrderedDict
@@ -399,6 +400,9 @@ class _Engine:
         self.owner = torch.empty(cfg.vocab_size, dtype=torch.int32, device=self.dev)
         self.split_ws = torch.empty(64 << 20, dtype=torch.uint8, device=self.dev)
         self.partials = torch.empty(8 << 20, dtype=torch.uint8, device=self.dev)
+        # LayerNorm-backward partial sums: one buffer per (LN site, layer parity) so that the reduction to
+        # d_gamma / d_beta / d_bias can run later, on the weight-gradient stream
+        self.ln_partials = [torch.empty(4 << 20, dtype=torch.uint8, device=self.dev) for _ in range(4)]
         self._ws = {}
         self._saved = None
         self.wgrad_stream = torch.cuda.Stream(device=self.dev)
@@ -665,11 +669,16 @@ class _Engine:
             if side is not main and (l + 2) in done:
                 main.wait_event(done[l + 2])
             # --- BertOutput: LN2 backward (+ dropout mask, bias grad), FFN2 wgrad/dgrad(+GELU')
+            np2 = ctypes.c_int32(0)
+            lp2 = self.ln_partials[2 * st]
             L.call("b2_layernorm_bwd", dx.data_ptr(), None, a["z2"].data_ptr(), a["mean2"].data_ptr(),
                    a["rstd2"].data_ptr(), w(pre + "output.LayerNorm.weight"), M, H, p_h, rng, 3 + 3 * l, 1,
                    ws["dz"].data_ptr(), dzd.data_ptr(), g(pre + "output.LayerNorm.weight"),
-                   g(pre + "output.LayerNorm.bias"), g(pre + "output.dense.bias"), scratch, scratch_bytes, s)
+                   g(pre + "output.LayerNorm.bias"), g(pre + "output.dense.bias"), lp2.data_ptr(), lp2.numel(),
+                   ctypes.byref(np2), s)
             fork()
+            L.call("b2_colsum_finish", lp2.data_ptr(), np2.value, 3, H, g(pre + "output.LayerNorm.weight"),
+                   g(pre + "output.LayerNorm.bias"), g(pre + "output.dense.bias"), ss)
             self.gemm(H, I, M, dzd.data_ptr(), H, MN, a["h"].data_ptr(), I, MN, g(pre + "output.dense.weight"), I,
                       split=True, stream=ss)
             acc_l = self.bias_acc.data_ptr() + 4 * l * (3 * H + I)
@@ -683,12 +692,16 @@ class _Engine:
             self.gemm(M, H, I, dU.data_ptr(), I, KM, w(pre + "intermediate.dense.weight"), H, MN,
                       dx_other.data_ptr(), H, L.EPI_RESIDUAL_F32, aux_in=ws["dz"].data_ptr(), ld_aux_in=H)
             # --- BertSelfOutput
+            np1 = ctypes.c_int32(0)
+            lp1 = self.ln_partials[2 * st + 1]
             L.call("b2_layernorm_bwd", dx_other.data_ptr(), None, a["z1"].data_ptr(), a["mean1"].data_ptr(),
                    a["rstd1"].data_ptr(), w(pre + "attention.output.LayerNorm.weight"), M, H, p_h, rng, 2 + 3 * l, 1,
                    ws["dz1"].data_ptr(), dz1d.data_ptr(), g(pre + "attention.output.LayerNorm.weight"),
-                   g(pre + "attention.output.LayerNorm.bias"), g(pre + "attention.output.dense.bias"), scratch,
-                   scratch_bytes, s)
+                   g(pre + "attention.output.LayerNorm.bias"), g(pre + "attention.output.dense.bias"),
+                   lp1.data_ptr(), lp1.numel(), ctypes.byref(np1), s)
             fork()
+            L.call("b2_colsum_finish", lp1.data_ptr(), np1.value, 3, H, g(pre + "attention.output.LayerNorm.weight"),
+                   g(pre + "attention.output.LayerNorm.bias"), g(pre + "attention.output.dense.bias"), ss)
             self.gemm(H, H, M, dz1d.data_ptr(), H, MN, a["ctx"].data_ptr(), H, MN,
                       g(pre + "attention.output.dense.weight"), H, split=True, stream=ss)
             self.gemm(M, H, H, dz1d.data_ptr(), H, KM, w(pre + "attention.output.dense.weight"), H, MN,

@@ -50,13 +50,26 @@ def test_layernorm_fwd_bwd(cuda_dev, H):
         rs = rng_state(dev)
         L.call("b2_layernorm_bwd", dy.data_ptr(), None, x.data_ptr(), mean.data_ptr(), rstd.data_ptr(), g.data_ptr(),
                rows, H, p, rs.data_ptr(), 11, 0, dx.data_ptr(), dxd.data_ptr(), dg.data_ptr(), db.data_ptr(),
-               dbias.data_ptr(), scratch.data_ptr(), scratch.numel(), S())
+               dbias.data_ptr(), scratch.data_ptr(), scratch.numel(), None, S())
         # fp32 gradient stream variant: fp32 dy in, fp32 dx out, bf16 dx_drop always written
         dy32, dx32, dxd32 = dy.float(), torch.empty(rows, H, device=dev), torch.empty_like(x)
         dg2, db2, dbias2 = (torch.empty(H, dtype=bf, device=dev) for _ in range(3))
         L.call("b2_layernorm_bwd", dy32.data_ptr(), None, x.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
                g.data_ptr(), rows, H, p, rs.data_ptr(), 11, 1, dx32.data_ptr(), dxd32.data_ptr(), dg2.data_ptr(),
-               db2.data_ptr(), dbias2.data_ptr(), scratch.data_ptr(), scratch.numel(), S())
+               db2.data_ptr(), dbias2.data_ptr(), scratch.data_ptr(), scratch.numel(), None, S())
+        # deferred finish: partials only, then the reduction as a separate call
+        import ctypes
+        npart = ctypes.c_int32(0)
+        dg3, db3, dbias3 = (torch.zeros(H, dtype=bf, device=dev) for _ in range(3))
+        scratch3 = torch.empty(4 << 20, dtype=torch.uint8, device=dev)
+        L.call("b2_layernorm_bwd", dy32.data_ptr(), None, x.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+               g.data_ptr(), rows, H, p, rs.data_ptr(), 11, 1, dx32.data_ptr(), dxd32.data_ptr(), dg3.data_ptr(),
+               db3.data_ptr(), dbias3.data_ptr(), scratch3.data_ptr(), scratch3.numel(), ctypes.byref(npart), S())
+        assert npart.value > 0 and float(dg3.float().abs().max()) == 0.0
+        L.call("b2_colsum_finish", scratch3.data_ptr(), npart.value, 3, H, dg3.data_ptr(), db3.data_ptr(),
+               dbias3.data_ptr(), S())
+        torch.cuda.synchronize()
+        assert torch.equal(dg3, dg2) and torch.equal(db3, db2) and torch.equal(dbias3, dbias2)
         torch.cuda.synchronize()
         assert rel_l2(dx32, dx.float()) < 5e-3 and rel_l2(dg2.float(), dg.float()) < 1e-2
         if p > 0:
