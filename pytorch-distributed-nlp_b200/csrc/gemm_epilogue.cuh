@@ -58,20 +58,23 @@ __device__ __forceinline__ void tile_s2g(uint8_t* stage, uint8_t* g, long long p
     if (r < rows_valid) *reinterpret_cast<uint4*>(g + (size_t)r * pitch + c * 16) = v;
   }
 }
-// the same global->staging copy split in two so that the global loads can be issued long before their use:
-// tile_g2r puts the 8 chunks of this lane into registers, tile_r2s parks them in the staging tile
-__device__ __forceinline__ void tile_g2r(uint4 (&reg)[8], const uint8_t* g, long long pitch, int lane, int rows_valid) {
+// asynchronous variant (cp.async, no registers held): issue early, tile_async_wait() + __syncwarp() before reading
+__device__ __forceinline__ void tile_g2s_async(uint8_t* stage, const uint8_t* g, long long pitch, int lane,
+                                               int rows_valid) {
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
     const int r = 4 * k + (lane >> 3), c = lane & 7;
-    reg[k] = make_uint4(0u, 0u, 0u, 0u);
-    if (r < rows_valid) reg[k] = __ldg(reinterpret_cast<const uint4*>(g + (size_t)r * pitch + c * 16));
+    uint4* dst = stage_ptr(stage, r, c);
+    if (r < rows_valid) {
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(g + (size_t)r * pitch + c * 16)
+                   : "memory");
+    } else {
+      *dst = make_uint4(0u, 0u, 0u, 0u);
+    }
   }
+  asm volatile("cp.async.commit_group;" ::: "memory");
 }
-__device__ __forceinline__ void tile_r2s(uint8_t* stage, const uint4 (&reg)[8], int lane) {
-#pragma unroll
-  for (int k = 0; k < 8; ++k) *stage_ptr(stage, 4 * k + (lane >> 3), lane & 7) = reg[k];
-}
+__device__ __forceinline__ void tile_async_wait() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 // this thread's own row (row == lane) of the staging tile: 8 chunks of 16 bytes
 __device__ __forceinline__ void row_write_bf16(uint8_t* stage, int lane, const float (&f)[64]) {
 #pragma unroll
@@ -112,13 +115,12 @@ __device__ __forceinline__ void epilogue_tile(const GemmKernelParams& p, const D
     const long long dst_ld = partial ? (long long)p.N : p.ldd;
     // the auxiliary tile (fp32 residual) does not depend on the accumulator: fetch it before waiting for the MMAs,
     // and the next group's while the current one is being combined and stored
-    uint4 pre[8];
     auto prefetch = [&](int c) {
       const int n = n0 + colhalf * kColsPerWarp + c * 32;
       if (!partial && n < p.N && rows_valid > 0)
-        tile_g2r(pre, reinterpret_cast<const uint8_t*>(reinterpret_cast<const float*>(p.aux_in) +
-                                                        (size_t)row0 * p.ld_aux_in + n),
-                 p.ld_aux_in * 4, lane, rows_valid);
+        tile_g2s_async(stage, reinterpret_cast<const uint8_t*>(reinterpret_cast<const float*>(p.aux_in) +
+                                                              (size_t)row0 * p.ld_aux_in + n),
+                       p.ld_aux_in * 4, lane, rows_valid);
     };
     prefetch(0);
     mbar_wait(acc_bar, acc_phase);
@@ -131,9 +133,9 @@ __device__ __forceinline__ void epilogue_tile(const GemmKernelParams& p, const D
       tmem_ld_wait();
       if (n < p.N && rows_valid > 0) {
         if (!partial) {
-          tile_r2s(stage, pre, lane);
+          if (c > 0) prefetch(c);   // group 0 was requested before the accumulator wait
+          tile_async_wait();
           __syncwarp();
-          if (c + 1 < kColsPerWarp / 32) prefetch(c + 1);
 #pragma unroll
           for (int k = 0; k < 8; ++k) {
             const uint4 t = *stage_ptr(stage, lane, k);
@@ -158,12 +160,11 @@ __device__ __forceinline__ void epilogue_tile(const GemmKernelParams& p, const D
   // ---- bf16 outputs: 64 columns (128 bytes) per group ----
   const bool has_aux = p.epilogue == B2_EPI_BIAS_DROPOUT_RESIDUAL || p.epilogue == B2_EPI_RESIDUAL ||
                        p.epilogue == B2_EPI_GELU_BWD;
-  uint4 pre[8];
   auto prefetch = [&](int g) {
     const int n = n0 + colhalf * kColsPerWarp + g * 64;
     if (has_aux && n < p.N && rows_valid > 0)
-      tile_g2r(pre, reinterpret_cast<const uint8_t*>(p.aux_in + (size_t)row0 * p.ld_aux_in + n), p.ld_aux_in * 2, lane,
-               rows_valid);
+      tile_g2s_async(stage, reinterpret_cast<const uint8_t*>(p.aux_in + (size_t)row0 * p.ld_aux_in + n),
+                     p.ld_aux_in * 2, lane, rows_valid);
   };
   prefetch(0);   // residual / saved pre-activation tile: independent of the accumulator, fetched under the mainloop
   mbar_wait(acc_bar, acc_phase);
@@ -202,9 +203,9 @@ __device__ __forceinline__ void epilogue_tile(const GemmKernelParams& p, const D
 #pragma unroll
         for (int j = 0; j < 64; ++j) f[j] = gelu_erf(bf16_round(f[j]));
       } else if (has_aux) {
-        tile_r2s(stage, pre, lane);
+        if (g > 0) prefetch(g);   // group 0 was requested before the accumulator wait
+        tile_async_wait();
         __syncwarp();
-        if (g + 1 < kColsPerWarp / 64) prefetch(g + 1);
         float r[64];
         row_read_bf16(stage, lane, r);
         __syncwarp();
