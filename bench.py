@@ -147,9 +147,9 @@ def time_gemm_family(eng, cfg, B, S, peaks):
         ("fwd ffn1     [M,I]<-[M,H]x[I,H]^T", M, I, H, KM, KM, L.EPI_BIAS_GELU),
         ("fwd ffn2     [M,H]<-[M,I]x[H,I]^T", M, H, I, KM, KM, L.EPI_BIAS_DROPOUT_RESIDUAL),
         ("dgrad ffn2   [M,I]<-[M,H]x[H,I]", M, I, H, KM, MN, L.EPI_GELU_BWD),
-        ("dgrad ffn1   [M,H]<-[M,I]x[I,H]", M, H, I, KM, MN, L.EPI_RESIDUAL),
+        ("dgrad ffn1   [M,H]<-[M,I]x[I,H] +fp32 res", M, H, I, KM, MN, L.EPI_RESIDUAL_F32),
         ("dgrad attn-o [M,H]<-[M,H]x[H,H]", M, H, H, KM, MN, L.EPI_NONE),
-        ("dgrad qkv    [M,H]<-[M,3H]x[3H,H]", M, H, 3 * H, KM, MN, L.EPI_RESIDUAL),
+        ("dgrad qkv    [M,H]<-[M,3H]x[3H,H] +fp32 res", M, H, 3 * H, KM, MN, L.EPI_RESIDUAL_F32),
         ("wgrad ffn2   [H,I]<-[M,H]^Tx[M,I]", H, I, M, MN, MN, L.EPI_NONE),
         ("wgrad ffn1   [I,H]<-[M,I]^Tx[M,H]", I, H, M, MN, MN, L.EPI_NONE),
         ("wgrad attn-o [H,H]<-[M,H]^Tx[M,H]", H, H, M, MN, MN, L.EPI_NONE),
@@ -163,14 +163,16 @@ def time_gemm_family(eng, cfg, B, S, peaks):
         sets = []
         for _ in range(NSET):
             sets.append(dict(A=torch.randn(a_shape, device=dev).to(bf), B=(torch.randn(b_shape, device=dev) * 0.05).to(bf),
-                             D=torch.empty(m, n, dtype=bf, device=dev), X=torch.randn(m, n, device=dev).to(bf),
+                             D=torch.empty(m, n, dtype=(torch.float32 if epi == L.EPI_RESIDUAL_F32 else bf), device=dev),
+                             X=(torch.randn(m, n, device=dev) if epi == L.EPI_RESIDUAL_F32
+                                else torch.randn(m, n, device=dev).to(bf)),
                              U=torch.empty(m, n, dtype=bf, device=dev), bias=torch.randn(n, device=dev).to(bf)))
 
         def launch(s):
             kw = {}
             if epi in (L.EPI_BIAS, L.EPI_BIAS_GELU, L.EPI_BIAS_DROPOUT_RESIDUAL):
                 kw["bias"] = s["bias"].data_ptr()
-            if epi in (L.EPI_BIAS_DROPOUT_RESIDUAL, L.EPI_RESIDUAL, L.EPI_GELU_BWD):
+            if epi in (L.EPI_BIAS_DROPOUT_RESIDUAL, L.EPI_RESIDUAL, L.EPI_GELU_BWD, L.EPI_RESIDUAL_F32):
                 kw["aux_in"], kw["ld_aux_in"] = s["X"].data_ptr(), n
             if epi == L.EPI_BIAS_GELU:
                 kw["aux_out"], kw["ld_aux_out"] = s["U"].data_ptr(), n
@@ -206,8 +208,15 @@ def time_gemm_family(eng, cfg, B, S, peaks):
         del sets
     achieved = tot_flops / tot_ms / 1e9
     peak = peaks["bf16_tflops"]
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "gemm_ncu_traffic.json")   # dram bytes per launch from `ncu --set full`
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp))
+        except Exception:
+            traffic = None
     return {"bound": "tensor", "achieved": round(achieved, 1), "peak": peak, "unit": "TFLOP/s",
-            "frac": round(achieved / peak, 4), "traffic": None,
+            "frac": round(achieved / peak, 4), "traffic": traffic,
             "kernel": "gemm_bf16_kernel (tcgen05/TMA), 12 GEMM shapes of one encoder-layer step, flop-weighted",
             "peak_source": peaks["source"] + ", burst cuBLAS bf16 (kernels timed in isolation)",
             "detail": detail}
@@ -272,10 +281,23 @@ def run_b200(args):
     t_e2e0 = time.time()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
+    # Every step: pinned H2D of that step's batch (inside train_step), the step, and a D2H read of a step's loss.  The
+    # read is software-pipelined by one step: the loss of step i is copied to pinned memory right behind step i and
+    # consumed by the host while step i+1 is already queued, so the host never drains the GPU (the reference's
+    # per-step print of the *current* loss [:178-181] forces exactly that drain).  The last loss is read after the loop,
+    # inside the timed region.
+    h_loss = [torch.zeros((), dtype=torch.float32).pin_memory() for _ in range(2)]
+    evs = [torch.cuda.Event(), torch.cuda.Event()]
     last = None
     for i in range(args.steps):
         loss = trainer.train_step(ring[i % len(ring)])
-        last = fused.loss_to_host()              # D2H read of the step's loss (4 bytes), synchronises the step
+        h_loss[i & 1].copy_(loss.reshape(()), non_blocking=True)
+        evs[i & 1].record()
+        if i > 0:
+            evs[(i - 1) & 1].synchronize()
+            last = float(h_loss[(i - 1) & 1])
+    evs[(args.steps - 1) & 1].synchronize()
+    last = float(h_loss[(args.steps - 1) & 1])
     ev1.record()
     barrier()
     e2e_ms = ev0.elapsed_time(ev1)
@@ -335,7 +357,9 @@ def run_b200(args):
                              "activations) exceeds the 126 MB L2; no explicit flush",
                        "cuda_graph": True},
             "e2e": {"value": round(e2e, 1), "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
-                    "ms_per_step": round(e2e_ms / args.steps, 4)},
+                    "ms_per_step": round(e2e_ms / args.steps, 4),
+                    "api": "Trainer.train_step(host batch dict) -> rank-mean loss; loss read back every step, "
+                           "pipelined one step behind"},
             "gpu_launches": int(launches_per_step * args.steps),
             "gpu_launches_per_step": int(launches_per_step),
             "clocks": clocks,
