@@ -210,13 +210,15 @@ def time_gemm_family(eng, cfg, B, S, peaks):
     peak = peaks["bf16_tflops"]
     traffic = None
     tp = os.path.join(ROOT, "profiles", "gemm_ncu_traffic.json")   # dram bytes per launch from `ncu --set full`
+    traffic_detail = None
     if os.path.exists(tp):
         try:
-            traffic = json.load(open(tp))
+            t = json.load(open(tp))
+            traffic, traffic_detail = t["bytes_per_launch_mean"], {"source": t["source"], "detail": t["detail"]}
         except Exception:
             traffic = None
     return {"bound": "tensor", "achieved": round(achieved, 1), "peak": peak, "unit": "TFLOP/s",
-            "frac": round(achieved / peak, 4), "traffic": traffic,
+            "frac": round(achieved / peak, 4), "traffic": traffic, "traffic_detail": traffic_detail,
             "kernel": "gemm_bf16_kernel (tcgen05/TMA), 12 GEMM shapes of one encoder-layer step, flop-weighted",
             "peak_source": peaks["source"] + ", burst cuBLAS bf16 (kernels timed in isolation)",
             "detail": detail}

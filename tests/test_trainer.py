@@ -40,7 +40,7 @@ def test_trainer_train_dev_test(cuda_dev, tmp_path, capsys, fused):
     args.ckpt_path = str(tmp_path / "ckpt.pt")
     args.fused = fused
     args.dev, args.eval_step = True, 3
-    loader, dev_loader = _Loader(cfg, 6, 4, 100), _Loader(cfg, 2, 4, 900)
+    loader, dev_loader = _Loader(cfg, 6, 4, 100), _Loader(cfg, 12, 4, 900)
     args.total_step = len(loader)
     opt = b2.build_optimizer(model, args)
     tr = b2.Trainer(args, cfg, model, torch.nn.CrossEntropyLoss(), opt)
@@ -62,6 +62,8 @@ def test_trainer_train_dev_test(cuda_dev, tmp_path, capsys, fused):
     ref_state = {k: v.cpu() for k, v in model.state_dict().items() if k in state}
     _, rz = bert_ref.forward(ref_state, cfg, b["input_ids"], b["token_type_ids"], b["attention_mask"], b["label"])
     assert float((logits.cpu() - rz).abs().max()) <= 1e-2
+    # like the reference, Trainer.test hands sklearn the 6 label names: every class must occur in y_true U y_pred
+    assert len({int(v) for b_ in dev_loader.batches for v in b_["label"]}) == 6
     report = tr.test(model, dev_loader, ["c%d" % i for i in range(6)])
     assert "precision" in report
     # reload the checkpoint into a fresh model (test.py:96-101 style) and into the optimizer-free eval path
