@@ -43,18 +43,16 @@ def _unwrap(model):
     return model.module if isinstance(model, DistributedDataParallel) else model
 
 
-class FusedTrainStep:
-    """One training step == one CUDA-graph replay: H2D of the batch, embeddings -> 12 layers -> head -> CE, the full
-    backward, the peer-HBM gradient exchange fused with AdamW, and the device-side step/RNG bump.  Semantically the body
-    of the reference loop [:166-176] without the host round trips."""
+class _StagedGraphStep:
+    """Shared plumbing of the graph-captured steps: one pinned staging buffer for the four host tensors of a batch, one
+    async H2D copy, two eager warm-up passes (first launches set kernel attributes), then capture + replay."""
 
-    def __init__(self, model, optimizer, batch_size, seq_len, use_graph=True):
+    def __init__(self, model, batch_size, seq_len, use_graph=True):
         self.wrapper = model if isinstance(model, DistributedDataParallel) else None
         self.model = _unwrap(model)
-        self.opt = optimizer
         self.eng = self.model._engine
         if self.eng is None:
-            raise RuntimeError("FusedTrainStep: model must be on CUDA")
+            raise RuntimeError("%s: model must be on CUDA" % type(self).__name__)
         dev = self.eng.dev
         self.B, self.S = batch_size, seq_len
         z = lambda *s: torch.zeros(*s, dtype=torch.int64, device=dev)
@@ -65,40 +63,29 @@ class FusedTrainStep:
         self.loss_out = torch.zeros((), dtype=torch.float32, device=dev)
         self.h_loss = torch.zeros((), dtype=torch.float32).pin_memory()
         self.use_graph = use_graph
-        # the fused step owns backward + optimizer: per-bucket AdamW (and, under DDP, the peer exchange) may start
-        # while backward is still running
-        optimizer._armed = True
         self.graph = None
-        self.kernel_launches = None
         self._warm = 0
         self._h2d_done = None
 
-    # the step body, expressed only with stream-ordered work (capturable)
-    def _body(self):
-        eng, m = self.eng, self.model
+    def _unstage(self):
         n = self.B * self.S
         st = self.d_stage
         self.d_ids.copy_(st[0:n].view(self.B, self.S))
         self.d_tt.copy_(st[n:2 * n].view(self.B, self.S))
         self.d_mask.copy_(st[2 * n:3 * n].view(self.B, self.S))
         self.d_lab.copy_(st[3 * n:3 * n + self.B])
-        logits, loss = eng.forward(self.d_ids, self.d_tt, self.d_mask, self.d_lab, training=True, need_backward=True)
-        ws = eng.workspace(self.B, self.S)
-        B, S, mask, p_h, p_a, p_c = eng._saved
-        eng._saved = None
-        # d(loss)/d(logits) was produced by the CE kernel: the reference's criterion(logits, label) [:169]
-        eng._backward_from_dlogits(ws["dloss_logits"], B, S, mask, p_h, p_a, p_c)
-        self.opt.step()
-        self.loss_out.copy_(loss)
 
-    def __call__(self, batch_data):
-        """batch_data: the dict the reference Collate yields (host int64 tensors).  Returns the device loss scalar
-        (local rank's mean CE, like `loss` at [:169])."""
+    def _body(self):
+        raise NotImplementedError
+
+    def stage(self, batch_data):
+        """Host batch (the dict the reference Collate yields, int64 tensors) -> pinned staging -> async H2D."""
         n = self.B * self.S
         ids, tt, mask, lab = batch_data["input_ids"], batch_data["token_type_ids"], batch_data["attention_mask"], \
             batch_data["label"]
         if tuple(ids.shape) != (self.B, self.S):
-            raise ValueError("FusedTrainStep was built for batch %dx%d, got %s" % (self.B, self.S, tuple(ids.shape)))
+            raise ValueError("%s was built for batch %dx%d, got %s"
+                             % (type(self).__name__, self.B, self.S, tuple(ids.shape)))
         hs = self.h_stage
         if self._h2d_done is not None:
             self._h2d_done.synchronize()  # previous step's copy out of the pinned staging buffer has drained
@@ -109,8 +96,6 @@ class FusedTrainStep:
         self.d_stage.copy_(hs, non_blocking=True)
         self._h2d_done = torch.cuda.Event()
         self._h2d_done.record(torch.cuda.current_stream(self.eng.dev))
-        self.run_device()
-        return self.loss_out
 
     def run_device(self):
         """The step with inputs already staged on the device (bench `value` path)."""
@@ -138,6 +123,62 @@ class FusedTrainStep:
         return float(self.h_loss)
 
 
+class FusedTrainStep(_StagedGraphStep):
+    """One training step == one CUDA-graph replay: H2D of the batch, embeddings -> 12 layers -> head -> CE, the full
+    backward, the peer-HBM gradient exchange fused with AdamW, and the device-side step/RNG bump.  Semantically the body
+    of the reference loop [:166-176] without the host round trips."""
+
+    def __init__(self, model, optimizer, batch_size, seq_len, use_graph=True):
+        super().__init__(model, batch_size, seq_len, use_graph)
+        self.opt = optimizer
+        # the fused step owns backward + optimizer: per-bucket AdamW (and, under DDP, the peer exchange) may start
+        # while backward is still running
+        optimizer._armed = True
+        self.kernel_launches = None
+
+    # the step body, expressed only with stream-ordered work (capturable)
+    def _body(self):
+        eng = self.eng
+        self._unstage()
+        logits, loss = eng.forward(self.d_ids, self.d_tt, self.d_mask, self.d_lab, training=True, need_backward=True)
+        ws = eng.workspace(self.B, self.S)
+        B, S, mask, p_h, p_a, p_c = eng._saved
+        eng._saved = None
+        # d(loss)/d(logits) was produced by the CE kernel: the reference's criterion(logits, label) [:169]
+        eng._backward_from_dlogits(ws["dloss_logits"], B, S, mask, p_h, p_a, p_c)
+        self.opt.step()
+        self.loss_out.copy_(loss)
+
+    def __call__(self, batch_data):
+        """batch_data: the dict the reference Collate yields (host int64 tensors).  Returns the device loss scalar
+        (local rank's mean CE, like `loss` at [:169])."""
+        self.stage(batch_data)
+        self.run_device()
+        return self.loss_out
+
+
+class FusedEvalStep(_StagedGraphStep):
+    """The reference's eval body (`on_step` + `criterion` under `no_grad`, [:204-208] / [:228-229]) as one CUDA-graph
+    replay: H2D of the batch, the dropout-free forward, mean CE.  Returns device tensors that are overwritten by the
+    next call (the callers below consume them before staging the next batch)."""
+
+    def __init__(self, model, batch_size, seq_len, use_graph=True):
+        super().__init__(model, batch_size, seq_len, use_graph)
+        self.logits_out = torch.zeros(batch_size, self.model.num_labels, dtype=torch.float32, device=self.eng.dev)
+
+    def _body(self):
+        self._unstage()
+        logits, loss = self.eng.forward(self.d_ids, self.d_tt, self.d_mask, self.d_lab, training=False,
+                                        need_backward=False)
+        self.logits_out.copy_(logits)
+        self.loss_out.copy_(loss)
+
+    def __call__(self, batch_data):
+        self.stage(batch_data)
+        self.run_device()
+        return self.logits_out, self.d_lab, self.loss_out
+
+
 class Trainer:
     def __init__(self, args, config, model, criterion, optimizer):
         self.args = args
@@ -146,6 +187,7 @@ class Trainer:
         self.criterion = criterion
         self.optimizer = optimizer
         self._fused = None
+        self._fused_eval = {}
         self._pin = {}
 
     def _to_device(self, batch_data):
@@ -175,6 +217,18 @@ class Trainer:
         output = self.model(input_ids=d["input_ids"], token_type_ids=d["token_type_ids"],
                             attention_mask=d["attention_mask"], labels=label)
         logits = output[1]
+        return logits, label
+
+    def eval_step(self, batch_data):
+        """`on_step` for the no-grad loops: the graph-captured forward when ``args.fused`` (one replay per batch instead
+        of ~100 eager launches), else the eager call.  Returns (logits, label) like `on_step`."""
+        if not getattr(self.args, "fused", True) or batch_data["input_ids"].is_cuda:
+            return self.on_step(batch_data)
+        B, S = batch_data["input_ids"].shape
+        key = (id(_unwrap(self.model)), B, S)     # `test` may swap the model [:222-224]
+        if key not in self._fused_eval:
+            self._fused_eval[key] = FusedEvalStep(self.model, B, S)
+        logits, label, _loss = self._fused_eval[key](batch_data)
         return logits, label
 
     def loss_reduce(self, loss):
@@ -246,7 +300,7 @@ class Trainer:
         loss_total = 0.
         with torch.no_grad():
             for step, batch_data in enumerate(dev_loader):
-                logits, label = self.on_step(batch_data)
+                logits, label = self.eval_step(batch_data)
                 loss = self.criterion(logits, label)
                 loss = self.loss_reduce(loss)
                 loss_total += loss
@@ -266,7 +320,7 @@ class Trainer:
         trues = []
         with torch.no_grad():
             for step, batch_data in enumerate(test_loader):
-                logits, label = self.on_step(batch_data)
+                logits, label = self.eval_step(batch_data)
                 logits, label = self.output_reduce(logits, label)
                 label = label.view(-1).detach().cpu().numpy().tolist()
                 logits = logits.detach().cpu().numpy()

@@ -62,6 +62,15 @@ def test_trainer_train_dev_test(cuda_dev, tmp_path, capsys, fused):
     ref_state = {k: v.cpu() for k, v in model.state_dict().items() if k in state}
     _, rz = bert_ref.forward(ref_state, cfg, b["input_ids"], b["token_type_ids"], b["attention_mask"], b["label"])
     assert float((logits.cpu() - rz).abs().max()) <= 1e-2
+    # the graph-captured eval forward (used by dev/test when args.fused) is the eager one, bit for bit, on every replay
+    ev = b2.FusedEvalStep(model, 4, 128)
+    for i in (0, 1, 2, 3, 0):
+        bi = dev_loader.batches[i]
+        flog, flab, floss = ev(bi)
+        with torch.no_grad():
+            elog, elab = tr.on_step(bi)
+        assert torch.equal(flog, elog) and torch.equal(flab, elab)
+        assert abs(float(floss) - float(F.cross_entropy(elog, elab))) <= 1e-6
     # like the reference, Trainer.test hands sklearn the 6 label names: every class must occur in y_true U y_pred
     assert len({int(v) for b_ in dev_loader.batches for v in b_["label"]}) == 6
     report = tr.test(model, dev_loader, ["c%d" % i for i in range(6)])
