@@ -28,7 +28,7 @@ extern "C" {
 /* ------------------------------------------------------------------------------------------------------ */
 const char* b2_last_error(void);
 int32_t b2_abi_version(void);             /* bumped when a struct below changes */
-#define B2_ABI_VERSION 6
+#define B2_ABI_VERSION 7
 int64_t b2_launch_count(void);            /* kernels launched by this library so far (process-wide) */
 
 /* ------------------------------------------------------------------------------------------------------ */
@@ -46,6 +46,8 @@ enum {
   B2_EPI_RESIDUAL = 4,              /* D = acc + aux_in                         (dgrad joining a residual)    */
   B2_EPI_GELU_BWD = 5,              /* D = acc * gelu_erf'(aux_in)              (dgrad through GELU)          */
   B2_EPI_RESIDUAL_F32 = 6,          /* D(fp32) = acc + aux_in(fp32); ldd / ld_aux_in count fp32 elements      */
+  B2_EPI_ACCUM_F32 = 7,             /* D(fp32) += acc (vector reductions at L2; D holds the residual stream;   */
+                                    /* split-K slices add in place, summation order unspecified)               */
   B2_EPI_PARTIAL_F32 = 100          /* internal: split-K partials                                           */
 };
 

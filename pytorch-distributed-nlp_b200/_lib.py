@@ -8,11 +8,12 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libb2ddpbert.so")
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 MAJOR_K, MAJOR_MN = 0, 1
 EPI_NONE, EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_DROPOUT_RESIDUAL, EPI_RESIDUAL, EPI_GELU_BWD = 0, 1, 2, 3, 4, 5
 EPI_RESIDUAL_F32 = 6
+EPI_ACCUM_F32 = 7
 IPC_HANDLE_BYTES = 64
 FLAG_SLOTS = 64
 

@@ -239,24 +239,38 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_fwd_kernel(const __grid
 // ------------------------------------------------------------------------------------------------------------
 // backward: grid (seq/128 kv blocks, heads, batch); loops over query blocks
 // ------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(ATT_THREADS) attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv,
-                                                                   const __grid_constant__ CUtensorMap tmap_do,
-                                                                   const AttnParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+//
+// kOneQ (seq == 128, the benchmark shape): the CTA is trimmed so TWO fit on an SM and hide each other's
+// TMA -> MMA -> TMEM-drain latencies (one CTA alone leaves the SM idle most of its ~13 us dependency chain):
+//   * shared memory 7 tiles (112 KB) instead of 8: V is dead once dP = dO V^T has been issued and completed, so the
+//     first 64-key half of P lives in V's tile;
+//   * TMEM 256 columns instead of 512: with a single query block nothing accumulates across iterations, so dQ / dV
+//     / dK overwrite the S / dP columns, which every thread has drained before the second MMA batch is issued.
+template <bool kOneQ>
+__global__ void __launch_bounds__(ATT_THREADS, kOneQ ? 2 : 1)
+attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_do,
+                     const AttnParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // kOneQ has no room for alignment slack: the dynamic window of a kernel without static shared memory starts
+  // 1024-aligned (checked below, loudly)
+  uint8_t* smem = kOneQ ? smem_raw
+                        : reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr int kTiles = kOneQ ? 7 : 8;
+  constexpr uint32_t kTmemCols = kOneQ ? 256 : 512;
   uint8_t* sK = smem;
   uint8_t* sV = smem + TILE_BYTES;
   uint8_t* sQ = smem + 2 * TILE_BYTES;
   uint8_t* sdO = smem + 3 * TILE_BYTES;
-  uint8_t* sP = smem + 4 * TILE_BYTES;   // 2 tiles
-  uint8_t* sdS = smem + 6 * TILE_BYTES;  // 2 tiles
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 8 * TILE_BYTES);
+  uint8_t* sP0 = kOneQ ? sV : smem + 4 * TILE_BYTES;                       // keys 0-63 of P
+  uint8_t* sP1 = kOneQ ? smem + 4 * TILE_BYTES : smem + 5 * TILE_BYTES;    // keys 64-127 of P
+  uint8_t* sdS = smem + (kOneQ ? 5 : 6) * TILE_BYTES;                      // 2 tiles
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kTiles * TILE_BYTES);
   uint64_t* bar_kv = &bars[0];
   uint64_t* bar_q = &bars[1];
   uint64_t* bar_s = &bars[2];
   uint64_t* bar_mma = &bars[3];
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(&bars[4]);
-  float* s_bias = reinterpret_cast<float*>(smem + 8 * TILE_BYTES + 64);  // [128] keys of this block
+  float* s_bias = reinterpret_cast<float*>(smem + kTiles * TILE_BYTES + 64);  // [128] keys of this block
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int row = (warp & 3) * 32 + lane;   // TMEM lane: query row inside the S/dP/dQ tiles, key row for dK/dV
@@ -265,6 +279,10 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_bwd_kernel(const __grid
   const int nq = p.seq / 128;
 
   if (tid == 0) {
+    if (kOneQ && (smem_u32(smem_raw) & 1023u) != 0u) {
+      printf("attention_bwd: dynamic shared memory is not 1024-byte aligned\n");
+      __trap();
+    }
     tma_prefetch_desc(&tmap_qkv);
     tma_prefetch_desc(&tmap_do);
     mbar_init(bar_kv, 1);
@@ -273,7 +291,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_bwd_kernel(const __grid
     mbar_init(bar_mma, 1);
     fence_mbar_init();
   }
-  if (warp == 0) tmem_alloc(tmem_holder, 512);
+  if (warp == 0) tmem_alloc(tmem_holder, kTmemCols);
   pdl_wait();               // PDL: setup above overlapped the predecessor's tail; global reads start below
   pdl_launch_dependents();
   if (tid < 128)
@@ -282,7 +300,8 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_bwd_kernel(const __grid
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_holder;
-  const uint32_t tm_s = tmem, tm_dp = tmem + 128, tm_dv = tmem + 256, tm_dk = tmem + 320, tm_dq = tmem + 384;
+  const uint32_t tm_s = tmem, tm_dp = tmem + 128;
+  const uint32_t tm_dq = tmem + (kOneQ ? 0 : 384), tm_dv = tmem + (kOneQ ? 64 : 256), tm_dk = tmem + (kOneQ ? 128 : 320);
   const uint32_t lane_base = ((uint32_t)((warp & 3) * 32)) << 16;
 
   const int row0 = b * p.seq;
@@ -368,7 +387,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_bwd_kernel(const __grid
         uint4 o;
         o.x = pack_bf16(pd[0], pd[1]); o.y = pack_bf16(pd[2], pd[3]);
         o.z = pack_bf16(pd[4], pd[5]); o.w = pack_bf16(pd[6], pd[7]);
-        st_tile_chunk(sP, row, half * 8 + c * 4 + g, o);
+        st_tile_chunk(half ? sP1 : sP0, row, c * 4 + g, o);
         o.x = pack_bf16(ds[0], ds[1]); o.y = pack_bf16(ds[2], ds[3]);
         o.z = pack_bf16(ds[4], ds[5]); o.w = pack_bf16(ds[6], ds[7]);
         st_tile_chunk(sdS, row, half * 8 + c * 4 + g, o);
@@ -379,12 +398,13 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_bwd_kernel(const __grid
     __syncthreads();
     if (tid == 0) {
       tc_fence_after();
-      const uint32_t ap = smem_u32(sP), ads = smem_u32(sdS), ado = smem_u32(sdO), aq = smem_u32(sQ),
+      const uint32_t ap = smem_u32(sP0), ads = smem_u32(sdS), ado = smem_u32(sdO), aq = smem_u32(sQ),
                      ak = smem_u32(sK);
+      const uint32_t p_pitch = smem_u32(sP1) - ap;   // byte distance between the two 64-key slabs of P
       // dV[key, d] += sum_q P[q, key] dO[q, d]      (A = P as MN-major: rows = q = K index)
 #pragma unroll
       for (int k = 0; k < 8; ++k)
-        umma_bf16(tm_dv, make_smem_desc(ap + k * 2048, TILE_BYTES, 1024), make_smem_desc(ado + k * 2048, 16, 1024),
+        umma_bf16(tm_dv, make_smem_desc(ap + k * 2048, p_pitch, 1024), make_smem_desc(ado + k * 2048, 16, 1024),
                   idesc_t, (i > 0 || k > 0) ? 1u : 0u);
       // dK[key, d] += sum_q dS[q, key] Q[q, d]
 #pragma unroll
@@ -474,7 +494,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_bwd_kernel(const __grid
   __syncthreads();
   if (warp == 0) {
     tc_fence_after();
-    tmem_dealloc(tmem, 512);
+    tmem_dealloc(tmem, kTmemCols);
   }
 }
 
@@ -496,6 +516,7 @@ __global__ void dq_convert_kernel(const float* __restrict__ acc, __nv_bfloat16* 
 
 constexpr int kFwdSmem = 5 * TILE_BYTES + 64 + 512 * 4 + 256 * 4 + 1024;
 constexpr int kBwdSmem = 8 * TILE_BYTES + 64 + 128 * 4 + 1024;
+constexpr int kBwdSmemOneQ = 7 * TILE_BYTES + 64 + 128 * 4;   // 115264 B: two CTAs per SM (2 x (this + 1 KB) <= 228 KB)
 
 static int32_t check_attn_shapes(const char* who, int64_t batch, int64_t seq, int64_t heads, int64_t head_dim) {
   B2_REQUIRE(batch > 0 && seq > 0 && heads > 0, "%s: empty problem (batch=%lld seq=%lld heads=%lld)", who,
@@ -572,11 +593,19 @@ extern "C" int32_t b2_attention_bwd(const void* qkv, const int64_t* attention_ma
   if (p.dq_accum) B2_CUDA(cudaMemsetAsync(p.dq_accum, 0, (size_t)tokens * hidden * 4, stream));
   static bool attr = false;
   if (!attr) {
-    B2_CUDA(cudaFuncSetAttribute(attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem));
+    B2_CUDA(cudaFuncSetAttribute(attention_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmem));
+    B2_CUDA(cudaFuncSetAttribute(attention_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 kBwdSmemOneQ));
+    B2_CUDA(cudaFuncSetAttribute(attention_bwd_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                 cudaSharedmemCarveoutMaxShared));
     attr = true;
   }
   dim3 grid((unsigned)(seq / 128), (unsigned)heads, (unsigned)batch);
-  B2_LAUNCH(attention_bwd_kernel, grid, ATT_THREADS, kBwdSmem, stream, tm_qkv, tm_do, p);
+  if (seq == 128) {
+    B2_LAUNCH(attention_bwd_kernel<true>, grid, ATT_THREADS, kBwdSmemOneQ, stream, tm_qkv, tm_do, p);
+  } else {
+    B2_LAUNCH(attention_bwd_kernel<false>, grid, ATT_THREADS, kBwdSmem, stream, tm_qkv, tm_do, p);
+  }
   B2_CUDA(cudaGetLastError());
   count_launches(1);
   if (p.dq_accum) {

@@ -447,7 +447,7 @@ static void fill_params(GemmKernelParams& p, const b2_gemm_args_t& a, int tile_m
   p.kblocks_total = (p.K + BK - 1) / BK;
   p.splits = splits;
   p.kblocks_per_split = (p.kblocks_total + splits - 1) / splits;
-  p.epilogue = splits > 1 ? B2_EPI_PARTIAL_F32 : a.epilogue;
+  p.epilogue = (splits > 1 && a.epilogue != B2_EPI_ACCUM_F32) ? B2_EPI_PARTIAL_F32 : a.epilogue;
   p.D = (__nv_bfloat16*)a.D; p.ldd = a.ldd;
   p.bias = (const __nv_bfloat16*)a.bias;
   p.aux_in = (const __nv_bfloat16*)a.aux_in; p.ld_aux_in = a.ld_aux_in;
@@ -491,7 +491,7 @@ static int32_t launch_gemm(const b2_gemm_args_t& a, int splits, cudaStream_t str
   B2_LAUNCH(kern, grid, GEMM_THREADS, Cfg::kSmemBytes, stream, ta, tb, p);
   B2_CUDA(cudaGetLastError());
   count_launches(1);
-  if (splits > 1) return launch_splitk_reduce(a, splits, stream);
+  if (splits > 1 && a.epilogue != B2_EPI_ACCUM_F32) return launch_splitk_reduce(a, splits, stream);
   return 0;
 }
 
@@ -520,7 +520,7 @@ static int32_t launch_gemm2(const b2_gemm_args_t& a, int splits, cudaStream_t st
   B2_LAUNCH(kern, 2 * pairs, GEMM_THREADS, Cfg::kSmemBytes, stream, ta, tb, p);
   B2_CUDA(cudaGetLastError());
   count_launches(1);
-  if (splits > 1) return launch_splitk_reduce(a, splits, stream);
+  if (splits > 1 && a.epilogue != B2_EPI_ACCUM_F32) return launch_splitk_reduce(a, splits, stream);
   return 0;
 }
 
@@ -530,7 +530,8 @@ struct Choice { int pair, bn, splits; };
 static Choice choose_config(const b2_gemm_args_t& a) {
   const int sms = num_sms();
   const int kblocks = (int)((a.K + BK - 1) / BK);
-  const bool can_split = (a.epilogue == B2_EPI_NONE) && a.workspace != nullptr && a.bias == nullptr;
+  const bool accum = a.epilogue == B2_EPI_ACCUM_F32;   // split-K slices add in place: no workspace, any split count
+  const bool can_split = accum || ((a.epilogue == B2_EPI_NONE) && a.workspace != nullptr && a.bias == nullptr);
   double best = 1e30;
   Choice c{0, 128, 1};
   const double l2_bytes_per_cycle = 5500.0;   // ~10 TB/s at ~1.85 GHz, shared by the busy SMs
@@ -543,9 +544,9 @@ static Choice choose_config(const b2_gemm_args_t& a) {
       const int tiles = (int)((a.M + tile_m - 1) / tile_m) * (int)((a.N + bn - 1) / bn);
       const int slots = pair ? sms / 2 : sms;
       const int max_s = can_split ? 8 : 1;
-      for (int s = 1; s <= max_s; s *= 2) {
+      for (int s = 1; s <= max_s; s = accum ? s + 1 : s * 2) {
         if (s > 1 && (kblocks / s < 8)) break;
-        if (s > 1 && (size_t)s * a.M * a.N * 4 > (size_t)a.workspace_bytes) break;
+        if (s > 1 && !accum && (size_t)s * a.M * a.N * 4 > (size_t)a.workspace_bytes) break;
         const int work = tiles * s;
         const int rounds = (work + slots - 1) / slots;
         const int busy_sms = (work < slots ? work : slots) * (pair ? 2 : 1);
@@ -554,7 +555,8 @@ static Choice choose_config(const b2_gemm_args_t& a) {
         const double feed_cycles = bytes_per_sm * busy_sms / l2_bytes_per_cycle;
         const double kb_cycles = mma_cycles > feed_cycles ? mma_cycles : feed_cycles;
         double t = rounds * ((double)((kblocks + s - 1) / s) * kb_cycles + 2500.0 /*prologue + epilogue tail*/);
-        if (s > 1) t += 1500.0 + (double)s * a.M * a.N * 8 / 3000.0;            // partial write + reduce pass
+        if (s > 1 && !accum) t += 1500.0 + (double)s * a.M * a.N * 8 / 3000.0;  // partial write + reduce pass
+        if (s > 1 && accum) t += (double)(s - 1) * a.M * a.N * 4 / 3000.0;      // extra reduction traffic at L2
         if (t < best) { best = t; c = Choice{pair, bn, s}; }
       }
     }
@@ -577,7 +579,7 @@ extern "C" int32_t b2_gemm_bf16(const b2_gemm_args_t* a, void* stream_) {
              "b2_gemm_bf16: K and leading dimensions must be multiples of 8 elements (16 B)");
   B2_REQUIRE(((uintptr_t)a->A % 16 == 0) && ((uintptr_t)a->B % 16 == 0) && ((uintptr_t)a->D % 16 == 0),
              "b2_gemm_bf16: operands must be 16-byte aligned");
-  B2_REQUIRE(a->epilogue >= B2_EPI_NONE && a->epilogue <= B2_EPI_RESIDUAL_F32, "b2_gemm_bf16: bad epilogue %d",
+  B2_REQUIRE(a->epilogue >= B2_EPI_NONE && a->epilogue <= B2_EPI_ACCUM_F32, "b2_gemm_bf16: bad epilogue %d",
              a->epilogue);
   if (a->epilogue == B2_EPI_BIAS || a->epilogue == B2_EPI_BIAS_GELU || a->epilogue == B2_EPI_BIAS_DROPOUT_RESIDUAL)
     B2_REQUIRE(a->bias != nullptr, "b2_gemm_bf16: epilogue %d needs a bias", a->epilogue);
@@ -606,9 +608,10 @@ extern "C" int32_t b2_gemm_bf16(const b2_gemm_args_t* a, void* stream_) {
   }
   if (a->force_splits >= 1) {
     B2_REQUIRE(a->force_splits == 1 ||
+                   a->epilogue == B2_EPI_ACCUM_F32 ||
                    (a->epilogue == B2_EPI_NONE && a->workspace &&
                     (size_t)a->force_splits * a->M * a->N * 4 <= (size_t)a->workspace_bytes),
-               "b2_gemm_bf16: split-K needs EPI_NONE and a large enough workspace");
+               "b2_gemm_bf16: split-K needs EPI_ACCUM_F32, or EPI_NONE and a large enough workspace");
     c.splits = a->force_splits;
   }
   const bool a_mn = a->a_major == B2_MAJOR_MN, b_mn = a->b_major == B2_MAJOR_MN;

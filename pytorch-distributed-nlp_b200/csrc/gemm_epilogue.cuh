@@ -58,6 +58,20 @@ __device__ __forceinline__ void tile_s2g(uint8_t* stage, uint8_t* g, long long p
     if (r < rows_valid) *reinterpret_cast<uint4*>(g + (size_t)r * pitch + c * 16) = v;
   }
 }
+// same tile walk, but ADDING the fp32 tile into global memory (one 16-byte vector reduction per lane and step)
+__device__ __forceinline__ void tile_s2g_red_f32(uint8_t* stage, uint8_t* g, long long pitch, int lane,
+                                                 int rows_valid) {
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int r = 4 * k + (lane >> 3), c = lane & 7;
+    const uint4 v = *stage_ptr(stage, r, c);
+    if (r < rows_valid)
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(g + (size_t)r * pitch + c * 16),
+                   "f"(__uint_as_float(v.x)), "f"(__uint_as_float(v.y)), "f"(__uint_as_float(v.z)),
+                   "f"(__uint_as_float(v.w))
+                   : "memory");
+  }
+}
 // asynchronous variant (cp.async, no registers held): issue early, tile_async_wait() + __syncwarp() before reading
 __device__ __forceinline__ void tile_g2s_async(uint8_t* stage, const uint8_t* g, long long pitch, int lane,
                                                int rows_valid) {
@@ -108,11 +122,15 @@ __device__ __forceinline__ void epilogue_tile(const GemmKernelParams& p, const D
   const int m = row0 + lane;
   const uint32_t taddr = tmem_acc + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(colhalf * kColsPerWarp);
 
-  if (p.epilogue == B2_EPI_PARTIAL_F32 || p.epilogue == B2_EPI_RESIDUAL_F32) {
+  if (p.epilogue == B2_EPI_PARTIAL_F32 || p.epilogue == B2_EPI_RESIDUAL_F32 || p.epilogue == B2_EPI_ACCUM_F32) {
     // ---- fp32 outputs: 32 columns (128 bytes) per group ----
-    const bool partial = p.epilogue == B2_EPI_PARTIAL_F32;
-    float* dst_base = partial ? p.partial + (size_t)split * p.M * p.N : reinterpret_cast<float*>(p.D);
-    const long long dst_ld = partial ? (long long)p.N : p.ldd;
+    // ACCUM_F32: D += acc with vector reductions at L2 -- D already holds the residual stream, and split-K slices
+    // of one tile simply add into the same place (no partial buffer, no reduce pass)
+    const bool accum = p.epilogue == B2_EPI_ACCUM_F32;
+    const bool partial = p.epilogue == B2_EPI_PARTIAL_F32 || accum;   // "no auxiliary tile to fetch"
+    const bool to_ws = p.epilogue == B2_EPI_PARTIAL_F32;
+    float* dst_base = to_ws ? p.partial + (size_t)split * p.M * p.N : reinterpret_cast<float*>(p.D);
+    const long long dst_ld = to_ws ? (long long)p.N : p.ldd;
     // the auxiliary tile (fp32 residual) does not depend on the accumulator: fetch it before waiting for the MMAs,
     // and the next group's while the current one is being combined and stored
     auto prefetch = [&](int c) {
@@ -150,7 +168,9 @@ __device__ __forceinline__ void epilogue_tile(const GemmKernelParams& p, const D
         for (int k = 0; k < 8; ++k)
           *stage_ptr(stage, lane, k) = make_uint4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
         __syncwarp();
-        tile_s2g(stage, reinterpret_cast<uint8_t*>(dst_base + (size_t)row0 * dst_ld + n), dst_ld * 4, lane, rows_valid);
+        uint8_t* gdst = reinterpret_cast<uint8_t*>(dst_base + (size_t)row0 * dst_ld + n);
+        if (accum) tile_s2g_red_f32(stage, gdst, dst_ld * 4, lane, rows_valid);
+        else       tile_s2g(stage, gdst, dst_ld * 4, lane, rows_valid);
       }
       __syncwarp();
     }

@@ -407,6 +407,7 @@ class _Engine:
         self._saved = None
         self.wgrad_stream = torch.cuda.Stream(device=self.dev)
         self.opt_stream = torch.cuda.Stream(device=self.dev)
+        self.accum_dgrad = os.environ.get("B2_ACCUM_DGRAD", "1") != "0"
         self.use_wgrad_stream = os.environ.get("B2_WGRAD_STREAM", "1") != "0"
         # fp32 accumulators for the bias gradients that kernels produce as a side effect of their epilogues (QKV bias
         # from attention backward, intermediate bias from the GELU' dgrad): per layer [3H | I]; one finishing launch
@@ -673,7 +674,8 @@ class _Engine:
             lp2 = self.ln_partials[2 * st]
             L.call("b2_layernorm_bwd", dx.data_ptr(), None, a["z2"].data_ptr(), a["mean2"].data_ptr(),
                    a["rstd2"].data_ptr(), w(pre + "output.LayerNorm.weight"), M, H, p_h, rng, 3 + 3 * l, 1,
-                   ws["dz"].data_ptr(), dzd.data_ptr(), g(pre + "output.LayerNorm.weight"),
+                   (dx_other if self.accum_dgrad else ws["dz"]).data_ptr(), dzd.data_ptr(),
+                   g(pre + "output.LayerNorm.weight"),
                    g(pre + "output.LayerNorm.bias"), g(pre + "output.dense.bias"), lp2.data_ptr(), lp2.numel(),
                    ctypes.byref(np2), s)
             fork()
@@ -689,14 +691,21 @@ class _Engine:
             fork()
             self.gemm(I, H, M, dU.data_ptr(), I, MN, a["x1"].data_ptr(), H, MN,
                       g(pre + "intermediate.dense.weight"), H, split=True, stream=ss)
-            self.gemm(M, H, I, dU.data_ptr(), I, KM, w(pre + "intermediate.dense.weight"), H, MN,
-                      dx_other.data_ptr(), H, L.EPI_RESIDUAL_F32, aux_in=ws["dz"].data_ptr(), ld_aux_in=H)
+            # dX1 = dZ2 + dU W1.  accum_dgrad: LayerNorm backward left dZ2 (fp32) in dx_other and the GEMM adds into
+            # it (split-K slices reduce in place at L2), else the epilogue reads dZ2 as an auxiliary tile
+            if self.accum_dgrad:
+                self.gemm(M, H, I, dU.data_ptr(), I, KM, w(pre + "intermediate.dense.weight"), H, MN,
+                          dx_other.data_ptr(), H, L.EPI_ACCUM_F32)
+            else:
+                self.gemm(M, H, I, dU.data_ptr(), I, KM, w(pre + "intermediate.dense.weight"), H, MN,
+                          dx_other.data_ptr(), H, L.EPI_RESIDUAL_F32, aux_in=ws["dz"].data_ptr(), ld_aux_in=H)
             # --- BertSelfOutput
             np1 = ctypes.c_int32(0)
             lp1 = self.ln_partials[2 * st + 1]
             L.call("b2_layernorm_bwd", dx_other.data_ptr(), None, a["z1"].data_ptr(), a["mean1"].data_ptr(),
                    a["rstd1"].data_ptr(), w(pre + "attention.output.LayerNorm.weight"), M, H, p_h, rng, 2 + 3 * l, 1,
-                   ws["dz1"].data_ptr(), dz1d.data_ptr(), g(pre + "attention.output.LayerNorm.weight"),
+                   (dx if self.accum_dgrad else ws["dz1"]).data_ptr(), dz1d.data_ptr(),
+                   g(pre + "attention.output.LayerNorm.weight"),
                    g(pre + "attention.output.LayerNorm.bias"), g(pre + "attention.output.dense.bias"),
                    lp1.data_ptr(), lp1.numel(), ctypes.byref(np1), s)
             fork()
@@ -719,8 +728,12 @@ class _Engine:
             if side is not main:
                 done[l] = torch.cuda.Event()
                 done[l].record(side)
-            self.gemm(M, H, 3 * H, dqkv.data_ptr(), 3 * H, KM, w(pre + "attention.self.query.weight"), H, MN,
-                      dx.data_ptr(), H, L.EPI_RESIDUAL_F32, aux_in=ws["dz1"].data_ptr(), ld_aux_in=H)
+            if self.accum_dgrad:
+                self.gemm(M, H, 3 * H, dqkv.data_ptr(), 3 * H, KM, w(pre + "attention.self.query.weight"), H, MN,
+                          dx.data_ptr(), H, L.EPI_ACCUM_F32)
+            else:
+                self.gemm(M, H, 3 * H, dqkv.data_ptr(), 3 * H, KM, w(pre + "attention.self.query.weight"), H, MN,
+                          dx.data_ptr(), H, L.EPI_RESIDUAL_F32, aux_in=ws["dz1"].data_ptr(), ld_aux_in=H)
             # fp32 accumulators -> bf16 bias gradients of this layer (and re-arm them); for S != 128 the QKV segment's
             # accumulator is unused (zero) and must not overwrite the colsum result: finish only the intermediate one
             seg0 = 2 * l if S == 128 else 2 * l + 1

@@ -145,6 +145,21 @@ def test_residual_f32_stream(cuda_dev):
         assert (D - ref).abs().max().item() <= 1e-3 * ref.abs().max().item()
 
 
+@pytest.mark.parametrize("kernel", [1, 2])
+@pytest.mark.parametrize("splits", [0, 1, 2, 3])
+def test_accum_f32_in_place(cuda_dev, kernel, splits):
+    """dgrad adding into the fp32 residual-gradient stream: D(fp32) += A @ B, split-K slices reducing in place at L2
+    (ragged M, K not a multiple of the split count's k-block share)"""
+    M, N, K = 300, 768, 2304
+    torch.manual_seed(19)
+    A, B = _rand((M, K), cuda_dev), _rand((K, N), cuda_dev, 0.05)
+    R = torch.randn(M, N, device=cuda_dev)
+    D = R.clone()
+    _call(M, N, K, A, K, L.MAJOR_K, B, N, L.MAJOR_MN, D, L.EPI_ACCUM_F32, kernel=kernel, splits=splits)
+    ref = A.float() @ B.float() + R
+    assert (D - ref).abs().max().item() <= 1e-3 * ref.abs().max().item()
+
+
 def test_residual_and_gelu_bwd(cuda_dev):
     M, N, K = 384, 768, 768
     torch.manual_seed(6)
