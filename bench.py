@@ -344,10 +344,10 @@ def run_b200(args):
         if world == 1:
             from oracle import cpu_step
             cores = cpu_step.usable_cores()
-            r = cpu_step.time_steps(cfg, 16, SEQ, steps=2, warmup=1, threads=cores)
+            r = cpu_step.time_steps(cfg, BATCH, SEQ, steps=5, warmup=2, threads=cores)
             cpu = {"value": round(r["samples_per_s"], 3), "unit": "samples/s", "cores": cores, "kind": "port",
-                   "sample": "2 timed steps (+1 warm-up) of batch 16 x seq 128: single-gpu-cls.py loop body, HF "
-                             "BertForSequenceClassification fp32 eager, dropout on, restated HF AdamW"}
+                   "sample": "5 timed steps (+2 warm-up) of batch %d x seq %d: single-gpu-cls.py loop body, HF "
+                             "BertForSequenceClassification fp32 eager, dropout on, restated HF AdamW" % (BATCH, SEQ)}
         h2d = (3 * BATCH * SEQ + BATCH) * 8
         line = {
             "metric": METRIC, "value": round(value, 1), "unit": "samples/s", "n_gpus": world, "steps": args.steps,
@@ -379,7 +379,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     args = ap.parse_args()
     if args.impl == "reference":

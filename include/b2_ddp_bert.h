@@ -28,7 +28,7 @@ extern "C" {
 /* ------------------------------------------------------------------------------------------------------ */
 const char* b2_last_error(void);
 int32_t b2_abi_version(void);             /* bumped when a struct below changes */
-#define B2_ABI_VERSION 7
+#define B2_ABI_VERSION 8
 int64_t b2_launch_count(void);            /* kernels launched by this library so far (process-wide) */
 
 /* ------------------------------------------------------------------------------------------------------ */
@@ -182,6 +182,13 @@ int32_t b2_head_bwd(const float* dlogits, const void* hidden_states, const void*
 typedef struct b2_adamw_hparams {
   double lr, beta1, beta2, eps, weight_decay; /* python doubles, rounded to fp32 the way torch rounds them */
   int32_t correct_bias;
+  /* optional DEVICE pointer to the fp32 loss scale of a torch.cuda.amp.GradScaler (the reference's -amp scripts,
+   * multi-gpu-distributed-mp-amp-cls.py:160-171): gradients are divided by *grad_scale before the update.
+   * NULL = unscaled gradients.                                                                                */
+  const float* grad_scale;
+  /* optional DEVICE pointer to the GradScaler's fp32 inf/nan indicator: a non-zero value skips the update (and the
+   * step count), as GradScaler.step() skips optimizer.step().  NULL = always update.                            */
+  const float* found_inf;
 } b2_adamw_hparams_t;
 
 /* Fused update of one contiguous slice [begin, end) (element indices, multiples of 8) of the flat parameter
@@ -195,8 +202,9 @@ int32_t b2_bucket_reduce_adamw(const void* const* peer_grads, void* const* peer_
                                const uint8_t* decay_flags, int64_t begin, int64_t end,
                                const b2_adamw_hparams_t* hp, const int64_t* step_counter, void* stream);
 
-/* ++step (AdamW t) and ++rng step (dropout stream) on the device: keeps CUDA-graph replays stateful        */
-int32_t b2_step_advance(int64_t* step_counter, void* rng_state, void* stream);
+/* ++step (AdamW t) and ++rng step (dropout stream) on the device: keeps CUDA-graph replays stateful.
+ * found_inf (optional device fp32, see b2_adamw_hparams_t): non-zero leaves the AdamW step count untouched.   */
+int32_t b2_step_advance(int64_t* step_counter, void* rng_state, const float* found_inf, void* stream);
 int32_t b2_rng_seed(void* rng_state, uint64_t seed, uint64_t step, void* stream);
 
 /* segments[i] = {src element offset in `src` (fp32), dst element offset in `dst` (bf16), count}: dst <- bf16(src), then

@@ -28,11 +28,14 @@ struct ReduceAdamWParams {
   float lr, beta1, beta2, one_minus_beta1, one_minus_beta2, eps, lr_wd;
   int correct_bias, has_wd;
   const long long* step_counter;
+  const float* grad_scale;   // optional device scalar (GradScaler): gradients are divided by it
+  const float* found_inf;    // optional device scalar (GradScaler): non-zero skips the update
 };
 
 __global__ void __launch_bounds__(256) reduce_adamw_kernel(const ReduceAdamWParams p) {
   pdl_wait();               // PDL: predecessors complete + visible before any global access
   pdl_launch_dependents();  // let the next kernel in the stream begin launching
+  if (p.found_inf != nullptr && *p.found_inf != 0.f) return;   // GradScaler saw inf/nan: this step is skipped
   // HF AdamW bias correction: step_size = lr * sqrt(1 - b2^t) / (1 - b1^t), t = steps taken including this one
   const long long t = *p.step_counter + 1;
   float step_size = p.lr;
@@ -41,7 +44,8 @@ __global__ void __launch_bounds__(256) reduce_adamw_kernel(const ReduceAdamWPara
     const double bc2 = 1.0 - pow(p.beta2_d, (double)t);
     step_size = (float)(p.lr_d * sqrt(bc2) / bc1);
   }
-  const float inv_world = 1.0f / (float)p.world;
+  // mean over ranks; with a GradScaler also the unscale (a power of two: exact)
+  const float inv_world = (p.grad_scale != nullptr ? 1.0f / *p.grad_scale : 1.0f) / (float)p.world;
   const long long nvec = (p.end - p.begin) >> 3;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec;
        i += (long long)gridDim.x * blockDim.x) {
@@ -87,11 +91,11 @@ __global__ void __launch_bounds__(256) reduce_adamw_kernel(const ReduceAdamWPara
   }
 }
 
-__global__ void step_advance_kernel(long long* step, unsigned long long* rng) {
+__global__ void step_advance_kernel(long long* step, unsigned long long* rng, const float* found_inf) {
   pdl_wait();               // PDL: predecessors complete + visible before any global access
   pdl_launch_dependents();  // let the next kernel in the stream begin launching
   if (threadIdx.x == 0 && blockIdx.x == 0) {
-    if (step) *step += 1;
+    if (step && !(found_inf != nullptr && *found_inf != 0.f)) *step += 1;
     if (rng) rng[1] += 1;
   }
 }
@@ -177,6 +181,8 @@ extern "C" int32_t b2_bucket_reduce_adamw(const void* const* peer_grads, void* c
   p.eps = (float)hp->eps; p.lr_wd = (float)(hp->lr * hp->weight_decay);
   p.correct_bias = hp->correct_bias; p.has_wd = hp->weight_decay > 0.0 ? 1 : 0;
   p.step_counter = (const long long*)step_counter;
+  p.grad_scale = hp->grad_scale;
+  p.found_inf = hp->found_inf;
   const long long nvec = (end - begin) >> 3;
   long long blocks = (nvec + 255) / 256;
   const long long cap = 148 * 8;
@@ -187,8 +193,9 @@ extern "C" int32_t b2_bucket_reduce_adamw(const void* const* peer_grads, void* c
   return 0;
 }
 
-extern "C" int32_t b2_step_advance(int64_t* step_counter, void* rng_state, void* stream_) {
-  B2_LAUNCH(step_advance_kernel, 1, 32, 0, (cudaStream_t)stream_, (long long*)step_counter, (unsigned long long*)rng_state);
+extern "C" int32_t b2_step_advance(int64_t* step_counter, void* rng_state, const float* found_inf, void* stream_) {
+  B2_LAUNCH(step_advance_kernel, 1, 32, 0, (cudaStream_t)stream_, (long long*)step_counter,
+            (unsigned long long*)rng_state, found_inf);
   B2_CUDA(cudaGetLastError());
   count_launches(1);
   return 0;

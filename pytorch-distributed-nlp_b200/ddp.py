@@ -191,7 +191,7 @@ class DistributedDataParallel(nn.Module):
             opt.advance(s)
         self._pending = None
         self._master_stale = True
-        opt._armed = bool(self.overlap)
+        opt._armed = bool(self.overlap) and not getattr(opt, "_amp_seen", False)
 
     def _gather_master(self):
         """fp32 masters are updated slice-wise by their owner ranks; re-assemble them (checkpoint time only)."""

@@ -198,7 +198,14 @@ class _StepFn(torch.autograd.Function):
             raise RuntimeError("backward reached the model without any gradient")
         eng.backward(d_logits, d_loss if ctx.has_loss else None)
         ctx.model._notify_backward_done()
-        return None, None, None, None, None, None
+        # Gradients live in the engine's bf16 bucket space, not in `.grad`.  The anchor (classifier.bias) gets its
+        # true gradient as a 6-float fp32 probe: it is the column sum of d_logits, so an inf/nan anywhere upstream
+        # of the model shows up in it -- which is what torch.cuda.amp.GradScaler's inf check needs to see.
+        off, shape = ctx.model._layout.entries["classifier.bias"]
+        n = 1
+        for d in shape:
+            n *= d
+        return eng.grads[off:off + n].float().view(shape), None, None, None, None, None
 
 
 class BertForSequenceClassification(nn.Module):

@@ -12,6 +12,14 @@ from . import _lib as L
 
 
 class AdamW(torch.optim.Optimizer):
+    # torch.cuda.amp.GradScaler contract for optimizers that unscale themselves (torch/amp/grad_scaler.py `step`):
+    # the scaler sets `self.grad_scale` (device fp32 scalar) / `self.found_inf` around step() instead of walking
+    # `.grad` tensors -- which do not exist here (gradients live in the bf16 bucket space).  This is what lets the
+    # reference's -amp loop (multi-gpu-distributed-mp-amp-cls.py:166-171: autocast, scaler.scale(loss).backward(),
+    # scaler.step(optimizer), scaler.update()) run unchanged.  bf16 has fp32's exponent range, so no overflow check
+    # is needed: found_inf stays 0 and the scale only has to be divided out (exactly: it is a power of two).
+    _step_supports_amp_scaling = True
+
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-6, weight_decay=0.0, correct_bias=True,
                  no_deprecation_warning=True):
         if lr < 0.0:
@@ -55,6 +63,8 @@ class AdamW(torch.optim.Optimizer):
         self._dev_state = None
         self._armed = False      # set by FusedTrainStep: per-bucket updates may start during backward
         self._pending = set()    # buckets already updated (on the engine's optimizer stream) in this step
+        self._amp_seen = False   # a GradScaler drives this optimizer: the scale is only known inside step(), so
+                                 # per-bucket updates must not start during backward
         self._model._optimizer = self
 
     # -- device state (fp32 moments, step counter) ------------------------------------------------------------------
@@ -79,11 +89,27 @@ class AdamW(torch.optim.Optimizer):
         hp.lr, hp.beta1, hp.beta2, hp.eps = float(g["lr"]), float(g["betas"][0]), float(g["betas"][1]), float(g["eps"])
         hp.weight_decay = float(self._wd)
         hp.correct_bias = 1 if g["correct_bias"] else 0
+        gs = getattr(self, "grad_scale", None)        # set by GradScaler.step() for the duration of step()
+        hp.grad_scale = gs.data_ptr() if gs is not None else None
+        if gs is not None and (gs.dtype != torch.float32 or not gs.is_cuda):
+            raise TypeError("grad_scale must be a CUDA fp32 scalar (torch.cuda.amp.GradScaler's)")
+        hp.found_inf = self._found_inf_ptr()
         return hp
+
+    def _found_inf_ptr(self):
+        fi = getattr(self, "found_inf", None)         # GradScaler: 0-dim fp32 tensor (or int 0 when nothing was checked)
+        if isinstance(fi, torch.Tensor):
+            if fi.dtype != torch.float32 or not fi.is_cuda:
+                raise TypeError("found_inf must be a CUDA fp32 scalar (torch.cuda.amp.GradScaler's)")
+            self._found_inf_keep = fi                 # keep the tensor alive until the kernels that read it have run
+            return fi.data_ptr()
+        return None
 
     def zero_grad(self, set_to_none=True):
         """Gradients live in the bf16 bucket space and are overwritten by every backward: nothing to clear
-        (the reference's zero_grad [:172] exists only because torch accumulates into .grad)."""
+        (the reference's zero_grad [:172] exists only because torch accumulates into .grad).  The one real `.grad`
+        is the small fp32 probe the eager backward leaves on classifier.bias for GradScaler's inf check."""
+        self._model._params_by_name["classifier.bias"].grad = None
         return None
 
     def update_range(self, begin, end, world, rank, peer_grads, peer_shadow, stream):
@@ -97,11 +123,13 @@ class AdamW(torch.optim.Optimizer):
 
     def advance(self, stream):
         st = self._state()
-        L.call("b2_step_advance", L.ptr(st["step"]), L.ptr(self._model._engine.rng), stream)
+        L.call("b2_step_advance", L.ptr(st["step"]), L.ptr(self._model._engine.rng), self._found_inf_ptr(), stream)
 
     @torch.no_grad()
     def step(self, closure=None):
         loss = closure() if closure is not None else None
+        if getattr(self, "grad_scale", None) is not None:
+            self._amp_seen = True
         model = self._model
         eng = model._engine
         if eng is None:
@@ -123,6 +151,9 @@ class AdamW(torch.optim.Optimizer):
                         self.update_range(b0, e0, 1, 0, [eng.grads.data_ptr()], [eng.shadow.data_ptr()], s)
             self._pending = set()
             self.advance(s)
+        # the inf-check probe has served its purpose (GradScaler reads it before calling step); the -amp scripts never
+        # call zero_grad, so drop it here or it would accumulate
+        model._params_by_name["classifier.bias"].grad = None
         return loss
 
     def moments(self):

@@ -1,6 +1,12 @@
-"""Run under torchrun (one rank per GPU): the peer-HBM DDP path vs the oracle's DDP restatement.
-Exits non-zero on any mismatch.  Used by tests/test_ddp.py and by hand: 
-    python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29555 tests/ddp_worker.py
+"""One rank per GPU: the peer-HBM DDP path vs the oracle's DDP restatement.  Exits non-zero on any mismatch.
+Two launchers, as in the reference:
+  * torchrun / torch.distributed.launch, env:// rendezvous (multi-gpu-distributed-cls.py:268-277, README.md:84):
+      python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29555 tests/ddp_worker.py
+  * torch.multiprocessing.spawn with a tcp:// rendezvous (multi-gpu-distributed-mp-cls.py:265,361):
+      python tests/ddp_worker.py --spawn 2
+Three step loops: "eager" (fwd / criterion / zero_grad / backward / step, :166-176), "amp" (the -amp scripts' loop:
+autocast + GradScaler.scale(loss).backward() / scaler.step / scaler.update, multi-gpu-distributed-mp-amp-cls.py
+:166-171) and "fused" (the whole step as one CUDA graph).
 """
 import os
 import sys
@@ -17,11 +23,17 @@ from parity import TOL_TRAJ, b2, bert_ref, state_from_hf_init, tiny_config
 from oracle import ddp_ref
 
 
-def main():
-    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    dist.init_process_group("nccl", device_id=dev)
+def main(local=None, world=None, init_method=None):
+    if init_method is None:     # torchrun
+        rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+        torch.cuda.set_device(local)
+        dev = torch.device("cuda", local)
+        dist.init_process_group("nccl", device_id=dev)
+    else:                       # mp.spawn(main_worker, nprocs=world, args=(world,)): first argument is the process index
+        rank = local
+        torch.cuda.set_device(local)
+        dev = torch.device("cuda", local)
+        dist.init_process_group("nccl", init_method=init_method, world_size=world, rank=rank)
     cfg = tiny_config(hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0)
     state = state_from_hf_init(cfg, seed=123)
     steps = 6
@@ -33,7 +45,7 @@ def main():
     class A:
         weight_decay, learning_rate = 0.01, 3e-5
 
-    for mode in ("eager", "fused"):
+    for mode in ("eager", "amp", "fused"):
         # every rank but 0 starts from different weights: the wrap-time broadcast must make rank 0 win
         init = state if rank == 0 else state_from_hf_init(cfg, seed=999)
         model = b2.BertForSequenceClassification(cfg)
@@ -43,10 +55,21 @@ def main():
         opt = b2.build_optimizer(ddp, A)
         assert [n for n, _ in ddp.named_parameters()][0].startswith("module.")
         fused = b2.FusedTrainStep(ddp, opt, 4, 128) if mode == "fused" else None
+        scaler = torch.amp.GradScaler("cuda") if mode == "amp" else None
         for s in range(steps):
             b = batches[s][rank]
             if fused is not None:
                 loss = fused(b)
+            elif scaler is not None:
+                d = {k: v.to(dev) for k, v in b.items()}
+                with torch.autocast("cuda"):
+                    out = ddp(input_ids=d["input_ids"], token_type_ids=d["token_type_ids"],
+                              attention_mask=d["attention_mask"], labels=d["label"])
+                    loss = F.cross_entropy(out[1], d["label"])
+                scaler.scale(loss).backward()
+                scaler.step(opt)
+                scaler.update()
+                assert float(scaler.get_scale()) == 65536.0   # bf16 gradients never trip the inf check
             else:
                 d = {k: v.to(dev) for k, v in b.items()}
                 out = ddp(input_ids=d["input_ids"], token_type_ids=d["token_type_ids"],
@@ -87,4 +110,9 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) >= 3 and sys.argv[1] == "--spawn":
+        import torch.multiprocessing as mp
+        n = int(sys.argv[2])
+        mp.spawn(main, nprocs=n, args=(n, "tcp://127.0.0.1:%d" % (29600 + os.getpid() % 300)))
+    else:
+        main()

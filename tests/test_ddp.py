@@ -18,4 +18,14 @@ def test_peer_hbm_ddp_matches_oracle(world):
            "--master-addr", "127.0.0.1", "--master-port", "29577", os.path.join(ROOT, "tests", "ddp_worker.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "mode eager OK" in r.stdout and "mode amp OK" in r.stdout and "mode fused OK" in r.stdout
+
+
+def test_mp_spawn_launcher(world=2):
+    """the -mp scripts' launcher: torch.multiprocessing.spawn + tcp:// rendezvous"""
+    if not torch.cuda.is_available() or torch.cuda.device_count() < world:
+        pytest.skip("needs %d GPUs" % world)
+    cmd = [sys.executable, os.path.join(ROOT, "tests", "ddp_worker.py"), "--spawn", str(world)]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "mode fused OK" in r.stdout

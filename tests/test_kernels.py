@@ -290,7 +290,7 @@ def test_adamw_matches_hf_restatement(cuda_dev):
         g = (torch.randn(n, device=dev) * 0.01).to(bf)
         L.call("b2_bucket_reduce_adamw", L.ptr_array([g.data_ptr()]), L.ptr_array([shadow.data_ptr()]), 1, 0,
                master.data_ptr(), m.data_ptr(), v.data_ptr(), decay.data_ptr(), 0, n, hp, step.data_ptr(), S())
-        L.call("b2_step_advance", step.data_ptr(), rs.data_ptr(), S())
+        L.call("b2_step_advance", step.data_ptr(), rs.data_ptr(), None, S())
         gc = g.float().cpu()
         opt.step({"w.weight": gc[: n // 2], "w.bias": gc[n // 2:]})
     torch.cuda.synchronize()

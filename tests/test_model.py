@@ -112,6 +112,63 @@ def test_tiny_trajectory_eager_and_fused(cuda_dev):
         assert float((sd[k].double() - sd2[k].double()).abs().max()) <= 2e-5, k
 
 
+def test_amp_script_loop_with_gradscaler(cuda_dev):
+    """The -amp scripts' loop (multi-gpu-distributed-mp-amp-cls.py:166-171: autocast, scaler.scale(loss).backward(),
+    scaler.step(optimizer), scaler.update(), and no zero_grad) runs unchanged and lands where the plain loop lands:
+    the loss scale (2^16) is divided out inside the fused AdamW; a poisoned step is skipped like GradScaler skips it."""
+    cfg = tiny_config(hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0)
+    state = state_from_hf_init(cfg)
+    batches = [bert_ref.synthetic_batch(cfg, 4, 128, 2100 + i, padded=(i % 2 == 1)) for i in range(4)]
+
+    class A:
+        weight_decay, learning_rate = 0.01, 3e-5
+
+    def fwd(model, b):
+        d = to_dev(b, cuda_dev)
+        out = model(input_ids=d["input_ids"], token_type_ids=d["token_type_ids"],
+                    attention_mask=d["attention_mask"], labels=d["label"])
+        return F.cross_entropy(out[1], d["label"])
+
+    plain = make_model(cfg, state, cuda_dev).train()
+    opt = b2.build_optimizer(plain, A)
+    ref_losses = []
+    for b in batches:
+        loss = fwd(plain, b)
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        ref_losses.append(float(loss))
+
+    amp = make_model(cfg, state, cuda_dev).train()
+    opt2 = b2.build_optimizer(amp, A)
+    scaler = torch.amp.GradScaler("cuda")
+    for i, b in enumerate(batches):
+        with torch.autocast("cuda"):
+            loss = fwd(amp, b)
+        scaler.scale(loss).backward()
+        scaler.step(opt2)
+        scaler.update()
+        assert abs(float(loss) - ref_losses[i]) <= 5e-4, (i, float(loss), ref_losses[i])
+    assert float(scaler.get_scale()) == 65536.0
+    sd, sd2 = plain.state_dict(), amp.state_dict()
+    for k in sd:
+        assert float((sd[k].double() - sd2[k].double()).abs().max()) <= 2e-5, k
+    # a non-finite loss: GradScaler's inf check sees it through the classifier.bias probe, the update and the AdamW
+    # step count are skipped on the device, the scale backs off
+    before = {k: v.clone() for k, v in amp.state_dict().items()}
+    t_before = int(opt2._state()["step"])
+    with torch.autocast("cuda"):
+        loss = fwd(amp, batches[0]) * float("inf")
+    scaler.scale(loss).backward()
+    scaler.step(opt2)
+    scaler.update()
+    assert float(scaler.get_scale()) == 32768.0
+    assert int(opt2._state()["step"]) == t_before
+    after = amp.state_dict()
+    for k in before:
+        assert torch.equal(before[k], after[k]), k
+
+
 def test_state_dict_round_trip_and_hf_loadable(cuda_dev):
     cfg = tiny_config()
     state = state_from_hf_init(cfg)
