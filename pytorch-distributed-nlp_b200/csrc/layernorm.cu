@@ -136,6 +136,131 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(
 #undef B2_REDUCE_SET
 }
 
+// The training engine's LayerNorm backward (fp32 gradient stream in and out, mode 0), rows staged through shared
+// memory by the TMA engine.  The register version above keeps at most one row per warp in flight (72 accumulator
+// registers leave no room to prefetch), i.e. ~36 KB per SM, and ran at ~2.4 TB/s.  Here lane 0 of every warp queues
+// 1-D bulk copies of the next kStages rows (dy fp32 + x bf16 = 6 bytes per element) into that warp's private ring
+// and the warp consumes them behind an mbarrier, so bytes in flight no longer depend on registers.  Same per-lane
+// column ownership, arithmetic order and partial-sum layout as the register version (bitwise-identical results for
+// a given grid size).
+constexpr int kLnStages = 4;
+template <int VPL>
+__global__ void __launch_bounds__(256) layernorm_bwd_tma_kernel(
+    const float* __restrict__ dy, const __nv_bfloat16* __restrict__ x, const float* __restrict__ mean,
+    const float* __restrict__ rstd, const __nv_bfloat16* __restrict__ gamma, int rows, float dropout_p,
+    const unsigned long long* rng, unsigned rng_site, float* __restrict__ dx, __nv_bfloat16* __restrict__ dx_drop,
+    float* __restrict__ partials /* [gridDim.x][3][H] */) {
+  constexpr int H = VPL * 256;
+  constexpr int WARPS = 8;
+  constexpr int kRowBytes = H * 6;   // fp32 dy row followed by the bf16 x row
+  extern __shared__ __align__(128) uint8_t ln_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint8_t* ring = ln_smem + (size_t)warp * kLnStages * kRowBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ln_smem + (size_t)WARPS * kLnStages * kRowBytes) + warp * kLnStages;
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < kLnStages; ++s) mbar_init(&bars[s], 1);
+    fence_mbar_init();
+  }
+  __syncwarp();
+  pdl_wait();               // PDL: predecessors complete + visible before any global access
+  pdl_launch_dependents();  // let the next kernel in the stream begin launching
+  const DropCtx drop = make_drop_ctx(rng, rng_site, dropout_p);
+  const int row0 = blockIdx.x * WARPS + warp, row_step = gridDim.x * WARPS;
+  const int my_rows = row0 < rows ? (rows - row0 + row_step - 1) / row_step : 0;
+
+  auto issue = [&](int k) {   // lane 0 only
+    const int row = row0 + k * row_step;
+    uint8_t* dst = ring + (size_t)(k % kLnStages) * kRowBytes;
+    uint64_t* bar = &bars[k % kLnStages];
+    mbar_expect_tx(bar, kRowBytes);
+    bulk_load_1d(dst, dy + (size_t)row * H, H * 4, bar);
+    bulk_load_1d(dst + H * 4, x + (size_t)row * H, H * 2, bar);
+  };
+  if (lane == 0)
+    for (int k = 0; k < kLnStages && k < my_rows; ++k) issue(k);
+
+  float g[VPL * 8];
+  load_row<VPL>(gamma, lane, g);
+  float acc_g[VPL * 8], acc_b[VPL * 8], acc_d[VPL * 8];
+#pragma unroll
+  for (int i = 0; i < VPL * 8; ++i) acc_g[i] = acc_b[i] = acc_d[i] = 0.f;
+
+  for (int k = 0; k < my_rows; ++k) {
+    const int row = row0 + k * row_step;
+    const float mu = mean[row], rs = rstd[row];
+    const uint8_t* src = ring + (size_t)(k % kLnStages) * kRowBytes;
+    mbar_wait(&bars[k % kLnStages], (uint32_t)((k / kLnStages) & 1));
+    float dyv[VPL * 8], xv[VPL * 8];
+#pragma unroll
+    for (int vv = 0; vv < VPL; ++vv) {
+      const float4 a = *reinterpret_cast<const float4*>(src + ((vv * 32 + lane) * 8) * 4);
+      const float4 b = *reinterpret_cast<const float4*>(src + ((vv * 32 + lane) * 8 + 4) * 4);
+      dyv[vv * 8 + 0] = a.x; dyv[vv * 8 + 1] = a.y; dyv[vv * 8 + 2] = a.z; dyv[vv * 8 + 3] = a.w;
+      dyv[vv * 8 + 4] = b.x; dyv[vv * 8 + 5] = b.y; dyv[vv * 8 + 6] = b.z; dyv[vv * 8 + 7] = b.w;
+      const uint4 t = *reinterpret_cast<const uint4*>(src + H * 4 + ((vv * 32 + lane) * 8) * 2);
+      xv[vv * 8 + 0] = bf16_lo(t.x); xv[vv * 8 + 1] = bf16_hi(t.x); xv[vv * 8 + 2] = bf16_lo(t.y);
+      xv[vv * 8 + 3] = bf16_hi(t.y); xv[vv * 8 + 4] = bf16_lo(t.z); xv[vv * 8 + 5] = bf16_hi(t.z);
+      xv[vv * 8 + 6] = bf16_lo(t.w); xv[vv * 8 + 7] = bf16_hi(t.w);
+    }
+    __syncwarp();   // every lane has drained this stage: lane 0 may hand it back to the copy engine
+    if (lane == 0 && k + kLnStages < my_rows) {
+      fence_proxy_async_smem();   // order the generic-proxy reads above before the async-proxy overwrite
+      issue(k + kLnStages);
+    }
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL * 8; ++i) {
+      xv[i] = (xv[i] - mu) * rs;               // xhat
+      const float dxh = dyv[i] * g[i];
+      s1 += dxh;
+      s2 += dxh * xv[i];
+      acc_g[i] += dyv[i] * xv[i];
+      acc_b[i] += dyv[i];
+    }
+    s1 = warp_sum(s1) * (1.0f / H);
+    s2 = warp_sum(s2) * (1.0f / H);
+    float dxv[VPL * 8];
+#pragma unroll
+    for (int i = 0; i < VPL * 8; ++i) dxv[i] = rs * (dyv[i] * g[i] - s1 - xv[i] * s2);
+    store_row_f32<VPL>(dx + (size_t)row * H, lane, dxv);
+#pragma unroll
+    for (int vv = 0; vv < VPL; ++vv) {
+      const uint32_t keep = dropout_keep8(drop, (unsigned long long)row * H + (vv * 32 + lane) * 8);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        // the GEMMs consume the bf16-rounded value; sum exactly what they see
+        const float t = ((keep >> i) & 1u) ? dxv[vv * 8 + i] * drop.scale : 0.f;
+        dxv[vv * 8 + i] = bf16_round(t);
+      }
+    }
+    store_row<VPL>(dx_drop + (size_t)row * H, lane, dxv);
+#pragma unroll
+    for (int i = 0; i < VPL * 8; ++i) acc_d[i] += dxv[i];
+  }
+
+  // block reduction of the three column-sum sets; the ring is idle (every queued row was consumed) and is reused
+  __syncthreads();
+  float (*red)[H] = reinterpret_cast<float (*)[H]>(ln_smem);
+  float* out = partials + (size_t)blockIdx.x * 3 * H;
+#define B2_REDUCE_SET(ARR, WHICH)                                                          \
+  {                                                                                        \
+    _Pragma("unroll") for (int vv = 0; vv < VPL; ++vv)                                     \
+        _Pragma("unroll") for (int i = 0; i < 8; ++i) red[warp][(vv * 32 + lane) * 8 + i] = ARR[vv * 8 + i]; \
+    __syncthreads();                                                                       \
+    for (int c = threadIdx.x; c < H; c += blockDim.x) {                                    \
+      float s = 0.f;                                                                       \
+      _Pragma("unroll") for (int w = 0; w < WARPS; ++w) s += red[w][c];                    \
+      out[(WHICH)*H + c] = s;                                                              \
+    }                                                                                      \
+    __syncthreads();                                                                       \
+  }
+  B2_REDUCE_SET(acc_g, 0)
+  B2_REDUCE_SET(acc_b, 1)
+  B2_REDUCE_SET(acc_d, 2)
+#undef B2_REDUCE_SET
+}
+
 // partials [nparts][nsets][cols] fp32 -> up to three bf16 [cols] outputs.  Block = 32 columns x 8 part-lanes so the
 // reduction over `nparts` is itself parallel (a serial per-column loop cost 60 us per call in the first profile).
 __global__ void __launch_bounds__(256) colsum_finish_kernel(const float* __restrict__ partials, int nparts, int nsets,
@@ -220,6 +345,26 @@ int32_t launch_colsum(const void* x, int64_t rows, int64_t cols, int64_t ldx, co
   return 0;
 }
 
+static int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+// B2_LN_BWD_STAGED=0 falls back to the register-only kernel (A/B measurements)
+static bool ln_bwd_staged() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("B2_LN_BWD_STAGED");
+    v = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
 int32_t launch_layernorm_bwd(const void* dy, const void* dy_add, const void* x, const float* mean, const float* rstd,
                              const void* gamma, int64_t rows, int64_t hidden, float dropout_p, const void* rng,
                              uint32_t site, int mode, int dy_f32, int dx_f32, void* dx, void* dx_drop, void* d_gamma,
@@ -243,8 +388,31 @@ int32_t launch_layernorm_bwd(const void* dy, const void* dy_add, const void* x, 
     else B2_LAUNCH((layernorm_bwd_kernel<VPL_, false, false>), nblocks, 256, 0, stream, B2_LN_ARGS);                  \
     break;
   B2_REQUIRE(dy_f32 || !dx_f32, "layernorm_bwd: fp32 dx with bf16 dy is not on the path");
-  switch ((int)(hidden / 256)) {
-    B2_LN_BWD(1) B2_LN_BWD(2) B2_LN_BWD(3) B2_LN_BWD(4)
+  const bool staged = dy_f32 && dx_f32 && mode == 0 && dy_add == nullptr && dx_drop != nullptr && ln_bwd_staged();
+  if (staged) {
+    // one resident block per SM (register-bound): a single wave, rows strided over the whole grid
+    if (nblocks > num_sms()) nblocks = num_sms();
+#define B2_LN_BWD_TMA(VPL_)                                                                                     \
+  case VPL_: {                                                                                                  \
+    constexpr int smem = 8 * kLnStages * (VPL_ * 256 * 6) + 8 * kLnStages * 8;                                  \
+    static bool attr = false;                                                                                   \
+    if (!attr) {                                                                                                \
+      B2_CUDA(cudaFuncSetAttribute(layernorm_bwd_tma_kernel<VPL_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                   smem));                                                                      \
+      attr = true;                                                                                              \
+    }                                                                                                           \
+    B2_LAUNCH((layernorm_bwd_tma_kernel<VPL_>), nblocks, 256, smem, stream, (const float*)dy,                   \
+              (const __nv_bfloat16*)x, mean, rstd, (const __nv_bfloat16*)gamma, (int)rows, dropout_p,           \
+              (const unsigned long long*)rng, site, (float*)dx, (__nv_bfloat16*)dx_drop, scratch);              \
+  } break;
+    switch ((int)(hidden / 256)) {
+      B2_LN_BWD_TMA(1) B2_LN_BWD_TMA(2) B2_LN_BWD_TMA(3) B2_LN_BWD_TMA(4)
+    }
+#undef B2_LN_BWD_TMA
+  } else {
+    switch ((int)(hidden / 256)) {
+      B2_LN_BWD(1) B2_LN_BWD(2) B2_LN_BWD(3) B2_LN_BWD(4)
+    }
   }
 #undef B2_LN_BWD
 #undef B2_LN_ARGS

@@ -34,6 +34,7 @@ class Args:
     device_ids = None
     rank = None
     dev = False
+    use_amp = False       # the -amp scripts' flag (multi-gpu-distributed-mp-amp-cls.py:160): GradScaler loop on the eager path
     fused = True          # capture fwd + bwd + exchange + AdamW in one CUDA graph
     log_every = 1         # the reference prints every step (forces a D2H sync per step)
     total_step = 0
@@ -187,6 +188,7 @@ class Trainer:
         self.criterion = criterion
         self.optimizer = optimizer
         self._fused = None
+        self._scaler = None
         self._fused_eval = {}
         self._pin = {}
 
@@ -249,6 +251,17 @@ class Trainer:
                 self._fused = FusedTrainStep(self.model, self.optimizer, B, S)
             self.model.train()
             loss = self._fused(batch_data)
+        elif getattr(self.args, "use_amp", False):
+            # the -amp scripts' loop body (multi-gpu-distributed-mp-amp-cls.py:166-171), scaler created once
+            if self._scaler is None:
+                self._scaler = torch.amp.GradScaler("cuda")
+            self.model.train()
+            with torch.autocast("cuda"):
+                logits, label = self.on_step(batch_data)
+                loss = self.criterion(logits, label)
+            self._scaler.scale(loss).backward()
+            self._scaler.step(self.optimizer)
+            self._scaler.update()
         else:
             self.model.train()
             logits, label = self.on_step(batch_data)
@@ -256,7 +269,7 @@ class Trainer:
             self.optimizer.zero_grad()
             loss.backward()
             self.optimizer.step()
-        return self.loss_reduce(loss)
+        return self.loss_reduce(loss.detach())
 
     def train(self, train_loader, dev_loader=None, train_sampler=None):
         gloabl_step = 1
