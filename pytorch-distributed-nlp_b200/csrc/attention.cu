@@ -162,7 +162,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_fwd_kernel(const __grid
       float pr[32];
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
-        pr[i] = exp2f(__uint_as_float(v[i]) * c2 + s_bias[j * 128 + half * 64 + c * 32 + i] - m_new);
+        pr[i] = ex2_approx(__uint_as_float(v[i]) * c2 + s_bias[j * 128 + half * 64 + c * 32 + i] - m_new);
         l_blk += pr[i];
       }
 #pragma unroll
@@ -378,7 +378,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
           const int cc = g * 8 + e;
-          const float pr = exp2f(__uint_as_float(vs[cc]) * c2 + s_bias[cb + cc] - lse2);
+          const float pr = ex2_approx(__uint_as_float(vs[cc]) * c2 + s_bias[cb + cc] - lse2);
           const bool kp = (keep >> e) & 1u;
           pd[e] = kp ? pr * drop.scale : 0.f;
           const float dp = kp ? __uint_as_float(vd[cc]) * drop.scale : 0.f;
@@ -428,19 +428,19 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_
       tmem_ld_wait();
       if (p.dq_accum == nullptr) {
         __nv_bfloat16* dst = p.d_qkv + (size_t)(row0 + q_row) * (3 * p.hidden) + col_q + half * 32;
+        float f[32];   // the bf16-rounded values (what the dgrad/wgrad GEMMs will read), for the bias-gradient sums
+#pragma unroll
+        for (int e = 0; e < 32; ++e) f[e] = __uint_as_float(v[e]);
 #pragma unroll
         for (int e = 0; e < 32; e += 8) {
           uint4 o;
-          o.x = pack_bf16(__uint_as_float(v[e]), __uint_as_float(v[e + 1]));
-          o.y = pack_bf16(__uint_as_float(v[e + 2]), __uint_as_float(v[e + 3]));
-          o.z = pack_bf16(__uint_as_float(v[e + 4]), __uint_as_float(v[e + 5]));
-          o.w = pack_bf16(__uint_as_float(v[e + 6]), __uint_as_float(v[e + 7]));
+          o.x = pack_bf16_round(f[e], f[e + 1]);
+          o.y = pack_bf16_round(f[e + 2], f[e + 3]);
+          o.z = pack_bf16_round(f[e + 4], f[e + 5]);
+          o.w = pack_bf16_round(f[e + 6], f[e + 7]);
           stg16(dst + e, o);
         }
         if (p.dbias != nullptr) {
-          float f[32];
-#pragma unroll
-          for (int e = 0; e < 32; ++e) f[e] = bf16_round(__uint_as_float(v[e]));
           const float t = warp_colsum32(f, lane);
           atomicAdd(p.dbias + col_q + half * 32 + lane, t);
         }
@@ -464,27 +464,27 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_
     tmem_ld32(tm_dk + lane_base + half * 32, v);
     tmem_ld32(tm_dv + lane_base + half * 32, w);
     tmem_ld_wait();
+    float f[32], g[32];   // bf16-rounded dK / dV values for the bias-gradient sums
+#pragma unroll
+    for (int e = 0; e < 32; ++e) {
+      f[e] = __uint_as_float(v[e]);
+      g[e] = __uint_as_float(w[e]);
+    }
 #pragma unroll
     for (int e = 0; e < 32; e += 8) {
       uint4 o;
-      o.x = pack_bf16(__uint_as_float(v[e]), __uint_as_float(v[e + 1]));
-      o.y = pack_bf16(__uint_as_float(v[e + 2]), __uint_as_float(v[e + 3]));
-      o.z = pack_bf16(__uint_as_float(v[e + 4]), __uint_as_float(v[e + 5]));
-      o.w = pack_bf16(__uint_as_float(v[e + 6]), __uint_as_float(v[e + 7]));
+      o.x = pack_bf16_round(f[e], f[e + 1]);
+      o.y = pack_bf16_round(f[e + 2], f[e + 3]);
+      o.z = pack_bf16_round(f[e + 4], f[e + 5]);
+      o.w = pack_bf16_round(f[e + 6], f[e + 7]);
       stg16(dk + e, o);
-      o.x = pack_bf16(__uint_as_float(w[e]), __uint_as_float(w[e + 1]));
-      o.y = pack_bf16(__uint_as_float(w[e + 2]), __uint_as_float(w[e + 3]));
-      o.z = pack_bf16(__uint_as_float(w[e + 4]), __uint_as_float(w[e + 5]));
-      o.w = pack_bf16(__uint_as_float(w[e + 6]), __uint_as_float(w[e + 7]));
+      o.x = pack_bf16_round(g[e], g[e + 1]);
+      o.y = pack_bf16_round(g[e + 2], g[e + 3]);
+      o.z = pack_bf16_round(g[e + 4], g[e + 5]);
+      o.w = pack_bf16_round(g[e + 6], g[e + 7]);
       stg16(dv + e, o);
     }
     if (p.dbias != nullptr) {
-      float f[32], g[32];
-#pragma unroll
-      for (int e = 0; e < 32; ++e) {
-        f[e] = bf16_round(__uint_as_float(v[e]));
-        g[e] = bf16_round(__uint_as_float(w[e]));
-      }
       const float tk = warp_colsum32(f, lane), tv = warp_colsum32(g, lane);
       atomicAdd(p.dbias + col_k + half * 32 + lane, tk);
       atomicAdd(p.dbias + col_v + half * 32 + lane, tv);

@@ -93,30 +93,46 @@ __device__ __forceinline__ float bf16_round(float x) {
 
 // erf-based GELU (transformers' "gelu", activations.py:85-89) and its derivative for the backward epilogue.
 // erf via Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7, far below bf16 resolution): one rcp.approx + one ex2.approx
-// + 6 FMA (~12 SASS instructions vs ~25 for libdevice erff; the GELU epilogues are issue-bound).  The same
-// exp(-x^2/2) serves erf(x/sqrt2) and the normal pdf of the derivative.
-__device__ __forceinline__ void gelu_terms(float x, float& cdf, float& pdf) {
-  const float ax = fabsf(x) * 0.70710678118654752f;              // z = |x| / sqrt(2)
-  float e, t;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-0.72134752044448170f * x * x));   // exp(-x^2/2) = exp(-z^2)
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, ax, 1.0f)));
-  float poly = fmaf(1.061405429f, t, -1.453152027f);
-  poly = fmaf(poly, t, 1.421413741f);
-  poly = fmaf(poly, t, -0.284496736f);
-  poly = fmaf(poly, t, 0.254829592f);
-  const float hq = 0.5f * poly * t * e;                          // (1 - erf(z)) / 2, z >= 0
-  cdf = x >= 0.f ? 1.0f - hq : hq;
-  pdf = 0.3989422804014327f * e;
+// + 5 FMA.  The GELU epilogues are instruction-bound (ncu: ~22 SASS instructions per element before this form), so
+// every constant is folded: hq = (1 - erf(|x|/sqrt2)) / 2 = poly_half(t) * t * exp(-x^2/2), t = 1/(1 + p|x|/sqrt2),
+// with the 1/2 folded into the polynomial coefficients, and
+//   gelu(x)  = max(x, 0) - |x| * hq                      (x >= 0: x(1-hq);  x < 0: x*hq)
+//   gelu'(x) = cdf + x * pdf,  cdf = x >= 0 ? 1 - hq : hq,  pdf = exp(-x^2/2) / sqrt(2 pi)
+// The same exp(-x^2/2) serves erf and the normal pdf of the derivative.
+__device__ __forceinline__ void gelu_hq(float x, float& hq, float& e) {
+  float t;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"((x * x) * -0.72134752044448170f));      // exp(-x^2/2)
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(fabsf(x), 0.23164189f, 1.0f)));     // p/sqrt2 = 0.3275911/1.41421356
+  float poly = fmaf(0.5307027145f, t, -0.7265760135f);   // A&S 7.1.26 coefficients a5..a1, halved
+  poly = fmaf(poly, t, 0.7107068705f);
+  poly = fmaf(poly, t, -0.142248368f);
+  poly = fmaf(poly, t, 0.127414796f);
+  hq = (poly * t) * e;
 }
 __device__ __forceinline__ float gelu_erf(float x) {
-  float cdf, pdf;
-  gelu_terms(x, cdf, pdf);
-  return x * cdf;
+  float hq, e;
+  gelu_hq(x, hq, e);
+  return fmaf(-fabsf(x), hq, fmaxf(x, 0.f));
 }
 __device__ __forceinline__ float gelu_erf_grad(float x) {
-  float cdf, pdf;
-  gelu_terms(x, cdf, pdf);
-  return fmaf(x, pdf, cdf);
+  float hq, e;
+  gelu_hq(x, hq, e);
+  const float cdf = x >= 0.f ? 1.0f - hq : hq;
+  return fmaf(x * 0.3989422804014327f, e, cdf);
+}
+// 2^x on the SFU without exp2f's denormal-range fix-up (arguments here are <= 0 or already flushed; the masked-key
+// bias -3.4e38 gives exactly 0)
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// round two fp32 values to bf16 (one F2FP) and hand back both the packed pair and the rounded values as fp32
+__device__ __forceinline__ uint32_t pack_bf16_round(float& lo, float& hi) {
+  const uint32_t u = pack_bf16(lo, hi);
+  lo = bf16_lo(u);
+  hi = bf16_hi(u);
+  return u;
 }
 
 // ----------------------------------------------------------------------------------------------

@@ -99,6 +99,16 @@ __device__ __forceinline__ void row_write_bf16(uint8_t* stage, int lane, const f
     *stage_ptr(stage, lane, c) = o;
   }
 }
+// same, and f[] comes back holding the bf16-rounded values (what a consumer of the stored tensor will read)
+__device__ __forceinline__ void row_write_bf16_round(uint8_t* stage, int lane, float (&f)[64]) {
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    uint4 o;
+    o.x = pack_bf16_round(f[8 * c + 0], f[8 * c + 1]); o.y = pack_bf16_round(f[8 * c + 2], f[8 * c + 3]);
+    o.z = pack_bf16_round(f[8 * c + 4], f[8 * c + 5]); o.w = pack_bf16_round(f[8 * c + 6], f[8 * c + 7]);
+    *stage_ptr(stage, lane, c) = o;
+  }
+}
 __device__ __forceinline__ void row_read_bf16(uint8_t* stage, int lane, float (&r)[64]) {
 #pragma unroll
   for (int c = 0; c < 8; ++c) {
@@ -215,13 +225,13 @@ __device__ __forceinline__ void epilogue_tile(const GemmKernelParams& p, const D
       }
       if (p.epilogue == B2_EPI_BIAS_GELU) {
         // keep the pre-activation (bf16) for the backward pass, emit gelu(pre-activation)
-        row_write_bf16(stage, lane, f);
+        row_write_bf16_round(stage, lane, f);
         __syncwarp();
         tile_s2g(stage, reinterpret_cast<uint8_t*>(p.aux_out + (size_t)row0 * p.ld_aux_out + n), p.ld_aux_out * 2, lane,
                  rows_valid);
         __syncwarp();
 #pragma unroll
-        for (int j = 0; j < 64; ++j) f[j] = gelu_erf(bf16_round(f[j]));
+        for (int j = 0; j < 64; ++j) f[j] = gelu_erf(f[j]);
       } else if (has_aux) {
         if (g > 0) prefetch(g);   // group 0 was requested before the accumulator wait
         tile_async_wait();

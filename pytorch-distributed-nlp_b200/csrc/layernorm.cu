@@ -228,13 +228,13 @@ __global__ void __launch_bounds__(256) layernorm_bwd_tma_kernel(
     for (int vv = 0; vv < VPL; ++vv) {
       const uint32_t keep = dropout_keep8(drop, (unsigned long long)row * H + (vv * 32 + lane) * 8);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        // the GEMMs consume the bf16-rounded value; sum exactly what they see
-        const float t = ((keep >> i) & 1u) ? dxv[vv * 8 + i] * drop.scale : 0.f;
-        dxv[vv * 8 + i] = bf16_round(t);
-      }
+      for (int i = 0; i < 8; ++i) dxv[vv * 8 + i] = ((keep >> i) & 1u) ? dxv[vv * 8 + i] * drop.scale : 0.f;
+      // the GEMMs consume the bf16-rounded value: round once while packing, sum exactly what they will read
+      uint4 o;
+      o.x = pack_bf16_round(dxv[vv * 8 + 0], dxv[vv * 8 + 1]); o.y = pack_bf16_round(dxv[vv * 8 + 2], dxv[vv * 8 + 3]);
+      o.z = pack_bf16_round(dxv[vv * 8 + 4], dxv[vv * 8 + 5]); o.w = pack_bf16_round(dxv[vv * 8 + 6], dxv[vv * 8 + 7]);
+      stg16(dx_drop + (size_t)row * H + (vv * 32 + lane) * 8, o);
     }
-    store_row<VPL>(dx_drop + (size_t)row * H, lane, dxv);
 #pragma unroll
     for (int i = 0; i < VPL * 8; ++i) acc_d[i] += dxv[i];
   }
