@@ -147,14 +147,15 @@ def time_gemm_family(eng, cfg, B, S, peaks):
         ("fwd ffn1     [M,I]<-[M,H]x[I,H]^T", M, I, H, KM, KM, L.EPI_BIAS_GELU),
         ("fwd ffn2     [M,H]<-[M,I]x[H,I]^T", M, H, I, KM, KM, L.EPI_BIAS_DROPOUT_RESIDUAL),
         ("dgrad ffn2   [M,I]<-[M,H]x[H,I]", M, I, H, KM, MN, L.EPI_GELU_BWD),
-        ("dgrad ffn1   [M,H]<-[M,I]x[I,H] +fp32 res", M, H, I, KM, MN, L.EPI_RESIDUAL_F32),
+        ("dgrad ffn1   [M,H](fp32)+=[M,I]x[I,H] split-K in place", M, H, I, KM, MN, L.EPI_ACCUM_F32),
         ("dgrad attn-o [M,H]<-[M,H]x[H,H]", M, H, H, KM, MN, L.EPI_NONE),
-        ("dgrad qkv    [M,H]<-[M,3H]x[3H,H] +fp32 res", M, H, 3 * H, KM, MN, L.EPI_RESIDUAL_F32),
+        ("dgrad qkv    [M,H](fp32)+=[M,3H]x[3H,H] split-K in place", M, H, 3 * H, KM, MN, L.EPI_ACCUM_F32),
         ("wgrad ffn2   [H,I]<-[M,H]^Tx[M,I]", H, I, M, MN, MN, L.EPI_NONE),
         ("wgrad ffn1   [I,H]<-[M,I]^Tx[M,H]", I, H, M, MN, MN, L.EPI_NONE),
         ("wgrad attn-o [H,H]<-[M,H]^Tx[M,H]", H, H, M, MN, MN, L.EPI_NONE),
         ("wgrad qkv    [3H,H]<-[M,3H]^Tx[M,H]", 3 * H, H, M, MN, MN, L.EPI_NONE),
     ]
+    F32_OUT = (L.EPI_RESIDUAL_F32, L.EPI_ACCUM_F32)
     detail, tot_flops, tot_ms = [], 0.0, 0.0
     stream = torch.cuda.current_stream(dev)
     for (name, m, n, k, am, bm, epi) in shapes:
@@ -163,8 +164,8 @@ def time_gemm_family(eng, cfg, B, S, peaks):
         sets = []
         for _ in range(NSET):
             sets.append(dict(A=torch.randn(a_shape, device=dev).to(bf), B=(torch.randn(b_shape, device=dev) * 0.05).to(bf),
-                             D=torch.empty(m, n, dtype=(torch.float32 if epi == L.EPI_RESIDUAL_F32 else bf), device=dev),
-                             X=(torch.randn(m, n, device=dev) if epi == L.EPI_RESIDUAL_F32
+                             D=torch.zeros(m, n, dtype=(torch.float32 if epi in F32_OUT else bf), device=dev),
+                             X=(torch.randn(m, n, device=dev) if epi in F32_OUT
                                 else torch.randn(m, n, device=dev).to(bf)),
                              U=torch.empty(m, n, dtype=bf, device=dev), bias=torch.randn(n, device=dev).to(bf)))
 

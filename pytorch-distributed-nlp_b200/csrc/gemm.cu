@@ -30,33 +30,34 @@ namespace b2 {
 constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int UMMA_K = 16;
-constexpr int NUM_EPI_WARPS = 8;
-constexpr int GEMM_THREADS = (4 + NUM_EPI_WARPS) * 32;
+// warps 0-3: TMA producer, MMA issuer, TMEM allocator, spare; warps 4.. : EW epilogue warps (8 or 16, see
+// gemm_epilogue.cuh).  16 is the default; B2_GEMM_EPI_WARPS=8 selects the 12-warp variant (A/B measurements).
+constexpr int gemm_threads(int EW) { return (4 + EW) * 32; }
 
 // ------------------------------------------------------------------------------------------------------------
 // single-CTA kernel
 // ------------------------------------------------------------------------------------------------------------
-template <int BN>
+template <int BN, int EW>
 struct GemmCfg {
-  static constexpr int kStages = (BN == 256) ? 4 : 5;
+  static constexpr int kStages = (BN == 256) ? (EW == 16 ? 3 : 4) : 5;
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kAccStride = (BN <= 128) ? 128 : 256;  // TMEM columns between the 2 accumulators
   static constexpr int kTmemCols = 2 * kAccStride;            // 256 or 512 (power of two)
   static constexpr int kPipeBytes = kStages * kStageBytes;
-  static constexpr int kSmemBytes = kPipeBytes + NUM_EPI_WARPS * kEpiStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int kSmemBytes = kPipeBytes + EW * kEpiStageBytes + 1024 /*align*/ + 256 /*barriers*/;
 };
 
-template <int BN, bool A_MN, bool B_MN>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+template <int BN, bool A_MN, bool B_MN, int EW>
+__global__ void __launch_bounds__(gemm_threads(EW), 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const GemmKernelParams p) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, EW>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* epi_stage = smem + Cfg::kPipeBytes;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_stage + NUM_EPI_WARPS * kEpiStageBytes);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_stage + EW * kEpiStageBytes);
   uint64_t* empty_bar = full_bar + Cfg::kStages;
   uint64_t* tmem_full = empty_bar + Cfg::kStages;
   uint64_t* tmem_empty = tmem_full + 2;
@@ -76,7 +77,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
-      mbar_init(&tmem_empty[s], NUM_EPI_WARPS);
+      mbar_init(&tmem_empty[s], EW);
     }
     fence_mbar_init();
   }
@@ -166,7 +167,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
       const int tile = w / p.splits, split = w % p.splits;
       const int m0 = (tile / p.tiles_n) * BM, n0 = (tile % p.tiles_n) * BN;
-      epilogue_tile<BN>(p, drop, tmem_base + acc * Cfg::kAccStride, warp, lane, m0, n0, split,
+      epilogue_tile<BN, EW>(p, drop, tmem_base + acc * Cfg::kAccStride, warp, lane, m0, n0, split,
                         epi_stage + (warp - 4) * kEpiStageBytes, &tmem_full[acc], acc_phase);
       tc_fence_before();
       __syncwarp();
@@ -245,27 +246,27 @@ __device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
       : "memory");
 }
 
-template <int BN>
+template <int BN, int EW>
 struct Gemm2Cfg {
   static constexpr int kABytes = BM * BK * 2;            // this CTA's 128 A rows
   static constexpr int kBBytes = (BN / 2) * BK * 2;      // this CTA's half of the B tile
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (BN == 256) ? 5 : 7;
+  static constexpr int kStages = (BN == 256) ? 5 : (EW == 16 ? 6 : 7);
   static constexpr int kAccStride = (BN <= 128) ? 128 : 256;
   static constexpr int kTmemCols = 2 * kAccStride;
   static constexpr int kPipeBytes = kStages * kStageBytes;
-  static constexpr int kSmemBytes = kPipeBytes + NUM_EPI_WARPS * kEpiStageBytes + 1024 + 256;
+  static constexpr int kSmemBytes = kPipeBytes + EW * kEpiStageBytes + 1024 + 256;
 };
 
-template <int BN, bool A_MN, bool B_MN>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+template <int BN, bool A_MN, bool B_MN, int EW>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(gemm_threads(EW), 1)
 gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                   const GemmKernelParams p) {
-  using Cfg = Gemm2Cfg<BN>;
+  using Cfg = Gemm2Cfg<BN, EW>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* epi_stage = smem + Cfg::kPipeBytes;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_stage + NUM_EPI_WARPS * kEpiStageBytes);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_stage + EW * kEpiStageBytes);
   uint64_t* empty_bar = full_bar + Cfg::kStages;
   uint64_t* tmem_full = empty_bar + Cfg::kStages;
   uint64_t* tmem_empty = tmem_full + 2;
@@ -289,7 +290,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
-      mbar_init(&tmem_empty[s], 2 * NUM_EPI_WARPS);
+      mbar_init(&tmem_empty[s], 2 * EW);
     }
     fence_mbar_init();
   }
@@ -385,7 +386,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       const int tile = w / p.splits, split = w % p.splits;
       const int m0 = (tile / p.tiles_n) * (2 * BM) + (int)rank * BM;
       const int n0 = (tile % p.tiles_n) * BN;
-      epilogue_tile<BN>(p, drop, tmem_base + acc * Cfg::kAccStride, warp, lane, m0, n0, split,
+      epilogue_tile<BN, EW>(p, drop, tmem_base + acc * Cfg::kAccStride, warp, lane, m0, n0, split,
                         epi_stage + (warp - 4) * kEpiStageBytes, &tmem_full[acc], acc_phase);
       tc_fence_before();
       __syncwarp();
@@ -467,9 +468,9 @@ static int32_t launch_splitk_reduce(const b2_gemm_args_t& a, int splits, cudaStr
   return 0;
 }
 
-template <int BN, bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN, int EW>
 static int32_t launch_gemm(const b2_gemm_args_t& a, int splits, cudaStream_t stream) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, EW>;
   CUtensorMap ta, tb;
   int32_t st;
   if (!A_MN) st = get_tensor_map_2d(&ta, a.A, (uint64_t)a.M, (uint64_t)a.K, (uint64_t)a.lda * 2, BM, 64);
@@ -480,7 +481,7 @@ static int32_t launch_gemm(const b2_gemm_args_t& a, int splits, cudaStream_t str
   if (st) return st;
   GemmKernelParams p;
   fill_params(p, a, BM, BN, splits);
-  auto kern = gemm_bf16_kernel<BN, A_MN, B_MN>;
+  auto kern = gemm_bf16_kernel<BN, A_MN, B_MN, EW>;
   static bool attr_set = false;
   if (!attr_set) {
     B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
@@ -488,16 +489,16 @@ static int32_t launch_gemm(const b2_gemm_args_t& a, int splits, cudaStream_t str
   }
   const int work = p.tiles_m * p.tiles_n * p.splits;
   const int grid = work < num_sms() ? work : num_sms();
-  B2_LAUNCH(kern, grid, GEMM_THREADS, Cfg::kSmemBytes, stream, ta, tb, p);
+  B2_LAUNCH(kern, grid, gemm_threads(EW), Cfg::kSmemBytes, stream, ta, tb, p);
   B2_CUDA(cudaGetLastError());
   count_launches(1);
   if (splits > 1 && a.epilogue != B2_EPI_ACCUM_F32) return launch_splitk_reduce(a, splits, stream);
   return 0;
 }
 
-template <int BN, bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN, int EW>
 static int32_t launch_gemm2(const b2_gemm_args_t& a, int splits, cudaStream_t stream) {
-  using Cfg = Gemm2Cfg<BN>;
+  using Cfg = Gemm2Cfg<BN, EW>;
   CUtensorMap ta, tb;
   int32_t st;
   if (!A_MN) st = get_tensor_map_2d(&ta, a.A, (uint64_t)a.M, (uint64_t)a.K, (uint64_t)a.lda * 2, BM, 64);
@@ -508,7 +509,7 @@ static int32_t launch_gemm2(const b2_gemm_args_t& a, int splits, cudaStream_t st
   if (st) return st;
   GemmKernelParams p;
   fill_params(p, a, 2 * BM, BN, splits);
-  auto kern = gemm2_bf16_kernel<BN, A_MN, B_MN>;
+  auto kern = gemm2_bf16_kernel<BN, A_MN, B_MN, EW>;
   static bool attr_set = false;
   if (!attr_set) {
     B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
@@ -517,7 +518,7 @@ static int32_t launch_gemm2(const b2_gemm_args_t& a, int splits, cudaStream_t st
   const int work = p.tiles_m * p.tiles_n * p.splits;
   const int max_pairs = num_sms() / 2;
   const int pairs = work < max_pairs ? work : max_pairs;
-  B2_LAUNCH(kern, 2 * pairs, GEMM_THREADS, Cfg::kSmemBytes, stream, ta, tb, p);
+  B2_LAUNCH(kern, 2 * pairs, gemm_threads(EW), Cfg::kSmemBytes, stream, ta, tb, p);
   B2_CUDA(cudaGetLastError());
   count_launches(1);
   if (splits > 1 && a.epilogue != B2_EPI_ACCUM_F32) return launch_splitk_reduce(a, splits, stream);
@@ -617,18 +618,27 @@ extern "C" int32_t b2_gemm_bf16(const b2_gemm_args_t* a, void* stream_) {
   const bool a_mn = a->a_major == B2_MAJOR_MN, b_mn = a->b_major == B2_MAJOR_MN;
   B2_REQUIRE(!(a_mn && !b_mn), "b2_gemm_bf16: layout TT (A MN-major, B K-major) is not on the path");
 
-#define B2_DISPATCH(FN, BN_)                                                           \
-  if (c.bn == BN_) {                                                                   \
-    if (!a_mn && !b_mn) return FN<BN_, false, false>(*a, c.splits, stream);            \
-    if (!a_mn && b_mn) return FN<BN_, false, true>(*a, c.splits, stream);              \
-    return FN<BN_, true, true>(*a, c.splits, stream);                                  \
+  static int epi_warps = 0;
+  if (epi_warps == 0) {
+    const char* e = getenv("B2_GEMM_EPI_WARPS");
+    epi_warps = (e != nullptr && atoi(e) == 8) ? 8 : 16;
+  }
+#define B2_DISPATCH(FN, BN_, EW_)                                                      \
+  if (c.bn == BN_ && epi_warps == EW_) {                                               \
+    if (!a_mn && !b_mn) return FN<BN_, false, false, EW_>(*a, c.splits, stream);       \
+    if (!a_mn && b_mn) return FN<BN_, false, true, EW_>(*a, c.splits, stream);         \
+    return FN<BN_, true, true, EW_>(*a, c.splits, stream);                             \
   }
   if (c.pair) {
-    B2_DISPATCH(launch_gemm2, 128)
-    B2_DISPATCH(launch_gemm2, 256)
+    B2_DISPATCH(launch_gemm2, 128, 16)
+    B2_DISPATCH(launch_gemm2, 256, 16)
+    B2_DISPATCH(launch_gemm2, 128, 8)
+    B2_DISPATCH(launch_gemm2, 256, 8)
   } else {
-    B2_DISPATCH(launch_gemm, 128)
-    B2_DISPATCH(launch_gemm, 256)
+    B2_DISPATCH(launch_gemm, 128, 16)
+    B2_DISPATCH(launch_gemm, 256, 16)
+    B2_DISPATCH(launch_gemm, 128, 8)
+    B2_DISPATCH(launch_gemm, 256, 8)
   }
 #undef B2_DISPATCH
   set_error("b2_gemm_bf16: no kernel for pair=%d BN=%d", c.pair, c.bn);
