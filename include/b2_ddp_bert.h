@@ -28,7 +28,7 @@ extern "C" {
 /* ------------------------------------------------------------------------------------------------------ */
 const char* b2_last_error(void);
 int32_t b2_abi_version(void);             /* bumped when a struct below changes */
-#define B2_ABI_VERSION 8
+#define B2_ABI_VERSION 9
 int64_t b2_launch_count(void);            /* kernels launched by this library so far (process-wide) */
 
 /* ------------------------------------------------------------------------------------------------------ */
@@ -80,6 +80,12 @@ typedef struct b2_gemm_args {
 } b2_gemm_args_t;
 
 int32_t b2_gemm_bf16(const b2_gemm_args_t* args, void* stream);
+
+/* `count` independent problems behind one launch where they allow it (all TN = both operands MN-major, plain bf16
+ * output, N % 256 == 0, one K; at most 4): the four weight-gradient GEMMs of an encoder layer (autograd's
+ * addmm backward nodes for BertSelfAttention/BertSelfOutput/BertIntermediate/BertOutput, modeling_bert.py:179-356).
+ * Other mixes are issued one by one; results are identical either way.                                         */
+int32_t b2_gemm_bf16_grouped(const b2_gemm_args_t* args, int32_t count, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------ */
 /* memory-bound kernels                                                                                   */

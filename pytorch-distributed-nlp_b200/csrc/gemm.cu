@@ -409,6 +409,167 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Grouped CTA-pair kernel: up to kMaxGroup independent TN problems (D_i[M_i,N_i] = A_i^T B_i, both operands MN-major,
+// same contraction length) behind ONE launch.  This is the weight-gradient step of an encoder layer: its four
+// GEMMs are small (4.8-19 GFLOP), so launched one by one each pays the ~7 us fixed cost of a launch (setup, first
+// operands, drain, pair exit, gap) and -- with 9-54 tiles on 74 CTA pairs -- needs split-K partials plus a reduce
+// kernel to fill the machine.  Together they are 108 full-K 256x256 tiles: two waves of one persistent kernel, no
+// partials.  Roles and barriers are those of gemm2_bf16_kernel; only the work decode differs.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int kMaxGroup = 4;
+struct GroupedProblem {
+  int M, N, tiles_n, tile_begin;   // tile_begin: first global work index of this problem
+  __nv_bfloat16* D; long long ldd;
+};
+struct GroupedParams {
+  int count, num_work, kblocks;
+  GroupedProblem pr[kMaxGroup];
+};
+struct GroupedMaps {
+  CUtensorMap a[kMaxGroup], b[kMaxGroup];
+};
+__device__ __forceinline__ int grouped_find(const GroupedParams& gp, int w) {
+  int pi = 0;
+#pragma unroll
+  for (int i = 1; i < kMaxGroup; ++i)
+    if (i < gp.count && w >= gp.pr[i].tile_begin) pi = i;
+  return pi;
+}
+
+template <int EW>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(gemm_threads(EW), 1)
+gemm2_grouped_tn_kernel(const __grid_constant__ GroupedMaps maps, const GroupedParams gp) {
+  constexpr int BN = 256;
+  using Cfg = Gemm2Cfg<BN, EW>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* epi_stage = smem + Cfg::kPipeBytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_stage + EW * kEpiStageBytes);
+  uint64_t* empty_bar = full_bar + Cfg::kStages;
+  uint64_t* tmem_full = empty_bar + Cfg::kStages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < gp.count; ++i) {
+      tma_prefetch_desc(&maps.a[i]);
+      tma_prefetch_desc(&maps.b[i]);
+    }
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < Cfg::kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full[s], 1);
+      mbar_init(&tmem_empty[s], 2 * EW);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc_2sm(tmem_holder, Cfg::kTmemCols);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+  pdl_wait();
+  pdl_launch_dependents();
+
+  if (warp == 0) {
+    // ------------------------------ TMA producer (both CTAs) ------------------------------
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int w = pair; w < gp.num_work; w += npairs) {
+        const int pi = grouped_find(gp, w);
+        const int lt = w - gp.pr[pi].tile_begin;
+        const int m0 = (lt / gp.pr[pi].tiles_n) * (2 * BM) + (int)rank * BM;
+        const int n0 = (lt % gp.pr[pi].tiles_n) * BN + (int)rank * (BN / 2);
+        const CUtensorMap* ta = &maps.a[pi];
+        const CUtensorMap* tb = &maps.b[pi];
+        for (int kb = 0; kb < gp.kblocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (leader) mbar_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
+          const uint32_t bar = mapa_u32(smem_u32(&full_bar[stage]), 0);
+          uint8_t* sa = smem + stage * Cfg::kStageBytes;
+          uint8_t* sb = sa + Cfg::kABytes;
+          const int k0 = kb * BK;
+#pragma unroll
+          for (int j = 0; j < BM / 64; ++j) tma_load_2d_2sm(sa + j * (BK * 128), ta, bar, m0 + 64 * j, k0);
+#pragma unroll
+          for (int j = 0; j < BN / 128; ++j) tma_load_2d_2sm(sb + j * (BK * 128), tb, bar, n0 + 64 * j, k0);
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------ MMA issuer (leader CTA only) ------------------------------
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(2 * BM, BN, true, true);
+      constexpr uint32_t lbo = BK * 128, kstep = UMMA_K * 128;
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int w = pair; w < gp.num_work; w += npairs) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * Cfg::kAccStride;
+        for (int kb = 0; kb < gp.kblocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
+          const uint32_t sb = sa + Cfg::kABytes;
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k)
+            umma_bf16_2sm(d_tmem, make_smem_desc(sa + k * kstep, lbo, 1024), make_smem_desc(sb + k * kstep, lbo, 1024),
+                          idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          umma_commit_2sm(&empty_bar[stage]);
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit_2sm(&tmem_full[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------ epilogue (both CTAs, own 128 rows) ------------------------------
+    GemmKernelParams q;
+    q.splits = 1; q.epilogue = B2_EPI_NONE; q.bias = nullptr; q.aux_in = nullptr; q.aux_out = nullptr;
+    q.partial = nullptr; q.dropout_p = 0.f; q.rng = nullptr; q.rng_site = 0; q.timing = nullptr; q.colsum = nullptr;
+    q.ld_aux_in = 0; q.ld_aux_out = 0; q.K = 0; q.tiles_m = 0; q.kblocks_per_split = 0; q.kblocks_total = 0;
+    DropCtx drop;
+    drop.k0 = 0; drop.k1 = 0; drop.step = 0; drop.site = 0; drop.thresh = 0; drop.scale = 1.f;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int w = pair; w < gp.num_work; w += npairs) {
+      const int pi = grouped_find(gp, w);
+      const int lt = w - gp.pr[pi].tile_begin;
+      q.M = gp.pr[pi].M; q.N = gp.pr[pi].N; q.tiles_n = gp.pr[pi].tiles_n; q.D = gp.pr[pi].D; q.ldd = gp.pr[pi].ldd;
+      const int m0 = (lt / gp.pr[pi].tiles_n) * (2 * BM) + (int)rank * BM;
+      const int n0 = (lt % gp.pr[pi].tiles_n) * BN;
+      epilogue_tile<BN, EW>(q, drop, tmem_base + acc * Cfg::kAccStride, warp, lane, m0, n0, 0,
+                            epi_stage + (warp - 4) * kEpiStageBytes, &tmem_full[acc], acc_phase);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (leader) mbar_arrive(&tmem_empty[acc]);
+        else mbar_arrive_remote(mapa_u32(smem_u32(&tmem_empty[acc]), 0));
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, Cfg::kTmemCols);
+  }
+}
+
 // sums split-K partials [splits][M][N] fp32 -> bf16 D
 __global__ void splitk_reduce_kernel(const float* __restrict__ partial, __nv_bfloat16* __restrict__ D,
                                      long long ldd, int M, int N, int splits) {
@@ -643,4 +804,59 @@ extern "C" int32_t b2_gemm_bf16(const b2_gemm_args_t* a, void* stream_) {
 #undef B2_DISPATCH
   set_error("b2_gemm_bf16: no kernel for pair=%d BN=%d", c.pair, c.bn);
   return -2;
+}
+
+extern "C" int32_t b2_gemm_bf16_grouped(const b2_gemm_args_t* args, int32_t count, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  B2_REQUIRE(args != nullptr && count >= 1, "b2_gemm_bf16_grouped: no problems");
+  // the one-launch path covers what the weight-gradient step needs: TN layouts, plain bf16 output, 256-wide tiles,
+  // one contraction length; anything else is issued problem by problem (same results, more launches)
+  bool groupable = count <= kMaxGroup;
+  for (int i = 0; i < count && groupable; ++i) {
+    const b2_gemm_args_t& a = args[i];
+    groupable = a.a_major == B2_MAJOR_MN && a.b_major == B2_MAJOR_MN && a.epilogue == B2_EPI_NONE &&
+                a.bias == nullptr && a.colsum_out == nullptr && a.N % 256 == 0 && a.K == args[0].K && a.M > 0 &&
+                a.K > 0 && a.A && a.B && a.D && a.K % 8 == 0 && a.lda % 8 == 0 && a.ldb % 8 == 0 &&
+                a.ldd % 8 == 0 && ((uintptr_t)a.A % 16 == 0) && ((uintptr_t)a.B % 16 == 0) &&
+                ((uintptr_t)a.D % 16 == 0) && a.force_kernel != 1 && a.force_splits <= 1 &&
+                (a.force_bn == 0 || a.force_bn == 256);
+  }
+  if (!groupable) {
+    for (int i = 0; i < count; ++i) {
+      const int32_t st = b2_gemm_bf16(&args[i], stream_);
+      if (st) return st;
+    }
+    return 0;
+  }
+  GroupedMaps maps;
+  GroupedParams gp;
+  gp.count = count;
+  gp.kblocks = (int)((args[0].K + BK - 1) / BK);
+  int work = 0;
+  for (int i = 0; i < count; ++i) {
+    const b2_gemm_args_t& a = args[i];
+    int32_t st = get_tensor_map_2d(&maps.a[i], a.A, (uint64_t)a.K, (uint64_t)a.M, (uint64_t)a.lda * 2, BK, 64);
+    if (st) return st;
+    st = get_tensor_map_2d(&maps.b[i], a.B, (uint64_t)a.K, (uint64_t)a.N, (uint64_t)a.ldb * 2, BK, 64);
+    if (st) return st;
+    GroupedProblem& g = gp.pr[i];
+    g.M = (int)a.M; g.N = (int)a.N; g.tiles_n = (int)(a.N / 256); g.tile_begin = work;
+    g.D = (__nv_bfloat16*)a.D; g.ldd = a.ldd;
+    work += (int)((a.M + 2 * BM - 1) / (2 * BM)) * g.tiles_n;
+  }
+  for (int i = count; i < kMaxGroup; ++i) { gp.pr[i] = gp.pr[0]; gp.pr[i].tile_begin = 0x7fffffff; maps.a[i] = maps.a[0]; maps.b[i] = maps.b[0]; }
+  gp.num_work = work;
+  using Cfg = Gemm2Cfg<256, 16>;
+  auto kern = gemm2_grouped_tn_kernel<16>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  const int max_pairs = num_sms() / 2;
+  const int pairs = work < max_pairs ? work : max_pairs;
+  B2_LAUNCH(kern, 2 * pairs, gemm_threads(16), Cfg::kSmemBytes, stream, maps, gp);
+  B2_CUDA(cudaGetLastError());
+  count_launches(1);
+  return 0;
 }

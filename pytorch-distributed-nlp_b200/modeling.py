@@ -415,6 +415,7 @@ class _Engine:
         self.wgrad_stream = torch.cuda.Stream(device=self.dev)
         self.opt_stream = torch.cuda.Stream(device=self.dev)
         self.accum_dgrad = os.environ.get("B2_ACCUM_DGRAD", "1") != "0"
+        self.grouped_wgrad = os.environ.get("B2_GROUPED_WGRAD", "1") != "0"
         self.use_wgrad_stream = os.environ.get("B2_WGRAD_STREAM", "1") != "0"
         # fp32 accumulators for the bias gradients that kernels produce as a side effect of their epilogues (QKV bias
         # from attention backward, intermediate bias from the GELU' dgrad): per layer [3H | I]; one finishing launch
@@ -488,8 +489,15 @@ class _Engine:
         self._ws[key] = ws
         return ws
 
+    def gemm_grouped(self, problems, stream):
+        """independent GEMMs behind one launch where the library can group them (the layer's weight gradients)"""
+        arr = (L.GemmArgs * len(problems))(*problems)
+        L.call("b2_gemm_bf16_grouped", arr, len(problems), stream)
+
     def gemm(self, M, N, K, A, lda, a_major, Bm, ldb, b_major, D, ldd, epi=L.EPI_NONE, bias=None, aux_in=None,
-             ld_aux_in=0, aux_out=None, ld_aux_out=0, p=0.0, site=0, split=False, stream=None, colsum=None):
+             ld_aux_in=0, aux_out=None, ld_aux_out=0, p=0.0, site=0, split=False, stream=None, colsum=None,
+             defer=None):
+        """defer: a list -> the problem is appended to it instead of being launched (see gemm_grouped)"""
         a = L.GemmArgs()
         a.M, a.N, a.K = M, N, K
         a.A, a.lda, a.a_major = A, lda, a_major
@@ -506,6 +514,9 @@ class _Engine:
         a.force_kernel = int(os.environ.get("B2_FORCE_KERNEL", "0"))
         a.debug_timing = None
         a.colsum_out = colsum
+        if defer is not None:
+            defer.append(a)
+            return
         L.call("b2_gemm_bf16", a, stream if stream is not None else self.stream())
 
     # ---- forward --------------------------------------------------------------------------------------------------------
@@ -688,8 +699,11 @@ class _Engine:
             fork()
             L.call("b2_colsum_finish", lp2.data_ptr(), np2.value, 3, H, g(pre + "output.LayerNorm.weight"),
                    g(pre + "output.LayerNorm.bias"), g(pre + "output.dense.bias"), ss)
+            # the layer's four weight gradients: launched one by one on the side stream, or (grouped_wgrad) collected
+            # and issued as ONE persistent launch once the last operand (dqkv) exists
+            wgrads = [] if self.grouped_wgrad else None
             self.gemm(H, I, M, dzd.data_ptr(), H, MN, a["h"].data_ptr(), I, MN, g(pre + "output.dense.weight"), I,
-                      split=True, stream=ss)
+                      split=True, stream=ss, defer=wgrads)
             acc_l = self.bias_acc.data_ptr() + 4 * l * (3 * H + I)
             # dU = (dY2 W2) * gelu'(u); its column sums (= intermediate bias gradient) accumulate in the same epilogue
             self.gemm(M, I, H, dzd.data_ptr(), H, KM, w(pre + "output.dense.weight"), I, MN, dU.data_ptr(), I,
@@ -697,7 +711,7 @@ class _Engine:
             # --- BertIntermediate
             fork()
             self.gemm(I, H, M, dU.data_ptr(), I, MN, a["x1"].data_ptr(), H, MN,
-                      g(pre + "intermediate.dense.weight"), H, split=True, stream=ss)
+                      g(pre + "intermediate.dense.weight"), H, split=True, stream=ss, defer=wgrads)
             # dX1 = dZ2 + dU W1.  accum_dgrad: LayerNorm backward left dZ2 (fp32) in dx_other and the GEMM adds into
             # it (split-K slices reduce in place at L2), else the epilogue reads dZ2 as an auxiliary tile
             if self.accum_dgrad:
@@ -719,7 +733,7 @@ class _Engine:
             L.call("b2_colsum_finish", lp1.data_ptr(), np1.value, 3, H, g(pre + "attention.output.LayerNorm.weight"),
                    g(pre + "attention.output.LayerNorm.bias"), g(pre + "attention.output.dense.bias"), ss)
             self.gemm(H, H, M, dz1d.data_ptr(), H, MN, a["ctx"].data_ptr(), H, MN,
-                      g(pre + "attention.output.dense.weight"), H, split=True, stream=ss)
+                      g(pre + "attention.output.dense.weight"), H, split=True, stream=ss, defer=wgrads)
             self.gemm(M, H, H, dz1d.data_ptr(), H, KM, w(pre + "attention.output.dense.weight"), H, MN,
                       ws["dctx"].data_ptr(), H)
             # --- BertSelfAttention
@@ -731,7 +745,12 @@ class _Engine:
                        scratch, scratch_bytes, s)
             fork()
             self.gemm(3 * H, H, M, dqkv.data_ptr(), 3 * H, MN, x_in.data_ptr(), H, MN,
-                      g(pre + "attention.self.query.weight"), H, split=True, stream=ss)
+                      g(pre + "attention.self.query.weight"), H, split=True, stream=ss, defer=wgrads)
+            if wgrads is not None:
+                # 108 full-K 256x256 tiles (BERT-base) in two waves of one kernel instead of four small split-K GEMMs
+                # and their reduce kernels; largest problems first
+                wgrads.sort(key=lambda t: -(t.M * t.N))
+                self.gemm_grouped(wgrads, ss)
             if side is not main:
                 done[l] = torch.cuda.Event()
                 done[l].record(side)

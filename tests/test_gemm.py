@@ -204,3 +204,36 @@ def test_errors(cuda_dev):
     a.lda = a.ldb = a.ldd = 64
     with pytest.raises(RuntimeError, match="multiple of 64"):
         L.call("b2_gemm_bf16", a, None)
+
+
+def _tn_problem(M, N, K, dev, seed):
+    torch.manual_seed(seed)
+    A, B = _rand((K, M), dev), _rand((K, N), dev, 0.05)     # both MN-major: D = A^T B
+    a = L.GemmArgs()
+    a.M, a.N, a.K = M, N, K
+    a.A, a.lda, a.a_major = A.data_ptr(), M, L.MAJOR_MN
+    a.B, a.ldb, a.b_major = B.data_ptr(), N, L.MAJOR_MN
+    D = torch.zeros(M, N, dtype=torch.bfloat16, device=dev)
+    a.D, a.ldd, a.epilogue = D.data_ptr(), N, L.EPI_NONE
+    return a, A, B, D
+
+
+@pytest.mark.parametrize("shapes", [
+    [(768, 3072), (3072, 768), (768, 768), (2304, 768)],      # one BERT-base layer's weight gradients
+    [(328, 256), (256, 512)],                                  # ragged M, tiny config widths
+    [(768, 768)],
+    [(768, 768), (768, 192)],                                  # N % 256 != 0 -> issued one by one, same result
+])
+def test_grouped_weight_gradients(cuda_dev, shapes):
+    """b2_gemm_bf16_grouped: several TN problems behind one launch == each problem on its own"""
+    K = 1024
+    probs = [_tn_problem(m, n, K, cuda_dev, 40 + i) for i, (m, n) in enumerate(shapes)]
+    arr = (L.GemmArgs * len(probs))(*[p[0] for p in probs])
+    before = L.launch_count()
+    L.call("b2_gemm_bf16_grouped", arr, len(probs), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    launches = L.launch_count() - before
+    if all(n % 256 == 0 for _, n in shapes):
+        assert launches == 1
+    for (_a, A, B, D) in probs:
+        _check(D, A.float().t() @ B.float())
