@@ -61,6 +61,7 @@ __device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
 // forward: grid (seq/128, heads, batch)
 // ------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(ATT_THREADS) attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv,
+                                                                   const __grid_constant__ CUtensorMap tmap_ctx,
                                                                    const AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -73,8 +74,8 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_fwd_kernel(const __grid
   uint64_t* bar_s = &bars[1];
   uint64_t* bar_o = &bars[2];
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(&bars[4]);
-  float* s_bias = reinterpret_cast<float*>(smem + 5 * TILE_BYTES + 64);  // [seq <= 512]
-  float* s_red = s_bias + 512;                                           // [2][128] row exchange between halves
+  uint32_t* s_mbits = reinterpret_cast<uint32_t*>(smem + 5 * TILE_BYTES + 64);  // [seq / 32 <= 16] masked-key bits
+  float* s_red = reinterpret_cast<float*>(smem + 5 * TILE_BYTES + 128);         // [2][128] row exchange between halves
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int row = (warp & 3) * 32 + lane;   // TMEM lane == query row of this thread
@@ -84,6 +85,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_fwd_kernel(const __grid
 
   if (tid == 0) {
     tma_prefetch_desc(&tmap_qkv);
+    tma_prefetch_desc(&tmap_ctx);
     mbar_init(bar_load, 1);
     mbar_init(bar_s, 1);
     mbar_init(bar_o, 1);
@@ -92,8 +94,11 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_fwd_kernel(const __grid
   if (warp == 0) tmem_alloc(tmem_holder, 256);
   pdl_wait();               // PDL: setup above overlapped the predecessor's tail; global reads start below
   pdl_launch_dependents();
-  for (int c = tid; c < p.seq; c += ATT_THREADS)
-    s_bias[c] = (p.mask != nullptr && p.mask[(size_t)b * p.seq + c] == 0) ? kMaskBias : 0.f;
+  for (int c = tid; c < p.seq; c += ATT_THREADS) {   // seq % 128 == 0: whole warps take part in every round
+    const bool masked = p.mask != nullptr && p.mask[(size_t)b * p.seq + c] == 0;
+    const unsigned bits = __ballot_sync(0xffffffffu, masked);
+    if (lane == 0) s_mbits[c >> 5] = bits;
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -137,17 +142,30 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_fwd_kernel(const __grid
     ph_s ^= 1;
     tc_fence_after();
 
+    // this thread's 64 key columns of the block: masked-key bits in two registers; the common unmasked block takes
+    // a warp-uniform fast path (no per-element select)
+    const uint32_t mb0 = s_mbits[j * 4 + half * 2], mb1 = s_mbits[j * 4 + half * 2 + 1];
+    const bool any_masked = (mb0 | mb1) != 0u;
     // pass 1: maximum of this thread's 64 scaled + masked scores (log2 domain), then across the two halves
     float m_loc = -INFINITY;
 #pragma unroll 1
     for (int c = 0; c < 2; ++c) {
+      const uint32_t mbits = c == 0 ? mb0 : mb1;
       uint32_t v[32];
       tmem_ld32(tmem_s + lane_base + half * 64 + c * 32, v);
       tmem_ld_wait();
+      if (!any_masked) {
 #pragma unroll
-      for (int i = 0; i < 32; ++i)
-        m_loc = fmaxf(m_loc, __uint_as_float(v[i]) * c2 + s_bias[j * 128 + half * 64 + c * 32 + i]);
+        for (int i = 0; i < 32; ++i) m_loc = fmaxf(m_loc, __uint_as_float(v[i]));
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          m_loc = fmaxf(m_loc, ((mbits >> i) & 1u) ? -INFINITY : __uint_as_float(v[i]));
+      }
     }
+    // scale after the max (c2 > 0); a masked key counts as score*c2 + (-3.4e38), which is -3.4e38 in fp32
+    m_loc = m_loc * c2;
+    if (any_masked) m_loc = fmaxf(m_loc, kMaskBias);
     s_red[half * 128 + row] = m_loc;
     __syncthreads();
     const float m_new = fmaxf(m_run, fmaxf(s_red[row], s_red[128 + row]));
@@ -156,13 +174,16 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_fwd_kernel(const __grid
     // pass 2: probabilities -> (dropout) -> bf16 P tile in smem
 #pragma unroll 1
     for (int c = 0; c < 2; ++c) {
+      const uint32_t mbits = c == 0 ? mb0 : mb1;
       uint32_t v[32];
       tmem_ld32(tmem_s + lane_base + half * 64 + c * 32, v);
       tmem_ld_wait();
       float pr[32];
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
-        pr[i] = ex2_approx(__uint_as_float(v[i]) * c2 + s_bias[j * 128 + half * 64 + c * 32 + i] - m_new);
+        float x = fmaf(__uint_as_float(v[i]), c2, -m_new);
+        if (any_masked && ((mbits >> i) & 1u)) x = kMaskBias - m_new;
+        pr[i] = ex2_approx(x);
         l_blk += pr[i];
       }
 #pragma unroll
@@ -215,7 +236,8 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_fwd_kernel(const __grid
   __syncthreads();
   const float l_tot = s_red[row] + s_red[128 + row];
   const float inv_l = 1.0f / l_tot;
-  __nv_bfloat16* out = p.ctx + (size_t)(row0 + q_row) * p.hidden + h * 64 + half * 32;
+  // the context tile leaves through Q's tile (its last reader, the final QK^T, completed long ago) as one TMA store:
+  // per-thread row stores would touch 32 different lines per instruction
 #pragma unroll
   for (int i = 0; i < 32; i += 8) {
     uint4 o;
@@ -223,13 +245,18 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_fwd_kernel(const __grid
     o.y = pack_bf16(o_acc[i + 2] * inv_l, o_acc[i + 3] * inv_l);
     o.z = pack_bf16(o_acc[i + 4] * inv_l, o_acc[i + 5] * inv_l);
     o.w = pack_bf16(o_acc[i + 6] * inv_l, o_acc[i + 7] * inv_l);
-    stg16(out + i, o);
+    st_tile_chunk(sQ, row, half * 4 + (i >> 3), o);
   }
   if (p.lse != nullptr && half == 0)
     p.lse[((size_t)b * p.heads + h) * p.seq + q_row] = (m_run + log2f(l_tot)) * kLn2;
 
+  fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
+  if (tid == 0) {
+    tma_store_2d(&tmap_ctx, sQ, h * 64, row0 + qb * 128);
+    tma_store_commit_and_wait();
+  }
   if (warp == 0) {
     tc_fence_after();
     tmem_dealloc(tmem, 256);
@@ -246,9 +273,16 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_fwd_kernel(const __grid
 //     first 64-key half of P lives in V's tile;
 //   * TMEM 256 columns instead of 512: with a single query block nothing accumulates across iterations, so dQ / dV
 //     / dK overwrite the S / dP columns, which every thread has drained before the second MMA batch is issued.
+// Memory paths (ncu on the first version: IPC 0.26, stalls = long scoreboard + LSU/MIO throttle from per-thread row
+// accesses): every global access of the hot loop is a TMA tile copy.  O comes in with Q and dO (into P's second
+// half, free until the dS pass) so delta = rowsum(dO * O) reads two swizzled smem rows; dQ / dK / dV leave through
+// the operand tiles that the last MMAs have released, as TMA tile stores; the key mask is a 64-bit register pair per
+// thread (bit tests, and a warp-uniform fast path when the block has no masked key) instead of a shared-memory
+// float per element.
 template <bool kOneQ>
 __global__ void __launch_bounds__(ATT_THREADS, kOneQ ? 2 : 1)
 attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_do,
+                     const __grid_constant__ CUtensorMap tmap_o, const __grid_constant__ CUtensorMap tmap_dqkv,
                      const AttnParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // kOneQ has no room for alignment slack: the dynamic window of a kernel without static shared memory starts
@@ -262,7 +296,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_
   uint8_t* sQ = smem + 2 * TILE_BYTES;
   uint8_t* sdO = smem + 3 * TILE_BYTES;
   uint8_t* sP0 = kOneQ ? sV : smem + 4 * TILE_BYTES;                       // keys 0-63 of P
-  uint8_t* sP1 = kOneQ ? smem + 4 * TILE_BYTES : smem + 5 * TILE_BYTES;    // keys 64-127 of P
+  uint8_t* sP1 = kOneQ ? smem + 4 * TILE_BYTES : smem + 5 * TILE_BYTES;    // keys 64-127 of P; holds O before that
   uint8_t* sdS = smem + (kOneQ ? 5 : 6) * TILE_BYTES;                      // 2 tiles
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kTiles * TILE_BYTES);
   uint64_t* bar_kv = &bars[0];
@@ -270,7 +304,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_
   uint64_t* bar_s = &bars[2];
   uint64_t* bar_mma = &bars[3];
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(&bars[4]);
-  float* s_bias = reinterpret_cast<float*>(smem + kTiles * TILE_BYTES + 64);  // [128] keys of this block
+  uint32_t* s_mbits = reinterpret_cast<uint32_t*>(smem + kTiles * TILE_BYTES + 48);  // [4]: masked-key bits of this block
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int row = (warp & 3) * 32 + lane;   // TMEM lane: query row inside the S/dP/dQ tiles, key row for dK/dV
@@ -285,6 +319,8 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_
     }
     tma_prefetch_desc(&tmap_qkv);
     tma_prefetch_desc(&tmap_do);
+    tma_prefetch_desc(&tmap_o);
+    tma_prefetch_desc(&tmap_dqkv);
     mbar_init(bar_kv, 1);
     mbar_init(bar_q, 1);
     mbar_init(bar_s, 1);
@@ -294,8 +330,11 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_
   if (warp == 0) tmem_alloc(tmem_holder, kTmemCols);
   pdl_wait();               // PDL: setup above overlapped the predecessor's tail; global reads start below
   pdl_launch_dependents();
-  if (tid < 128)
-    s_bias[tid] = (p.mask != nullptr && p.mask[(size_t)b * p.seq + jb * 128 + tid] == 0) ? kMaskBias : 0.f;
+  if (tid < 128) {
+    const bool masked = p.mask != nullptr && p.mask[(size_t)b * p.seq + jb * 128 + tid] == 0;
+    const unsigned bits = __ballot_sync(0xffffffffu, masked);
+    if (lane == 0) s_mbits[warp] = bits;
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -303,6 +342,8 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_
   const uint32_t tm_s = tmem, tm_dp = tmem + 128;
   const uint32_t tm_dq = tmem + (kOneQ ? 0 : 384), tm_dv = tmem + (kOneQ ? 64 : 256), tm_dk = tmem + (kOneQ ? 128 : 320);
   const uint32_t lane_base = ((uint32_t)((warp & 3) * 32)) << 16;
+  const uint32_t mb0 = s_mbits[half * 2], mb1 = s_mbits[half * 2 + 1];   // this thread's 64 key columns
+  const bool any_masked = (mb0 | mb1) != 0u;                              // warp-uniform
 
   const int row0 = b * p.seq;
   const int col_q = h * 64, col_k = p.hidden + h * 64, col_v = 2 * p.hidden + h * 64;
@@ -323,9 +364,10 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_
   for (int i = 0; i < nq; ++i) {
     const int q_row = i * 128 + row;  // this thread's query row in the sequence
     if (tid == 0) {
-      mbar_expect_tx(bar_q, 2 * TILE_BYTES);
+      mbar_expect_tx(bar_q, 3 * TILE_BYTES);
       tma_load_2d(sQ, &tmap_qkv, bar_q, col_q, row0 + i * 128);
       tma_load_2d(sdO, &tmap_do, bar_q, h * 64, row0 + i * 128);
+      tma_load_2d(sP1, &tmap_o, bar_q, h * 64, row0 + i * 128);   // O, consumed by the delta pass below
       if (i == 0) mbar_wait(bar_kv, 0);
       mbar_wait(bar_q, ph_q);
       tc_fence_after();
@@ -340,24 +382,22 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_
                   k > 0 ? 1u : 0u);
       umma_commit(bar_s);
     }
-    ph_q ^= 1;
     __syncwarp();
-
-    // delta = rowsum(dO * O) and the row's log-sum-exp, straight from HBM while the MMAs run (both threads of a row
-    // compute the same value; 16 loads each)
+    // delta = rowsum(dO * O) from the two smem tiles while the MMAs run (both threads of a row compute the same value)
+    mbar_wait(bar_q, ph_q);
+    ph_q ^= 1;
     float delta = 0.f;
-    {
-      const __nv_bfloat16* o_row = p.ctx_in + (size_t)(row0 + q_row) * p.hidden + h * 64;
-      const __nv_bfloat16* do_row = p.d_ctx + (size_t)(row0 + q_row) * p.hidden + h * 64;
 #pragma unroll
-      for (int k = 0; k < 64; k += 8) {
-        const uint4 a = ldg16(o_row + k), g = ldg16(do_row + k);
-        delta += bf16_lo(a.x) * bf16_lo(g.x) + bf16_hi(a.x) * bf16_hi(g.x) + bf16_lo(a.y) * bf16_lo(g.y) +
-                 bf16_hi(a.y) * bf16_hi(g.y) + bf16_lo(a.z) * bf16_lo(g.z) + bf16_hi(a.z) * bf16_hi(g.z) +
-                 bf16_lo(a.w) * bf16_lo(g.w) + bf16_hi(a.w) * bf16_hi(g.w);
-      }
+    for (int c = 0; c < 8; ++c) {
+      const int off = row * 128 + ((c ^ (row & 7)) << 4);
+      const uint4 a = *reinterpret_cast<const uint4*>(sP1 + off);
+      const uint4 g = *reinterpret_cast<const uint4*>(sdO + off);
+      delta += bf16_lo(a.x) * bf16_lo(g.x) + bf16_hi(a.x) * bf16_hi(g.x) + bf16_lo(a.y) * bf16_lo(g.y) +
+               bf16_hi(a.y) * bf16_hi(g.y) + bf16_lo(a.z) * bf16_lo(g.z) + bf16_hi(a.z) * bf16_hi(g.z) +
+               bf16_lo(a.w) * bf16_lo(g.w) + bf16_hi(a.w) * bf16_hi(g.w);
     }
     const float lse2 = p.lse[((size_t)b * p.heads + h) * p.seq + q_row] * kLog2e;
+    __syncthreads();   // every thread has read its O row: P may overwrite the tile in the pass below
 
     mbar_wait(bar_s, ph_s);
     ph_s ^= 1;
@@ -365,6 +405,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_
 #pragma unroll 1
     for (int c = 0; c < 2; ++c) {
       const int cb = half * 64 + c * 32;   // first key column of this chunk inside the 128-key block
+      const uint32_t mbits = c == 0 ? mb0 : mb1;
       uint32_t vs[32], vd[32];
       tmem_ld32(tm_s + lane_base + cb, vs);
       tmem_ld32(tm_dp + lane_base + cb, vd);
@@ -378,7 +419,9 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
           const int cc = g * 8 + e;
-          const float pr = ex2_approx(__uint_as_float(vs[cc]) * c2 + s_bias[cb + cc] - lse2);
+          float x = fmaf(__uint_as_float(vs[cc]), c2, -lse2);
+          if (any_masked && ((mbits >> cc) & 1u)) x = kMaskBias - lse2;   // what score*c2 + (-3.4e38) rounds to
+          const float pr = ex2_approx(x);
           const bool kp = (keep >> e) & 1u;
           pd[e] = kp ? pr * drop.scale : 0.f;
           const float dp = kp ? __uint_as_float(vd[cc]) * drop.scale : 0.f;
@@ -427,8 +470,8 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_
       tmem_ld32(tm_dq + lane_base + half * 32, v);
       tmem_ld_wait();
       if (p.dq_accum == nullptr) {
-        __nv_bfloat16* dst = p.d_qkv + (size_t)(row0 + q_row) * (3 * p.hidden) + col_q + half * 32;
-        float f[32];   // the bf16-rounded values (what the dgrad/wgrad GEMMs will read), for the bias-gradient sums
+        // seq == 128: dQ leaves through Q's tile (its last reader, the dK product, has completed) as a TMA store
+        float f[32];   // bf16-rounded values (what the dgrad/wgrad GEMMs will read), for the bias-gradient sums
 #pragma unroll
         for (int e = 0; e < 32; ++e) f[e] = __uint_as_float(v[e]);
 #pragma unroll
@@ -438,7 +481,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_
           o.y = pack_bf16_round(f[e + 2], f[e + 3]);
           o.z = pack_bf16_round(f[e + 4], f[e + 5]);
           o.w = pack_bf16_round(f[e + 6], f[e + 7]);
-          stg16(dst + e, o);
+          st_tile_chunk(sQ, row, half * 4 + (e >> 3), o);
         }
         if (p.dbias != nullptr) {
           const float t = warp_colsum32(f, lane);
@@ -450,15 +493,14 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_
         for (int e = 0; e < 32; ++e) atomicAdd(dst + e, __uint_as_float(v[e]));
       }
     }
-    tc_fence_before();
-    __syncthreads();
+    if (p.dq_accum != nullptr) {
+      tc_fence_before();
+      __syncthreads();   // TMEM / smem reuse by the next query block
+    }
   }
 
-  // dK, dV for this thread's key row (32 of the 64 head dims each)
+  // dK, dV for this thread's key row (32 of the 64 head dims each) -> K's and V's tiles -> TMA stores
   {
-    const int k_row = jb * 128 + row;
-    __nv_bfloat16* dk = p.d_qkv + (size_t)(row0 + k_row) * (3 * p.hidden) + col_k + half * 32;
-    __nv_bfloat16* dv = p.d_qkv + (size_t)(row0 + k_row) * (3 * p.hidden) + col_v + half * 32;
     tc_fence_after();
     uint32_t v[32], w[32];
     tmem_ld32(tm_dk + lane_base + half * 32, v);
@@ -477,12 +519,12 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_
       o.y = pack_bf16_round(f[e + 2], f[e + 3]);
       o.z = pack_bf16_round(f[e + 4], f[e + 5]);
       o.w = pack_bf16_round(f[e + 6], f[e + 7]);
-      stg16(dk + e, o);
+      st_tile_chunk(sK, row, half * 4 + (e >> 3), o);
       o.x = pack_bf16_round(g[e], g[e + 1]);
       o.y = pack_bf16_round(g[e + 2], g[e + 3]);
       o.z = pack_bf16_round(g[e + 4], g[e + 5]);
       o.w = pack_bf16_round(g[e + 6], g[e + 7]);
-      stg16(dv + e, o);
+      st_tile_chunk(sV, row, half * 4 + (e >> 3), o);
     }
     if (p.dbias != nullptr) {
       const float tk = warp_colsum32(f, lane), tv = warp_colsum32(g, lane);
@@ -490,8 +532,15 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_
       atomicAdd(p.dbias + col_v + half * 32 + lane, tv);
     }
   }
+  fence_proxy_async_smem();   // generic-proxy tile writes above -> visible to the TMA engine
   tc_fence_before();
   __syncthreads();
+  if (tid == 0) {
+    if (p.dq_accum == nullptr) tma_store_2d(&tmap_dqkv, sQ, col_q, row0 + (nq - 1) * 128);
+    tma_store_2d(&tmap_dqkv, sK, col_k, row0 + jb * 128);
+    tma_store_2d(&tmap_dqkv, sV, col_v, row0 + jb * 128);
+    tma_store_commit_and_wait();
+  }
   if (warp == 0) {
     tc_fence_after();
     tmem_dealloc(tmem, kTmemCols);
@@ -514,9 +563,9 @@ __global__ void dq_convert_kernel(const float* __restrict__ acc, __nv_bfloat16* 
   *reinterpret_cast<uint2*>(d_qkv + t * 3 * hidden + c) = o;
 }
 
-constexpr int kFwdSmem = 5 * TILE_BYTES + 64 + 512 * 4 + 256 * 4 + 1024;
-constexpr int kBwdSmem = 8 * TILE_BYTES + 64 + 128 * 4 + 1024;
-constexpr int kBwdSmemOneQ = 7 * TILE_BYTES + 64 + 128 * 4;   // 115264 B: two CTAs per SM (2 x (this + 1 KB) <= 228 KB)
+constexpr int kFwdSmem = 5 * TILE_BYTES + 128 + 256 * 4 + 1024;
+constexpr int kBwdSmem = 8 * TILE_BYTES + 64 + 1024;
+constexpr int kBwdSmemOneQ = 7 * TILE_BYTES + 64;   // 114752 B: two CTAs per SM (2 x (this + 1 KB) <= 228 KB)
 
 static int32_t check_attn_shapes(const char* who, int64_t batch, int64_t seq, int64_t heads, int64_t head_dim) {
   B2_REQUIRE(batch > 0 && seq > 0 && heads > 0, "%s: empty problem (batch=%lld seq=%lld heads=%lld)", who,
@@ -555,8 +604,11 @@ extern "C" int32_t b2_attention_fwd(const void* qkv, const int64_t* attention_ma
     B2_CUDA(cudaFuncSetAttribute(attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmem));
     attr = true;
   }
+  CUtensorMap tm_ctx;
+  st = get_tensor_map_2d(&tm_ctx, ctx, (uint64_t)tokens, (uint64_t)hidden, (uint64_t)(hidden * 2), 128, 64);
+  if (st) return st;
   dim3 grid((unsigned)(seq / 128), (unsigned)heads, (unsigned)batch);
-  B2_LAUNCH(attention_fwd_kernel, grid, ATT_THREADS, kFwdSmem, stream, tm, p);
+  B2_LAUNCH(attention_fwd_kernel, grid, ATT_THREADS, kFwdSmem, stream, tm, tm_ctx, p);
   B2_CUDA(cudaGetLastError());
   count_launches(1);
   return 0;
@@ -577,6 +629,11 @@ extern "C" int32_t b2_attention_bwd(const void* qkv, const int64_t* attention_ma
   st = get_tensor_map_2d(&tm_qkv, qkv, (uint64_t)tokens, (uint64_t)(3 * hidden), (uint64_t)(3 * hidden * 2), 128, 64);
   if (st) return st;
   st = get_tensor_map_2d(&tm_do, d_ctx, (uint64_t)tokens, (uint64_t)hidden, (uint64_t)(hidden * 2), 128, 64);
+  if (st) return st;
+  CUtensorMap tm_o, tm_dqkv;
+  st = get_tensor_map_2d(&tm_o, ctx, (uint64_t)tokens, (uint64_t)hidden, (uint64_t)(hidden * 2), 128, 64);
+  if (st) return st;
+  st = get_tensor_map_2d(&tm_dqkv, d_qkv, (uint64_t)tokens, (uint64_t)(3 * hidden), (uint64_t)(3 * hidden * 2), 128, 64);
   if (st) return st;
   AttnParams p{};
   p.batch = (int)batch; p.seq = (int)seq; p.heads = (int)heads; p.hidden = (int)hidden;
@@ -602,9 +659,9 @@ extern "C" int32_t b2_attention_bwd(const void* qkv, const int64_t* attention_ma
   }
   dim3 grid((unsigned)(seq / 128), (unsigned)heads, (unsigned)batch);
   if (seq == 128) {
-    B2_LAUNCH(attention_bwd_kernel<true>, grid, ATT_THREADS, kBwdSmemOneQ, stream, tm_qkv, tm_do, p);
+    B2_LAUNCH(attention_bwd_kernel<true>, grid, ATT_THREADS, kBwdSmemOneQ, stream, tm_qkv, tm_do, tm_o, tm_dqkv, p);
   } else {
-    B2_LAUNCH(attention_bwd_kernel<false>, grid, ATT_THREADS, kBwdSmem, stream, tm_qkv, tm_do, p);
+    B2_LAUNCH(attention_bwd_kernel<false>, grid, ATT_THREADS, kBwdSmem, stream, tm_qkv, tm_do, tm_o, tm_dqkv, p);
   }
   B2_CUDA(cudaGetLastError());
   count_launches(1);
