@@ -28,7 +28,7 @@ extern "C" {
 /* ------------------------------------------------------------------------------------------------------ */
 const char* b2_last_error(void);
 int32_t b2_abi_version(void);             /* bumped when a struct below changes */
-#define B2_ABI_VERSION 9
+#define B2_ABI_VERSION 10
 int64_t b2_launch_count(void);            /* kernels launched by this library so far (process-wide) */
 
 /* ------------------------------------------------------------------------------------------------------ */
@@ -135,6 +135,15 @@ int32_t b2_layernorm_bwd(const void* dy, const void* dy_add, const void* x, cons
                          path, e.g. onto another stream) */,
                          void* stream);
 
+/* The training engine's form of b2_layernorm_bwd (fp32 gradient stream: dy fp32 in, dx fp32 out, dx_drop bf16 out,
+ * dropout mask on the input branch): the three column-sum sets are ADDED into accum (fp32 [3][hidden]: d_gamma,
+ * d_beta, d_bias) instead of going through partials + b2_colsum_finish; the caller converts them with
+ * b2_accum_finish.                                                                                             */
+int32_t b2_layernorm_bwd_accum(const float* dy, const void* x, const float* mean, const float* rstd,
+                               const void* gamma, int64_t rows, int64_t hidden, float dropout_p,
+                               const void* rng_state, uint32_t rng_site, float* dx, void* dx_drop, float* accum,
+                               void* stream);
+
 /* partials [nparts][nsets][cols] fp32 -> up to three bf16 [cols] outputs (the second half of b2_layernorm_bwd) */
 int32_t b2_colsum_finish(const float* partials, int32_t nparts, int32_t nsets, int64_t cols, void* out0, void* out1,
                          void* out2, void* stream);
@@ -176,7 +185,7 @@ int32_t b2_head_bwd(const float* dlogits, const void* hidden_states, const void*
                     int64_t seq, int64_t hidden, const void* pool_w, const void* cls_w, int64_t num_labels,
                     float dropout_p, const void* rng_state, uint32_t rng_site, void* d_pool_w, void* d_pool_b,
                     void* d_cls_w, void* d_cls_b, void* d_hidden /* [batch*seq, hidden], rows != CLS zeroed */,
-                    int32_t d_hidden_fp32 /* 0: bf16, 1: fp32 */, float* scratch /* fp32 [batch, hidden] */,
+                    int32_t d_hidden_fp32 /* 0: bf16, 1: fp32 */, float* scratch /* fp32 [2, batch, hidden] */,
                     void* stream);
 
 /* ------------------------------------------------------------------------------------------------------ */

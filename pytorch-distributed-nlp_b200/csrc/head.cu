@@ -116,41 +116,47 @@ __global__ void __launch_bounds__(256) ce_fwd_bwd_kernel(const float* __restrict
 }
 
 // ---- backward ----
-// k1: per (b, j): dpd = sum_c dlogits[b,c] Wc[c,j]  -> d_pooled = mask*scale*dpd -> d_pre = d_pooled*(1-pooled^2)
-//     (fp32 scratch [batch, H]).  Also the classifier grads: d_cls_w[c,j] = sum_b dlogits[b,c]*drop(pooled[b,j]),
-//     d_cls_b[c] = sum_b dlogits[b,c].  One thread per column j; loops over batch and classes.
+// k1: one thread per (b, j): dpd = sum_c dlogits[b,c] Wc[c,j] -> d_pooled = mask*scale*dpd -> d_pre = d_pooled*(1 -
+//     pooled^2) (fp32 scratch [batch, H]); also pm[b,j] = dropout(pooled)[b,j] (second fp32 scratch plane) for k1b.
+//     grid = (ceil(H/256), batch).  (A first version looped over the batch inside 3 blocks: 28 us of pure latency at
+//     the head of the backward critical path.)
 __global__ void __launch_bounds__(256) head_bwd_k1(const float* __restrict__ dlogits,
                                                   const __nv_bfloat16* __restrict__ pooled, int batch, int H,
                                                   const __nv_bfloat16* __restrict__ Wc, int C, float dropout_p,
                                                   const unsigned long long* rng, unsigned site,
-                                                  float* __restrict__ d_pre, __nv_bfloat16* __restrict__ d_cls_w,
-                                                  __nv_bfloat16* __restrict__ d_cls_b) {
+                                                  float* __restrict__ d_pre, float* __restrict__ pm) {
   pdl_wait();               // PDL: predecessors complete + visible before any global access
   pdl_launch_dependents();  // let the next kernel in the stream begin launching
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j < C && blockIdx.x == 0) {  // class bias grads (C <= blockDim.x)
-    float s = 0.f;
-    for (int b = 0; b < batch; ++b) s += dlogits[(size_t)b * C + j];
-    d_cls_b[j] = __float2bfloat16_rn(s);
-  }
+  const int b = blockIdx.y;
   if (j >= H) return;
   const DropCtx drop = make_drop_ctx(rng, site, dropout_p);
-  constexpr int MAXC = 64;
-  float dw[MAXC];
-  for (int c = 0; c < C; ++c) dw[c] = 0.f;
+  const float p = __bfloat162float(pooled[(size_t)b * H + j]);
+  const uint32_t keep8 = dropout_keep8(drop, ((unsigned long long)b * H + j) & ~7ull);
+  const float m = ((keep8 >> (j & 7)) & 1u) ? drop.scale : 0.f;
+  float dpd = 0.f;
+  for (int c = 0; c < C; ++c) dpd = fmaf(dlogits[(size_t)b * C + c], __bfloat162float(Wc[(size_t)c * H + j]), dpd);
+  d_pre[(size_t)b * H + j] = dpd * m * (1.f - p * p);
+  pm[(size_t)b * H + j] = p * m;
+}
+// k1b: classifier grads: d_cls_w[c,j] = sum_b dlogits[b,c] * pm[b,j];  d_cls_b[c] = sum_b dlogits[b,c].
+//     grid = (ceil(H/256), C)
+__global__ void __launch_bounds__(256) head_bwd_k1b(const float* __restrict__ dlogits, const float* __restrict__ pm,
+                                                   int batch, int H, int C, __nv_bfloat16* __restrict__ d_cls_w,
+                                                   __nv_bfloat16* __restrict__ d_cls_b) {
+  pdl_wait();               // PDL: predecessors complete + visible before any global access
+  pdl_launch_dependents();  // let the next kernel in the stream begin launching
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = blockIdx.y;
+  if (j >= H) return;
+  float s = 0.f, sb = 0.f;
   for (int b = 0; b < batch; ++b) {
-    const float p = __bfloat162float(pooled[(size_t)b * H + j]);
-    const uint32_t keep8 = dropout_keep8(drop, ((unsigned long long)b * H + j) & ~7ull);
-    const float m = ((keep8 >> (j & 7)) & 1u) ? drop.scale : 0.f;
-    float dpd = 0.f;
-    for (int c = 0; c < C; ++c) {
-      const float dl = dlogits[(size_t)b * C + c];
-      dpd += dl * __bfloat162float(Wc[(size_t)c * H + j]);
-      dw[c] += dl * (p * m);
-    }
-    d_pre[(size_t)b * H + j] = dpd * m * (1.f - p * p);
+    const float dl = dlogits[(size_t)b * C + c];
+    s = fmaf(dl, pm[(size_t)b * H + j], s);
+    sb += dl;
   }
-  for (int c = 0; c < C; ++c) d_cls_w[(size_t)c * H + j] = __float2bfloat16_rn(dw[c]);
+  d_cls_w[(size_t)c * H + j] = __float2bfloat16_rn(s);
+  if (j == 0) d_cls_b[c] = __float2bfloat16_rn(sb);
 }
 
 // k2: d_pool_w[j, k] = sum_b d_pre[b, j] * h0[b, k];  d_pool_b[j] = sum_b d_pre[b, j].
@@ -257,21 +263,26 @@ extern "C" int32_t b2_head_bwd(const float* dlogits, const void* hidden_states, 
              "head_bwd: null pointer");
   B2_REQUIRE(batch > 0 && seq > 0, "head_bwd: empty batch");
   B2_REQUIRE(hidden % 256 == 0 && hidden / 8 <= 1024, "head_bwd: hidden=%lld unsupported", (long long)hidden);
-  B2_REQUIRE(num_labels <= 64, "head_bwd: num_labels=%lld > 64", (long long)num_labels);
+  B2_REQUIRE(num_labels >= 1 && num_labels <= 65535, "head_bwd: num_labels=%lld", (long long)num_labels);
   B2_CUDA(cudaMemsetAsync(d_hidden, 0, (size_t)batch * seq * hidden * (d_hidden_fp32 ? 4 : 2), stream));
-  B2_LAUNCH(head_bwd_k1, (unsigned)((hidden + 255) / 256), 256, 0, stream, 
-      dlogits, (const __nv_bfloat16*)pooled, (int)batch, (int)hidden, (const __nv_bfloat16*)cls_w, (int)num_labels,
-      dropout_p, (const unsigned long long*)rng_state, rng_site, scratch, (__nv_bfloat16*)d_cls_w,
-      (__nv_bfloat16*)d_cls_b);
+  float* pm = scratch + (size_t)batch * hidden;   // second scratch plane: dropout(pooled)
+  B2_LAUNCH(head_bwd_k1, dim3((unsigned)((hidden + 255) / 256), (unsigned)batch), 256, 0, stream, dlogits,
+            (const __nv_bfloat16*)pooled, (int)batch, (int)hidden, (const __nv_bfloat16*)cls_w, (int)num_labels,
+            dropout_p, (const unsigned long long*)rng_state, rng_site, scratch, pm);
+  B2_CUDA(cudaGetLastError());
+  count_launches(1);
+  // the critical path continues with k3 (d_hidden); the two weight-gradient kernels follow it
+  B2_LAUNCH(head_bwd_k3, dim3((unsigned)batch, (unsigned)(hidden / 64)), 256, 0, stream, scratch,
+            (const __nv_bfloat16*)pool_w, (int)seq, (int)hidden, d_hidden, d_hidden_fp32 ? 1 : 0);
+  B2_CUDA(cudaGetLastError());
+  count_launches(1);
+  B2_LAUNCH(head_bwd_k1b, dim3((unsigned)((hidden + 255) / 256), (unsigned)num_labels), 256, 0, stream, dlogits, pm,
+            (int)batch, (int)hidden, (int)num_labels, (__nv_bfloat16*)d_cls_w, (__nv_bfloat16*)d_cls_b);
   B2_CUDA(cudaGetLastError());
   count_launches(1);
   B2_LAUNCH(head_bwd_k2, (unsigned)hidden, (unsigned)(hidden / 8), 0, stream, 
       scratch, (const __nv_bfloat16*)hidden_states, (int)batch, (int)seq, (int)hidden, (__nv_bfloat16*)d_pool_w,
       (__nv_bfloat16*)d_pool_b);
-  B2_CUDA(cudaGetLastError());
-  count_launches(1);
-  B2_LAUNCH(head_bwd_k3, dim3((unsigned)batch, (unsigned)(hidden / 64)), 256, 0, stream, scratch, (const __nv_bfloat16*)pool_w, (int)seq,
-                                                                      (int)hidden, d_hidden, d_hidden_fp32 ? 1 : 0);
   B2_CUDA(cudaGetLastError());
   count_launches(1);
   return 0;

@@ -148,7 +148,7 @@ __global__ void __launch_bounds__(512) layernorm_bwd_pair_kernel(
     const float* __restrict__ dy, const __nv_bfloat16* __restrict__ x, const float* __restrict__ mean,
     const float* __restrict__ rstd, const __nv_bfloat16* __restrict__ gamma, int rows, float dropout_p,
     const unsigned long long* rng, unsigned rng_site, float* __restrict__ dx, __nv_bfloat16* __restrict__ dx_drop,
-    float* __restrict__ partials /* [gridDim.x][3][H] */) {
+    float* __restrict__ partials /* [gridDim.x][3][H] */, float* __restrict__ accum /* or: fp32 [3][H], += */) {
   pdl_wait();               // PDL: predecessors complete + visible before any global access
   pdl_launch_dependents();  // let the next kernel in the stream begin launching
   constexpr int H = NV * 256;
@@ -277,8 +277,10 @@ __global__ void __launch_bounds__(512) layernorm_bwd_pair_kernel(
     for (int i = 0; i < E; ++i) acc_d[i] += dxv[i];
   }
 
-  // block reduction of the three column-sum sets (8 row slots -> one partial row per block)
-  float* out = partials + (size_t)blockIdx.x * 3 * H;
+  // block reduction of the three column-sum sets (8 row slots -> one row per block), then either a partial row for
+  // a finishing kernel, or -- accum -- straight into the caller's fp32 accumulators (one reduction per column and
+  // block at L2; the caller converts them together with its other fused bias-gradient sums)
+  float* out = accum != nullptr ? accum : partials + (size_t)blockIdx.x * 3 * H;
 #define B2_REDUCE_SET(ARR, WHICH)                                                          \
   {                                                                                        \
     _Pragma("unroll") for (int j = 0; j < NV; ++j)                                         \
@@ -288,7 +290,8 @@ __global__ void __launch_bounds__(512) layernorm_bwd_pair_kernel(
     for (int c = threadIdx.x; c < H; c += blockDim.x) {                                    \
       float s = 0.f;                                                                       \
       _Pragma("unroll") for (int w = 0; w < SLOTS; ++w) s += red[w][c];                    \
-      out[(WHICH)*H + c] = s;                                                              \
+      if (accum != nullptr) atomicAdd(out + (WHICH)*H + c, s);                             \
+      else out[(WHICH)*H + c] = s;                                                         \
     }                                                                                      \
     __syncthreads();                                                                       \
   }
@@ -406,10 +409,10 @@ int32_t launch_layernorm_bwd(const void* dy, const void* dy_add, const void* x, 
                              const void* gamma, int64_t rows, int64_t hidden, float dropout_p, const void* rng,
                              uint32_t site, int mode, int dy_f32, int dx_f32, void* dx, void* dx_drop, void* d_gamma,
                              void* d_beta, void* d_bias, float* scratch, int64_t scratch_bytes, cudaStream_t stream,
-                             int32_t* deferred_nparts) {
+                             int32_t* deferred_nparts, float* accum) {
   B2_REQUIRE(hidden % 256 == 0 && hidden >= 256 && hidden <= 1024, "layernorm: hidden=%lld unsupported",
              (long long)hidden);
-  int nblocks = (int)(scratch_bytes / (3 * hidden * 4));
+  int nblocks = accum != nullptr ? 1 << 20 : (int)(scratch_bytes / (3 * hidden * 4));
   const int want = 296;
   if (nblocks > want) nblocks = want;
   const int max_useful = (int)((rows + 7) / 8);
@@ -440,13 +443,14 @@ int32_t launch_layernorm_bwd(const void* dy, const void* dy_add, const void* x, 
     }                                                                                                           \
     B2_LAUNCH((layernorm_bwd_pair_kernel<NV_>), nblocks, 512, smem, stream, (const float*)dy,                   \
               (const __nv_bfloat16*)x, mean, rstd, (const __nv_bfloat16*)gamma, (int)rows, dropout_p,           \
-              (const unsigned long long*)rng, site, (float*)dx, (__nv_bfloat16*)dx_drop, scratch);              \
+              (const unsigned long long*)rng, site, (float*)dx, (__nv_bfloat16*)dx_drop, scratch, accum);       \
   } break;
     switch ((int)(hidden / 256)) {
       B2_LN_BWD_PAIR(1) B2_LN_BWD_PAIR(2) B2_LN_BWD_PAIR(3) B2_LN_BWD_PAIR(4)
     }
 #undef B2_LN_BWD_PAIR
   } else {
+    B2_REQUIRE(accum == nullptr, "layernorm_bwd: accumulate mode needs the fp32-stream pair kernel");
     switch ((int)(hidden / 256)) {
       B2_LN_BWD(1) B2_LN_BWD(2) B2_LN_BWD(3) B2_LN_BWD(4)
     }
@@ -455,6 +459,7 @@ int32_t launch_layernorm_bwd(const void* dy, const void* dy_add, const void* x, 
 #undef B2_LN_ARGS
   B2_CUDA(cudaGetLastError());
   count_launches(1);
+  if (accum != nullptr) return 0;     // column sums already added into the caller's accumulators
   if (deferred_nparts != nullptr) {   // the caller runs b2_colsum_finish itself (e.g. on another stream)
     *deferred_nparts = nblocks;
     return 0;
@@ -526,4 +531,16 @@ extern "C" int32_t b2_colsum(const void* x, int64_t rows, int64_t cols, int64_t 
   B2_REQUIRE(rows > 0 && cols > 0, "colsum: empty input");
   return launch_colsum(x, rows, cols, ldx, nullptr, 0, out, scratch_partials, scratch_partials_bytes,
                        (cudaStream_t)stream_);
+}
+
+extern "C" int32_t b2_layernorm_bwd_accum(const float* dy, const void* x, const float* mean, const float* rstd,
+                                          const void* gamma, int64_t rows, int64_t hidden, float dropout_p,
+                                          const void* rng_state, uint32_t rng_site, float* dx, void* dx_drop,
+                                          float* accum, void* stream_) {
+  B2_REQUIRE(dy && x && mean && rstd && gamma && dx && dx_drop && accum, "layernorm_bwd_accum: null pointer");
+  B2_REQUIRE(rows > 0, "layernorm_bwd_accum: rows=%lld", (long long)rows);
+  B2_REQUIRE(!(dropout_p > 0.f) || rng_state, "layernorm_bwd_accum: dropout needs rng_state");
+  return launch_layernorm_bwd(dy, nullptr, x, mean, rstd, gamma, rows, hidden, dropout_p, rng_state, rng_site, 0, 1, 1,
+                              dx, dx_drop, nullptr, nullptr, nullptr, nullptr, 0, (cudaStream_t)stream_, nullptr,
+                              accum);
 }

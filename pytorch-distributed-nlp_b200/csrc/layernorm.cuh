@@ -90,6 +90,6 @@ int32_t launch_layernorm_bwd(const void* dy, const void* dy_add, const void* x, 
                              const void* gamma, int64_t rows, int64_t hidden, float dropout_p, const void* rng,
                              uint32_t site, int mode, int dy_f32, int dx_f32, void* dx, void* dx_drop, void* d_gamma,
                              void* d_beta, void* d_bias, float* scratch, int64_t scratch_bytes, cudaStream_t stream,
-                             int32_t* deferred_nparts = nullptr);
+                             int32_t* deferred_nparts = nullptr, float* accum = nullptr);
 
 }  // namespace b2

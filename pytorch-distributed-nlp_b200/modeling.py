@@ -407,9 +407,6 @@ class _Engine:
         self.owner = torch.empty(cfg.vocab_size, dtype=torch.int32, device=self.dev)
         self.split_ws = torch.empty(64 << 20, dtype=torch.uint8, device=self.dev)
         self.partials = torch.empty(8 << 20, dtype=torch.uint8, device=self.dev)
-        # LayerNorm-backward partial sums: one buffer per (LN site, layer parity) so that the reduction to
-        # d_gamma / d_beta / d_bias can run later, on the weight-gradient stream
-        self.ln_partials = [torch.empty(4 << 20, dtype=torch.uint8, device=self.dev) for _ in range(4)]
         self._ws = {}
         self._saved = None
         self.wgrad_stream = torch.cuda.Stream(device=self.dev)
@@ -420,13 +417,26 @@ class _Engine:
         # fp32 accumulators for the bias gradients that kernels produce as a side effect of their epilogues (QKV bias
         # from attention backward, intermediate bias from the GELU' dgrad): per layer [3H | I]; one finishing launch
         # per step turns them into bf16 gradients and re-zeroes them
-        per = 3 * self.H + self.I
+        # ... and for the LayerNorm-backward column sums (d_gamma, d_beta, dense-bias gradient of the branch): per
+        # layer [3H qkv | I intermediate | 3H output-LN sets | 3H attention-output-LN sets]
+        H_, I_ = self.H, self.I
+        per = self.acc_per_layer = 9 * H_ + I_
         self.bias_acc = torch.zeros(max(1, self.nl * per), dtype=torch.float32, device=self.dev)
         segs = []
         for l in range(self.nl):
             pre = "bert.encoder.layer.%d." % l
-            segs.append([l * per, self.lay.off(pre + "attention.self.query.bias"), 3 * self.H])
-            segs.append([l * per + 3 * self.H, self.lay.off(pre + "intermediate.dense.bias"), self.I])
+            o = self.lay.off
+            segs.append([l * per, o(pre + "attention.self.query.bias"), 3 * H_])
+            segs.append([l * per + 3 * H_, o(pre + "intermediate.dense.bias"), I_])
+            b2_ = l * per + 3 * H_ + I_
+            segs.append([b2_, o(pre + "output.LayerNorm.weight"), H_])
+            segs.append([b2_ + H_, o(pre + "output.LayerNorm.bias"), H_])
+            segs.append([b2_ + 2 * H_, o(pre + "output.dense.bias"), H_])
+            b1_ = b2_ + 3 * H_
+            segs.append([b1_, o(pre + "attention.output.LayerNorm.weight"), H_])
+            segs.append([b1_ + H_, o(pre + "attention.output.LayerNorm.bias"), H_])
+            segs.append([b1_ + 2 * H_, o(pre + "attention.output.dense.bias"), H_])
+        self.segs_per_layer = 8
         self.bias_segs = torch.tensor(segs if segs else [[0, 0, 0]], dtype=torch.int64, device=self.dev)
         s = self.stream()
         L.call("b2_embed_owner_init", L.ptr(self.owner), cfg.vocab_size, s)
@@ -479,7 +489,7 @@ class _Engine:
             # gradient of the residual stream: fp32 (12 layers of residual adds would otherwise each round it to bf16);
             # dzd / dz1d are the bf16 (dropout-masked) copies the tensor cores consume
             "dxA": e(M, H, dtype=f32), "dxB": e(M, H, dtype=f32), "dz": e(M, H, dtype=f32),
-            "dz1": e(M, H, dtype=f32), "emb_dx": e(M, H), "dctx": e(M, H), "head_scratch": e(B, H, dtype=f32),
+            "dz1": e(M, H, dtype=f32), "emb_dx": e(M, H), "dctx": e(M, H), "head_scratch": e(2 * B, H, dtype=f32),
             # operands of the weight-gradient GEMMs, double-buffered by layer parity (see _backward_from_dlogits)
             "dzd": [e(M, H), e(M, H)], "dz1d": [e(M, H), e(M, H)], "dU": [e(M, I), e(M, I)],
             "dqkv": [e(M, 3 * H), e(M, 3 * H)],
@@ -688,28 +698,25 @@ class _Engine:
             if side is not main and (l + 2) in done:
                 main.wait_event(done[l + 2])
             # --- BertOutput: LN2 backward (+ dropout mask, bias grad), FFN2 wgrad/dgrad(+GELU')
-            np2 = ctypes.c_int32(0)
-            lp2 = self.ln_partials[2 * st]
-            L.call("b2_layernorm_bwd", dx.data_ptr(), None, a["z2"].data_ptr(), a["mean2"].data_ptr(),
-                   a["rstd2"].data_ptr(), w(pre + "output.LayerNorm.weight"), M, H, p_h, rng, 3 + 3 * l, 1,
+            acc_l = self.bias_acc.data_ptr() + 4 * l * self.acc_per_layer
+            # column sums (d_gamma, d_beta, d_bias) are added into this layer's fp32 accumulators by the kernel itself
+            L.call("b2_layernorm_bwd_accum", dx.data_ptr(), a["z2"].data_ptr(), a["mean2"].data_ptr(),
+                   a["rstd2"].data_ptr(), w(pre + "output.LayerNorm.weight"), M, H, p_h, rng, 3 + 3 * l,
                    (dx_other if self.accum_dgrad else ws["dz"]).data_ptr(), dzd.data_ptr(),
-                   g(pre + "output.LayerNorm.weight"),
-                   g(pre + "output.LayerNorm.bias"), g(pre + "output.dense.bias"), lp2.data_ptr(), lp2.numel(),
-                   ctypes.byref(np2), s)
-            fork()
-            L.call("b2_colsum_finish", lp2.data_ptr(), np2.value, 3, H, g(pre + "output.LayerNorm.weight"),
-                   g(pre + "output.LayerNorm.bias"), g(pre + "output.dense.bias"), ss)
+                   acc_l + 4 * (3 * H + I), s)
             # the layer's four weight gradients: launched one by one on the side stream, or (grouped_wgrad) collected
             # and issued as ONE persistent launch once the last operand (dqkv) exists
             wgrads = [] if self.grouped_wgrad else None
+            if wgrads is None:
+                fork()
             self.gemm(H, I, M, dzd.data_ptr(), H, MN, a["h"].data_ptr(), I, MN, g(pre + "output.dense.weight"), I,
                       split=True, stream=ss, defer=wgrads)
-            acc_l = self.bias_acc.data_ptr() + 4 * l * (3 * H + I)
             # dU = (dY2 W2) * gelu'(u); its column sums (= intermediate bias gradient) accumulate in the same epilogue
             self.gemm(M, I, H, dzd.data_ptr(), H, KM, w(pre + "output.dense.weight"), I, MN, dU.data_ptr(), I,
                       L.EPI_GELU_BWD, aux_in=a["u"].data_ptr(), ld_aux_in=I, colsum=acc_l + 4 * 3 * H)
             # --- BertIntermediate
-            fork()
+            if wgrads is None:
+                fork()
             self.gemm(I, H, M, dU.data_ptr(), I, MN, a["x1"].data_ptr(), H, MN,
                       g(pre + "intermediate.dense.weight"), H, split=True, stream=ss, defer=wgrads)
             # dX1 = dZ2 + dU W1.  accum_dgrad: LayerNorm backward left dZ2 (fp32) in dx_other and the GEMM adds into
@@ -721,17 +728,12 @@ class _Engine:
                 self.gemm(M, H, I, dU.data_ptr(), I, KM, w(pre + "intermediate.dense.weight"), H, MN,
                           dx_other.data_ptr(), H, L.EPI_RESIDUAL_F32, aux_in=ws["dz"].data_ptr(), ld_aux_in=H)
             # --- BertSelfOutput
-            np1 = ctypes.c_int32(0)
-            lp1 = self.ln_partials[2 * st + 1]
-            L.call("b2_layernorm_bwd", dx_other.data_ptr(), None, a["z1"].data_ptr(), a["mean1"].data_ptr(),
-                   a["rstd1"].data_ptr(), w(pre + "attention.output.LayerNorm.weight"), M, H, p_h, rng, 2 + 3 * l, 1,
+            L.call("b2_layernorm_bwd_accum", dx_other.data_ptr(), a["z1"].data_ptr(), a["mean1"].data_ptr(),
+                   a["rstd1"].data_ptr(), w(pre + "attention.output.LayerNorm.weight"), M, H, p_h, rng, 2 + 3 * l,
                    (dx if self.accum_dgrad else ws["dz1"]).data_ptr(), dz1d.data_ptr(),
-                   g(pre + "attention.output.LayerNorm.weight"),
-                   g(pre + "attention.output.LayerNorm.bias"), g(pre + "attention.output.dense.bias"),
-                   lp1.data_ptr(), lp1.numel(), ctypes.byref(np1), s)
-            fork()
-            L.call("b2_colsum_finish", lp1.data_ptr(), np1.value, 3, H, g(pre + "attention.output.LayerNorm.weight"),
-                   g(pre + "attention.output.LayerNorm.bias"), g(pre + "attention.output.dense.bias"), ss)
+                   acc_l + 4 * (6 * H + I), s)
+            if wgrads is None:
+                fork()
             self.gemm(H, H, M, dz1d.data_ptr(), H, MN, a["ctx"].data_ptr(), H, MN,
                       g(pre + "attention.output.dense.weight"), H, split=True, stream=ss, defer=wgrads)
             self.gemm(M, H, H, dz1d.data_ptr(), H, KM, w(pre + "attention.output.dense.weight"), H, MN,
@@ -762,9 +764,10 @@ class _Engine:
                           dx.data_ptr(), H, L.EPI_RESIDUAL_F32, aux_in=ws["dz1"].data_ptr(), ld_aux_in=H)
             # fp32 accumulators -> bf16 bias gradients of this layer (and re-arm them); for S != 128 the QKV segment's
             # accumulator is unused (zero) and must not overwrite the colsum result: finish only the intermediate one
-            seg0 = 2 * l if S == 128 else 2 * l + 1
+            spl = self.segs_per_layer
+            seg0 = spl * l if S == 128 else spl * l + 1
             L.call("b2_accum_finish", self.bias_acc.data_ptr(), self.grads.data_ptr(),
-                   self.bias_segs.data_ptr() + 24 * seg0, (2 * l + 2) - seg0, max(3 * H, I), s)
+                   self.bias_segs.data_ptr() + 24 * seg0, spl * (l + 1) - seg0, max(3 * H, I), s)
             bucket_ready(1 + l, done.get(l))   # complete only with this layer's weight gradients
         L.call("b2_embed_bwd", dx.data_ptr(), 1, ws["emb_pre"].data_ptr(), ws["emb_mean"].data_ptr(),
                ws["emb_rstd"].data_ptr(), w("bert.embeddings.LayerNorm.weight"), ws["ids32"].data_ptr(),

@@ -57,6 +57,16 @@ def test_layernorm_fwd_bwd(cuda_dev, H):
         L.call("b2_layernorm_bwd", dy32.data_ptr(), None, x.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
                g.data_ptr(), rows, H, p, rs.data_ptr(), 11, 1, dx32.data_ptr(), dxd32.data_ptr(), dg2.data_ptr(),
                db2.data_ptr(), dbias2.data_ptr(), scratch.data_ptr(), scratch.numel(), None, S())
+        # accumulate form (what the engine calls): same dx / dx_drop, column sums ADDED into fp32 [3][H]
+        acc = torch.full((3, H), 0.5, dtype=torch.float32, device=dev)
+        dx_a, dxd_a = torch.empty(rows, H, device=dev), torch.empty_like(x)
+        L.call("b2_layernorm_bwd_accum", dy32.data_ptr(), x.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+               g.data_ptr(), rows, H, p, rs.data_ptr(), 11, dx_a.data_ptr(), dxd_a.data_ptr(), acc.data_ptr(), S())
+        torch.cuda.synchronize()
+        assert torch.equal(dx_a, dx32) and torch.equal(dxd_a, dxd32)
+        for k, ref in enumerate((dg2, db2, dbias2)):
+            got = acc[k] - 0.5
+            assert float((got - ref.float()).abs().max()) <= 1e-2 * float(ref.float().abs().max()) + 1e-3, k
         # deferred finish: partials only, then the reduction as a separate call
         import ctypes
         npart = ctypes.c_int32(0)
@@ -257,7 +267,7 @@ def test_head_and_ce(cuda_dev, p):
 
     grads = {k: torch.empty_like(v) for k, v in dict(Wp=Wp, bp=bp, Wc=Wc, bc=bc).items()}
     d_hidden = torch.empty(B * Sq, H, dtype=bf, device=dev)
-    scratch = torch.empty(B, H, dtype=torch.float32, device=dev)
+    scratch = torch.empty(2 * B, H, dtype=torch.float32, device=dev)
     L.call("b2_head_bwd", dlog.data_ptr(), hs.data_ptr(), pooled.data_ptr(), B, Sq, H, Wp.data_ptr(), Wc.data_ptr(),
            C, p, rs.data_ptr(), 37, grads["Wp"].data_ptr(), grads["bp"].data_ptr(), grads["Wc"].data_ptr(),
            grads["bc"].data_ptr(), d_hidden.data_ptr(), 0, scratch.data_ptr(), S())
