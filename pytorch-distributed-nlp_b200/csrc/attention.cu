@@ -264,6 +264,186 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_fwd_kernel(const __grid
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// forward, seq == 128 (the benchmark shape): one key block, so no online rescale and no accumulator carried across
+// iterations.  The CTA is trimmed to fit FOUR per SM (ncu on the general kernel: a third of its samples are
+// mbarrier spins -- TMA / MMA latency -- and 384 CTAs need two waves at 2 per SM): 3 smem tiles (P overwrites Q and K
+// once S = QK^T has completed), 128 TMEM columns (O overwrites the drained S columns), 16-column register passes
+// (62 registers).  Same arithmetic, same Philox indexing as attention_fwd_kernel.
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(ATT_THREADS, 4) attention_fwd128_kernel(const __grid_constant__ CUtensorMap tmap_qkv,
+                                                                         const __grid_constant__ CUtensorMap tmap_ctx,
+                                                                         const AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;                      // later: keys 0-63 of P
+  uint8_t* sK = smem + TILE_BYTES;         // later: keys 64-127 of P
+  uint8_t* sV = smem + 2 * TILE_BYTES;     // later: the context tile on its way out
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 3 * TILE_BYTES);
+  uint64_t* bar_load = &bars[0];
+  uint64_t* bar_s = &bars[1];
+  uint64_t* bar_o = &bars[2];
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(&bars[3]);
+  uint32_t* s_mbits = reinterpret_cast<uint32_t*>(smem + 3 * TILE_BYTES + 48);   // [4]
+  float* s_red = reinterpret_cast<float*>(smem + 3 * TILE_BYTES + 64);           // [2][128]
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int row = (warp & 3) * 32 + lane;   // TMEM lane == query row of this thread
+  const int half = warp >> 2;               // which 64 of the 128 key columns (and which 32 of the 64 output dims)
+  const int h = blockIdx.y, b = blockIdx.z;
+
+  if (tid == 0) {
+    tma_prefetch_desc(&tmap_qkv);
+    tma_prefetch_desc(&tmap_ctx);
+    mbar_init(bar_load, 1);
+    mbar_init(bar_s, 1);
+    mbar_init(bar_o, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_holder, 128);
+  pdl_wait();               // PDL: setup above overlapped the predecessor's tail; global reads start below
+  pdl_launch_dependents();
+  if (tid < 128) {
+    const bool masked = p.mask != nullptr && p.mask[(size_t)b * 128 + tid] == 0;
+    const unsigned bits = __ballot_sync(0xffffffffu, masked);
+    if (lane == 0) s_mbits[warp] = bits;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_holder;
+  const uint32_t lane_base = ((uint32_t)((warp & 3) * 32)) << 16;
+  const int row0 = b * 128;
+  const int col_q = h * 64, col_k = p.hidden + h * 64, col_v = 2 * p.hidden + h * 64;
+  const DropCtx drop = make_drop_ctx(p.rng, p.rng_site, p.dropout_p);
+  const float c2 = p.scale * kLog2e;
+  const uint32_t mb0 = s_mbits[half * 2], mb1 = s_mbits[half * 2 + 1];
+  const bool any_masked = (mb0 | mb1) != 0u;   // warp-uniform
+
+  if (tid == 0) {
+    mbar_expect_tx(bar_load, 3 * TILE_BYTES);
+    tma_load_2d(sQ, &tmap_qkv, bar_load, col_q, row0);
+    tma_load_2d(sK, &tmap_qkv, bar_load, col_k, row0);
+    tma_load_2d(sV, &tmap_qkv, bar_load, col_v, row0);
+    mbar_wait(bar_load, 0);
+    tc_fence_after();
+    constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, false, false);
+    const uint32_t aq = smem_u32(sQ), ak = smem_u32(sK);
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      umma_bf16(tmem, make_smem_desc(aq + k * 32, 16, 1024), make_smem_desc(ak + k * 32, 16, 1024), idesc_s,
+                k > 0 ? 1u : 0u);
+    umma_commit(bar_s);
+  }
+  __syncwarp();
+  mbar_wait(bar_s, 0);
+  tc_fence_after();
+
+  // pass 1: maximum of this thread's 64 scores, then across the two halves of the row
+  float m_loc = -INFINITY;
+#pragma unroll 1
+  for (int c = 0; c < 4; ++c) {
+    const uint32_t mbits = (c < 2 ? mb0 : mb1) >> ((c & 1) * 16);
+    uint32_t v[16];
+    tmem_ld16(tmem + lane_base + half * 64 + c * 16, v);
+    tmem_ld_wait();
+    if (!any_masked) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) m_loc = fmaxf(m_loc, __uint_as_float(v[i]));
+    } else {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) m_loc = fmaxf(m_loc, ((mbits >> i) & 1u) ? -INFINITY : __uint_as_float(v[i]));
+    }
+  }
+  m_loc = m_loc * c2;                                  // scale after the max (c2 > 0)
+  if (any_masked) m_loc = fmaxf(m_loc, kMaskBias);     // a masked key counts as score*c2 + (-3.4e38) = -3.4e38
+  s_red[half * 128 + row] = m_loc;
+  __syncthreads();
+  const float m_new = fmaxf(s_red[row], s_red[128 + row]);
+  __syncthreads();                                     // s_red is reused for the row sums below
+
+  // pass 2: probabilities -> (dropout) -> bf16 P in the Q / K tiles (both dead: S has completed)
+  float l_loc = 0.f;
+  uint8_t* sP = half ? sK : sQ;
+  const int q_row = row;
+#pragma unroll 1
+  for (int c = 0; c < 4; ++c) {
+    const uint32_t mbits = (c < 2 ? mb0 : mb1) >> ((c & 1) * 16);
+    uint32_t v[16];
+    tmem_ld16(tmem + lane_base + half * 64 + c * 16, v);
+    tmem_ld_wait();
+    float pr[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      float x = fmaf(__uint_as_float(v[i]), c2, -m_new);
+      if (any_masked && ((mbits >> i) & 1u)) x = kMaskBias - m_new;
+      pr[i] = ex2_approx(x);
+      l_loc += pr[i];
+    }
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+      const unsigned long long idx =
+          (((unsigned long long)(b * p.heads + h) * 128 + q_row) * 128) + half * 64 + c * 16 + g * 8;
+      const uint32_t keep = dropout_keep8(drop, idx);
+      float q8[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) q8[i] = ((keep >> i) & 1u) ? pr[g * 8 + i] * drop.scale : 0.f;
+      uint4 o;
+      o.x = pack_bf16(q8[0], q8[1]); o.y = pack_bf16(q8[2], q8[3]);
+      o.z = pack_bf16(q8[4], q8[5]); o.w = pack_bf16(q8[6], q8[7]);
+      st_tile_chunk(sP, row, c * 2 + g, o);
+    }
+  }
+  s_red[half * 128 + row] = l_loc;
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  if (tid == 0) {
+    tc_fence_after();
+    constexpr uint32_t idesc_o = make_idesc_bf16(128, 64, false, true);
+    const uint32_t ap0 = smem_u32(sQ), ap1 = smem_u32(sK), av = smem_u32(sV);
+    // O[q, d] = sum_key P[q, key] V[key, d]; O reuses S's first 64 TMEM columns (every thread has drained S)
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      umma_bf16(tmem, make_smem_desc((k < 4 ? ap0 : ap1) + (k & 3) * 32, 16, 1024),
+                make_smem_desc(av + k * 2048, 16, 1024), idesc_o, k > 0 ? 1u : 0u);
+    umma_commit(bar_o);
+  }
+  __syncwarp();
+  const float l_tot = s_red[row] + s_red[128 + row];
+  const float inv_l = 1.0f / l_tot;
+  if (p.lse != nullptr && half == 0)
+    p.lse[((size_t)b * p.heads + h) * 128 + q_row] = (m_new + log2f(l_tot)) * kLn2;
+  mbar_wait(bar_o, 0);
+  tc_fence_after();
+  {
+    uint32_t v[32];
+    tmem_ld32(tmem + lane_base + half * 32, v);
+    tmem_ld_wait();
+    // the context tile leaves through V's tile (read for the last time by the product above) as one TMA store
+#pragma unroll
+    for (int i = 0; i < 32; i += 8) {
+      uint4 o;
+      o.x = pack_bf16(__uint_as_float(v[i]) * inv_l, __uint_as_float(v[i + 1]) * inv_l);
+      o.y = pack_bf16(__uint_as_float(v[i + 2]) * inv_l, __uint_as_float(v[i + 3]) * inv_l);
+      o.z = pack_bf16(__uint_as_float(v[i + 4]) * inv_l, __uint_as_float(v[i + 5]) * inv_l);
+      o.w = pack_bf16(__uint_as_float(v[i + 6]) * inv_l, __uint_as_float(v[i + 7]) * inv_l);
+      st_tile_chunk(sV, row, half * 4 + (i >> 3), o);
+    }
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  if (tid == 0) {
+    tma_store_2d(&tmap_ctx, sV, h * 64, row0);
+    tma_store_commit_and_wait();
+  }
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 128);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // backward: grid (seq/128 kv blocks, heads, batch); loops over query blocks
 // ------------------------------------------------------------------------------------------------------------
 //
@@ -564,7 +744,18 @@ __global__ void dq_convert_kernel(const float* __restrict__ acc, __nv_bfloat16* 
 }
 
 constexpr int kFwdSmem = 5 * TILE_BYTES + 128 + 256 * 4 + 1024;
+constexpr int kFwd128Smem = 3 * TILE_BYTES + 64 + 256 * 4 + 1024;
 constexpr int kBwdSmem = 8 * TILE_BYTES + 64 + 1024;
+
+// B2_ATTN_FWD128=0 keeps seq == 128 on the general forward kernel (A/B measurements)
+static bool fwd128_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("B2_ATTN_FWD128");
+    v = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
 constexpr int kBwdSmemOneQ = 7 * TILE_BYTES + 64;   // 114752 B: two CTAs per SM (2 x (this + 1 KB) <= 228 KB)
 
 static int32_t check_attn_shapes(const char* who, int64_t batch, int64_t seq, int64_t heads, int64_t head_dim) {
@@ -608,6 +799,19 @@ extern "C" int32_t b2_attention_fwd(const void* qkv, const int64_t* attention_ma
   st = get_tensor_map_2d(&tm_ctx, ctx, (uint64_t)tokens, (uint64_t)hidden, (uint64_t)(hidden * 2), 128, 64);
   if (st) return st;
   dim3 grid((unsigned)(seq / 128), (unsigned)heads, (unsigned)batch);
+  if (seq == 128 && fwd128_enabled()) {
+    static bool attr128 = false;
+    if (!attr128) {
+      B2_CUDA(cudaFuncSetAttribute(attention_fwd128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwd128Smem));
+      B2_CUDA(cudaFuncSetAttribute(attention_fwd128_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                   cudaSharedmemCarveoutMaxShared));
+      attr128 = true;
+    }
+    B2_LAUNCH(attention_fwd128_kernel, grid, ATT_THREADS, kFwd128Smem, stream, tm, tm_ctx, p);
+    B2_CUDA(cudaGetLastError());
+    count_launches(1);
+    return 0;
+  }
   B2_LAUNCH(attention_fwd_kernel, grid, ATT_THREADS, kFwdSmem, stream, tm, tm_ctx, p);
   B2_CUDA(cudaGetLastError());
   count_launches(1);
