@@ -50,7 +50,7 @@ struct GemmCfg {
 };
 
 template <int BN, bool A_MN, bool B_MN, int EW>
-__global__ void __launch_bounds__(gemm_threads(EW), 1)
+__global__ void __launch_bounds__(gemm_threads(EW)) __maxnreg__(EW == 8 ? 128 : 96)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const GemmKernelParams p) {
   using Cfg = GemmCfg<BN, EW>;
@@ -259,7 +259,7 @@ struct Gemm2Cfg {
 };
 
 template <int BN, bool A_MN, bool B_MN, int EW>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(gemm_threads(EW), 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(gemm_threads(EW)) __maxnreg__(EW == 8 ? 128 : 96)
 gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                   const GemmKernelParams p) {
   using Cfg = Gemm2Cfg<BN, EW>;
@@ -438,7 +438,7 @@ __device__ __forceinline__ int grouped_find(const GroupedParams& gp, int w) {
 }
 
 template <int EW>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(gemm_threads(EW), 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(gemm_threads(EW)) __maxnreg__(EW == 8 ? 128 : 96)
 gemm2_grouped_tn_kernel(const __grid_constant__ GroupedMaps maps, const GroupedParams gp) {
   constexpr int BN = 256;
   using Cfg = Gemm2Cfg<BN, EW>;
@@ -730,6 +730,18 @@ static Choice choose_config(const b2_gemm_args_t& a) {
 
 using namespace b2;
 
+// Epilogue warps per CTA: 16 (640 threads x 96 registers: the CTA owns the SM's register file) or, with
+// B2_GEMM_EPI_WARPS=8, 8 (384 threads capped at 128 registers: a quarter of the register file stays free, so a
+// 256-thread block of a memory-bound kernel from another stream -- the AdamW update -- can be co-resident).
+static int gemm_epi_warps() {
+  static int v = 0;
+  if (v == 0) {
+    const char* e = getenv("B2_GEMM_EPI_WARPS");
+    v = (e != nullptr && atoi(e) == 8) ? 8 : 16;
+  }
+  return v;
+}
+
 extern "C" int32_t b2_gemm_bf16(const b2_gemm_args_t* a, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   B2_REQUIRE(a != nullptr, "b2_gemm_bf16: null args");
@@ -779,11 +791,7 @@ extern "C" int32_t b2_gemm_bf16(const b2_gemm_args_t* a, void* stream_) {
   const bool a_mn = a->a_major == B2_MAJOR_MN, b_mn = a->b_major == B2_MAJOR_MN;
   B2_REQUIRE(!(a_mn && !b_mn), "b2_gemm_bf16: layout TT (A MN-major, B K-major) is not on the path");
 
-  static int epi_warps = 0;
-  if (epi_warps == 0) {
-    const char* e = getenv("B2_GEMM_EPI_WARPS");
-    epi_warps = (e != nullptr && atoi(e) == 8) ? 8 : 16;
-  }
+  const int epi_warps = gemm_epi_warps();
 #define B2_DISPATCH(FN, BN_, EW_)                                                      \
   if (c.bn == BN_ && epi_warps == EW_) {                                               \
     if (!a_mn && !b_mn) return FN<BN_, false, false, EW_>(*a, c.splits, stream);       \
@@ -846,16 +854,22 @@ extern "C" int32_t b2_gemm_bf16_grouped(const b2_gemm_args_t* args, int32_t coun
   }
   for (int i = count; i < kMaxGroup; ++i) { gp.pr[i] = gp.pr[0]; gp.pr[i].tile_begin = 0x7fffffff; maps.a[i] = maps.a[0]; maps.b[i] = maps.b[0]; }
   gp.num_work = work;
-  using Cfg = Gemm2Cfg<256, 16>;
-  auto kern = gemm2_grouped_tn_kernel<16>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    attr_set = true;
-  }
   const int max_pairs = num_sms() / 2;
   const int pairs = work < max_pairs ? work : max_pairs;
-  B2_LAUNCH(kern, 2 * pairs, gemm_threads(16), Cfg::kSmemBytes, stream, maps, gp);
+  static bool attr_set = false;
+  if (!attr_set) {
+    B2_CUDA(cudaFuncSetAttribute(gemm2_grouped_tn_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 Gemm2Cfg<256, 16>::kSmemBytes));
+    B2_CUDA(cudaFuncSetAttribute(gemm2_grouped_tn_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 Gemm2Cfg<256, 8>::kSmemBytes));
+    attr_set = true;
+  }
+  if (gemm_epi_warps() == 8) {
+    B2_LAUNCH(gemm2_grouped_tn_kernel<8>, 2 * pairs, gemm_threads(8), (Gemm2Cfg<256, 8>::kSmemBytes), stream, maps, gp);
+  } else {
+    B2_LAUNCH(gemm2_grouped_tn_kernel<16>, 2 * pairs, gemm_threads(16), (Gemm2Cfg<256, 16>::kSmemBytes), stream, maps,
+              gp);
+  }
   B2_CUDA(cudaGetLastError());
   count_launches(1);
   return 0;
