@@ -138,6 +138,88 @@ __global__ void embed_pos_kernel(const __nv_bfloat16* __restrict__ dx, int batch
   stg16(d_pos + (size_t)s * H + threadIdx.x * 8, o);
 }
 
+// ---- fast word-row path: fp32 accumulation keyed by the OWNER TOKEN of each vocabulary row ---------------------
+// acc[owner[id]][:] += dx[t][:] for every token (vector reductions at L2; a row met once is a single add into
+// zero, i.e. exact), then the owner converts its row to bf16.  Two fully parallel passes instead of one CTA per
+// token scanning all later tokens for duplicates (32 us at 4096 tokens); the summation order of duplicated rows is
+// no longer fixed (fp32 accumulation, rounded once).
+__global__ void embed_word_accum_kernel(const __nv_bfloat16* __restrict__ dx, const int* __restrict__ ids32, int H,
+                                        int pad_id, const int* __restrict__ owner, float* __restrict__ acc) {
+  pdl_wait();               // PDL: predecessors complete + visible before any global access
+  pdl_launch_dependents();  // let the next kernel in the stream begin launching
+  const int t = blockIdx.x;
+  const int id = ids32[t];
+  if (id == pad_id) return;   // nn.Embedding(padding_idx): the pad row never receives gradient
+  const int o = owner[id];
+  const uint4 v = ldg16(dx + (size_t)t * H + threadIdx.x * 8);
+  float* dst = acc + (size_t)o * H + threadIdx.x * 8;
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(bf16_lo(v.x)), "f"(bf16_hi(v.x)),
+               "f"(bf16_lo(v.y)), "f"(bf16_hi(v.y))
+               : "memory");
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4), "f"(bf16_lo(v.z)), "f"(bf16_hi(v.z)),
+               "f"(bf16_lo(v.w)), "f"(bf16_hi(v.w))
+               : "memory");
+}
+__global__ void embed_word_finish_kernel(const float* __restrict__ acc, const int* __restrict__ ids32, int H, int pad_id,
+                                         int* __restrict__ owner, __nv_bfloat16* __restrict__ d_word) {
+  pdl_wait();               // PDL: predecessors complete + visible before any global access
+  pdl_launch_dependents();  // let the next kernel in the stream begin launching
+  const int t = blockIdx.x;
+  const int id = ids32[t];
+  if (id == pad_id || owner[id] != t) return;   // non-owners never match: owner[id] is the minimum index or INT_MAX
+  const float4 a = *reinterpret_cast<const float4*>(acc + (size_t)t * H + threadIdx.x * 8);
+  const float4 b = *reinterpret_cast<const float4*>(acc + (size_t)t * H + threadIdx.x * 8 + 4);
+  uint4 o;
+  o.x = pack_bf16(a.x, a.y); o.y = pack_bf16(a.z, a.w);
+  o.z = pack_bf16(b.x, b.y); o.w = pack_bf16(b.z, b.w);
+  stg16(d_word + (size_t)id * H + threadIdx.x * 8, o);
+  __syncthreads();
+  if (threadIdx.x == 0) owner[id] = INT_MAX;    // leave the table armed for the next step
+}
+
+// position rows and per-position token-type partial sums in one pass: CTA s walks the batch once.
+//   d_pos[s] = sum_b dx[b*seq + s];  type_part[s][ty] = sum over the same rows with tt == ty (fp32, ty < T <= 3)
+constexpr int kMaxTypeFast = 3;
+__global__ void embed_pos_type_kernel(const __nv_bfloat16* __restrict__ dx, const int* __restrict__ tt32, int batch,
+                                      int seq, int H, int T, __nv_bfloat16* __restrict__ d_pos,
+                                      float* __restrict__ type_part /* [seq][T][H] */) {
+  pdl_wait();               // PDL: predecessors complete + visible before any global access
+  pdl_launch_dependents();  // let the next kernel in the stream begin launching
+  const int s = blockIdx.x;
+  float all[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  float ty[kMaxTypeFast][8];
+#pragma unroll
+  for (int k = 0; k < kMaxTypeFast; ++k)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) ty[k][i] = 0.f;
+  for (int b = 0; b < batch; ++b) {
+    const size_t r = (size_t)b * seq + s;
+    const int tt = tt32[r];
+    const uint4 v = ldg16(dx + r * H + threadIdx.x * 8);
+    const float f[8] = {bf16_lo(v.x), bf16_hi(v.x), bf16_lo(v.y), bf16_hi(v.y),
+                        bf16_lo(v.z), bf16_hi(v.z), bf16_lo(v.w), bf16_hi(v.w)};
+#pragma unroll
+    for (int i = 0; i < 8; ++i) all[i] += f[i];
+#pragma unroll
+    for (int k = 0; k < kMaxTypeFast; ++k)
+      if (tt == k) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) ty[k][i] += f[i];
+      }
+  }
+  uint4 o;
+  o.x = pack_bf16(all[0], all[1]); o.y = pack_bf16(all[2], all[3]);
+  o.z = pack_bf16(all[4], all[5]); o.w = pack_bf16(all[6], all[7]);
+  stg16(d_pos + (size_t)s * H + threadIdx.x * 8, o);
+#pragma unroll
+  for (int k = 0; k < kMaxTypeFast; ++k)
+    if (k < T) {
+      float* dst = type_part + ((size_t)s * T + k) * H + threadIdx.x * 8;
+      *reinterpret_cast<float4*>(dst) = make_float4(ty[k][0], ty[k][1], ty[k][2], ty[k][3]);
+      *reinterpret_cast<float4*>(dst + 4) = make_float4(ty[k][4], ty[k][5], ty[k][6], ty[k][7]);
+    }
+}
+
 __global__ void fill_int_kernel(int* p, int n, int v) {
   pdl_wait();               // PDL: predecessors complete + visible before any global access
   pdl_launch_dependents();  // let the next kernel in the stream begin launching
@@ -204,6 +286,28 @@ extern "C" int32_t b2_embed_bwd(const void* dy, int32_t dy_fp32, const void* pre
   B2_LAUNCH(embed_owner_kernel, (tokens + 255) / 256, 256, 0, stream, ids32, tokens, (int)pad_token_id, owner);
   B2_CUDA(cudaGetLastError());
   count_launches(1);
+  // fast path: fp32 owner-row accumulation + fused position/type pass (needs scratch for [tokens + seq*T][H] fp32)
+  const int64_t fast_bytes = 4 * hidden * ((int64_t)tokens + seq * type_vocab);
+  if (type_vocab <= kMaxTypeFast && scratch_partials_bytes >= fast_bytes) {
+    float* acc = scratch_partials;
+    float* type_part = scratch_partials + (size_t)tokens * hidden;
+    B2_CUDA(cudaMemsetAsync(acc, 0, (size_t)tokens * hidden * 4, stream));
+    B2_LAUNCH(embed_word_accum_kernel, tokens, (unsigned)(hidden / 8), 0, stream, (const __nv_bfloat16*)scratch_dx, ids32,
+              (int)hidden, (int)pad_token_id, owner, acc);
+    B2_CUDA(cudaGetLastError());
+    count_launches(1);
+    B2_LAUNCH(embed_word_finish_kernel, tokens, (unsigned)(hidden / 8), 0, stream, acc, ids32, (int)hidden,
+              (int)pad_token_id, owner, (__nv_bfloat16*)d_word);
+    B2_CUDA(cudaGetLastError());
+    count_launches(1);
+    B2_LAUNCH(embed_pos_type_kernel, (unsigned)seq, (unsigned)(hidden / 8), 0, stream, (const __nv_bfloat16*)scratch_dx,
+              tt32, (int)batch, (int)seq, (int)hidden, (int)type_vocab, (__nv_bfloat16*)d_pos, type_part);
+    B2_CUDA(cudaGetLastError());
+    count_launches(1);
+    __nv_bfloat16* dt = (__nv_bfloat16*)d_type;
+    return b2_colsum_finish(type_part, (int32_t)seq, (int32_t)type_vocab, hidden, dt,
+                            type_vocab > 1 ? dt + hidden : nullptr, type_vocab > 2 ? dt + 2 * hidden : nullptr, stream_);
+  }
   B2_LAUNCH(embed_word_scatter_kernel, tokens, 128, 0, stream, (const __nv_bfloat16*)scratch_dx, ids32, tokens, (int)hidden,
                                                         (int)pad_token_id, owner, (__nv_bfloat16*)d_word);
   B2_CUDA(cudaGetLastError());

@@ -406,7 +406,8 @@ class _Engine:
         self.rng = torch.zeros(2, dtype=torch.int64, device=self.dev)         # {seed, step} for the dropout streams
         self.owner = torch.empty(cfg.vocab_size, dtype=torch.int32, device=self.dev)
         self.split_ws = torch.empty(64 << 20, dtype=torch.uint8, device=self.dev)
-        self.partials = torch.empty(8 << 20, dtype=torch.uint8, device=self.dev)
+        self.partials = torch.empty(32 << 20, dtype=torch.uint8, device=self.dev)   # column-sum partials; the embedding
+        # backward's fp32 owner-row accumulators ([tokens + seq*types][H] fp32 = 13.4 MB at config A)
         self._ws = {}
         self._saved = None
         self.wgrad_stream = torch.cuda.Stream(device=self.dev)

@@ -150,23 +150,26 @@ def test_embed_fwd_bwd(cuda_dev, p):
     d_typ, d_g, d_b = torch.zeros(T, H, dtype=bf, device=dev), torch.zeros(H, dtype=bf, device=dev), \
         torch.zeros(H, dtype=bf, device=dev)
     scratch_dx = torch.empty(M, H, dtype=bf, device=dev)
-    scratch = torch.empty(4 << 20, dtype=torch.uint8, device=dev)
     owner = torch.empty(V, dtype=torch.int32, device=dev)
     L.call("b2_embed_owner_init", owner.data_ptr(), V, S())
-    for _ in range(2):  # twice: the owner table must re-arm itself
-        d_word.zero_()
-        L.call("b2_embed_bwd", dy.data_ptr(), 0, pre.data_ptr(), mean.data_ptr(), rstd.data_ptr(), gam.data_ptr(),
-               ids32.data_ptr(), tt32.data_ptr(), B, Sq, H, V, T, 0, p, rs.data_ptr(), 0, d_word.data_ptr(),
-               d_pos.data_ptr(), d_typ.data_ptr(), d_g.data_ptr(), d_b.data_ptr(), scratch_dx.data_ptr(),
-               scratch.data_ptr(), scratch.numel(), owner.data_ptr(), S())
-    torch.cuda.synchronize()
     yr.backward(dy.float().view(B, Sq, H))
-    assert rel_l2(d_word.float(), wr.grad) < 1.5e-2
-    assert float(d_word[0].float().abs().max()) == 0.0        # padding_idx row
-    assert rel_l2(d_pos.float(), pr.grad) < 1.5e-2
-    assert rel_l2(d_typ.float(), tr.grad) < 1.5e-2
-    assert rel_l2(d_g.float(), gr.grad) < 1.5e-2
-    assert rel_l2(d_b.float(), br.grad) < 1.5e-2
+    # 4 MB of scratch: the fp32 owner-row path ([tokens + seq*types][H] fp32 = 3.9 MB here); 3 MB: the scan path
+    for scratch_bytes in (4 << 20, 3 << 20):
+        scratch = torch.empty(scratch_bytes, dtype=torch.uint8, device=dev)
+        for _ in range(2):  # twice: the owner table must re-arm itself
+            for t in (d_word, d_pos, d_typ, d_g, d_b):
+                t.zero_()
+            L.call("b2_embed_bwd", dy.data_ptr(), 0, pre.data_ptr(), mean.data_ptr(), rstd.data_ptr(), gam.data_ptr(),
+                   ids32.data_ptr(), tt32.data_ptr(), B, Sq, H, V, T, 0, p, rs.data_ptr(), 0, d_word.data_ptr(),
+                   d_pos.data_ptr(), d_typ.data_ptr(), d_g.data_ptr(), d_b.data_ptr(), scratch_dx.data_ptr(),
+                   scratch.data_ptr(), scratch.numel(), owner.data_ptr(), S())
+        torch.cuda.synchronize()
+        assert rel_l2(d_word.float(), wr.grad) < 1.5e-2
+        assert float(d_word[0].float().abs().max()) == 0.0        # padding_idx row
+        assert rel_l2(d_pos.float(), pr.grad) < 1.5e-2
+        assert rel_l2(d_typ.float(), tr.grad) < 1.5e-2
+        assert rel_l2(d_g.float(), gr.grad) < 1.5e-2
+        assert rel_l2(d_b.float(), br.grad) < 1.5e-2
 
 
 def _attn_ref(qkv, mask, B, Sq, nh, keep=None, p=0.0):
