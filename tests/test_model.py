@@ -40,6 +40,35 @@ def test_tiny_step_matches_oracle(cuda_dev, padded, dropout):
     assert worst <= TOL_GRAD_REL, sorted(rows, key=lambda r: -r[1])[:5]
 
 
+@pytest.mark.parametrize("name,cfg_kw,batch,seq", [
+    # BASELINE.json config B (bert-base, seq 512): the multi-block attention paths (online softmax rescale forward,
+    # dQ accumulation across key blocks backward) and the padded tail blocks, at 2 layers
+    ("config-B-shape", dict(vocab_size=2000, hidden_size=768, num_hidden_layers=2, num_attention_heads=12,
+                            intermediate_size=3072, max_position_embeddings=512), 2, 512),
+    # BASELINE.json config C (bert-large widths: H 1024, 16 heads, I 4096), at 2 layers
+    ("config-C-shape", dict(vocab_size=2000, hidden_size=1024, num_hidden_layers=2, num_attention_heads=16,
+                            intermediate_size=4096, max_position_embeddings=512), 4, 128),
+    ("seq-256", dict(max_position_embeddings=256), 3, 256),
+])
+@pytest.mark.parametrize("dropout", [False, True])
+def test_other_baseline_shapes_match_oracle(cuda_dev, name, cfg_kw, batch, seq, dropout):
+    kw = dict(cfg_kw)
+    if not dropout:
+        kw.update(hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0)
+    cfg = tiny_config(**kw)
+    state = state_from_hf_init(cfg)
+    model = make_model(cfg, state, cuda_dev).train()
+    model._engine.seed_dropout(31, 2)
+    b = bert_ref.synthetic_batch(cfg, batch, seq, 4242, padded=True)
+    out, loss = _fwd_bwd(model, b, cuda_dev)
+    masks = oracle_masks(cfg, batch, seq, 31, 2) if dropout else None
+    rl, rz, rg = bert_ref.loss_and_grads(state, cfg, b, masks=masks)
+    assert abs(float(loss) - float(rl)) <= TOL_LOSS
+    assert float((out[1].detach().cpu() - rz).abs().max()) <= TOL_LOGITS
+    worst, rows = grad_report(model.grad_dict(), rg)
+    assert worst <= 2 * TOL_GRAD_REL, sorted(rows, key=lambda r: -r[1])[:5]   # q/k projections: see DESIGN.md §2
+
+
 def test_eval_forward_and_output_surface(cuda_dev):
     cfg = tiny_config()
     state = state_from_hf_init(cfg)
