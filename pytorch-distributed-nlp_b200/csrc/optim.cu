@@ -30,6 +30,7 @@ struct ReduceAdamWParams {
   const long long* step_counter;
   const float* grad_scale;   // optional device scalar (GradScaler): gradients are divided by it
   const float* found_inf;    // optional device scalar (GradScaler): non-zero skips the update
+  const uint8_t* skip;       // optional per-vector flags: already updated by the fused wgrad epilogue
 };
 
 __global__ void __launch_bounds__(256) reduce_adamw_kernel(const ReduceAdamWParams p) {
@@ -50,6 +51,7 @@ __global__ void __launch_bounds__(256) reduce_adamw_kernel(const ReduceAdamWPara
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec;
        i += (long long)gridDim.x * blockDim.x) {
     const long long e = p.begin + (i << 3);
+    if (p.skip != nullptr && p.skip[e >> 3]) continue;
     float g[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int r = 0; r < MAX_WORLD; ++r) {
@@ -183,6 +185,7 @@ extern "C" int32_t b2_bucket_reduce_adamw(const void* const* peer_grads, void* c
   p.step_counter = (const long long*)step_counter;
   p.grad_scale = hp->grad_scale;
   p.found_inf = hp->found_inf;
+  p.skip = hp->skip_flags;
   const long long nvec = (end - begin) >> 3;
   long long blocks = (nvec + 255) / 256;
   const long long cap = 148 * 8;

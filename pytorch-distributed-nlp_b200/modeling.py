@@ -414,6 +414,10 @@ class _Engine:
         self.opt_stream = torch.cuda.Stream(device=self.dev)
         self.accum_dgrad = os.environ.get("B2_ACCUM_DGRAD", "1") != "0"
         self.grouped_wgrad = os.environ.get("B2_GROUPED_WGRAD", "1") != "0"
+        # experimental, off: measured 4.17 ms/step vs 3.94 with the separate per-bucket AdamW launches -- the epilogue's
+        # optimizer-state round trips (one 4 KB staging tile per warp) keep too few bytes in flight; see DESIGN.md 4.3
+        self.fused_adamw = os.environ.get("B2_FUSED_ADAMW", "0") == "1"
+        self.fused_adamw_active = False
         self.use_wgrad_stream = os.environ.get("B2_WGRAD_STREAM", "1") != "0"
         # fp32 accumulators for the bias gradients that kernels produce as a side effect of their epilogues (QKV bias
         # from attention backward, intermediate bias from the GELU' dgrad): per layer [3H | I]; one finishing launch
@@ -669,6 +673,12 @@ class _Engine:
         # (head bucket is announced right after these helpers are defined)
         opt = self.model._optimizer
         overlap_opt = hooks is None and opt is not None and getattr(opt, "_armed", False)
+        # single GPU, optimizer armed by the fused step, no GradScaler: the encoder weight matrices are updated in the
+        # epilogue of the grouped weight-gradient GEMM itself (no gradient round trip, no separate HBM-bound pass over
+        # 85 % of the parameters); the per-bucket AdamW launches then skip those vectors
+        self.fused_adamw_active = bool(overlap_opt and self.grouped_wgrad and self.fused_adamw and
+                                       getattr(opt, "grad_scale", None) is None and
+                                       not getattr(opt, "_amp_seen", False))
 
         def bucket_ready(idx, wg_event=None):
             """bucket `idx` holds its final gradients once the main stream reaches this point (and `wg_event`,
@@ -753,7 +763,14 @@ class _Engine:
                 # 108 full-K 256x256 tiles (BERT-base) in two waves of one kernel instead of four small split-K GEMMs
                 # and their reduce kernels; largest problems first
                 wgrads.sort(key=lambda t: -(t.M * t.N))
-                self.gemm_grouped(wgrads, ss)
+                if self.fused_adamw_active:
+                    hp = opt.hparams()
+                    hp.skip_flags = None
+                    arr = (L.GemmArgs * len(wgrads))(*wgrads)
+                    L.call("b2_gemm_bf16_grouped_adamw", arr, opt.fused_targets(wgrads), len(wgrads), hp,
+                           L.ptr(opt._state()["step"]), ss)
+                else:
+                    self.gemm_grouped(wgrads, ss)
             if side is not main:
                 done[l] = torch.cuda.Event()
                 done[l].record(side)

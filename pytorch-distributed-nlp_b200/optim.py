@@ -80,8 +80,40 @@ class AdamW(torch.optim.Optimizer):
                 "exp_avg_sq": torch.zeros(n, dtype=torch.float32, device=eng.dev),
                 "step": torch.zeros(1, dtype=torch.int64, device=eng.dev),
                 "decay": self._decay_flags_cpu.to(eng.dev),
+                "skip": self._fused_skip_flags().to(eng.dev),
             }
         return self._dev_state
+
+    def _fused_skip_flags(self):
+        """uint8 per 8-element vector: 1 for the encoder weight matrices, which the single-GPU fused step updates in the
+        epilogue of the grouped weight-gradient GEMM (b2_gemm_bf16_grouped_adamw); the per-bucket update skips them."""
+        lay = self._model._layout
+        flags = torch.zeros(lay.total // 8, dtype=torch.uint8)
+        for l in range(self._model.config.num_hidden_layers):
+            pre = "bert.encoder.layer.%d." % l
+            for nm in ("attention.self.query.weight", "attention.self.key.weight", "attention.self.value.weight",
+                       "attention.output.dense.weight", "intermediate.dense.weight", "output.dense.weight"):
+                off, shape = lay.entries[pre + nm]
+                flags[off // 8:(off + shape[0] * shape[1]) // 8] = 1
+        return flags
+
+    def fused_targets(self, problems):
+        """b2_fused_adamw_target_t array for weight-gradient problems whose D pointers lie in the engine's bf16 gradient
+        space: the optimizer state of the same elements."""
+        st = self._state()
+        model = self._model
+        eng = model._engine
+        gbase = eng.grads.data_ptr()
+        arr = (L.FusedAdamWTarget * len(problems))()
+        decay = self._decay_flags_cpu
+        for i, pr in enumerate(problems):
+            off = (pr.D - gbase) // 2
+            arr[i].master = model._flat.data_ptr() + 4 * off
+            arr[i].exp_avg = st["exp_avg"].data_ptr() + 4 * off
+            arr[i].exp_avg_sq = st["exp_avg_sq"].data_ptr() + 4 * off
+            arr[i].shadow = eng.shadow.data_ptr() + 2 * off
+            arr[i].decay = int(decay[off // 8])
+        return arr
 
     def hparams(self):
         g = self.param_groups[0]
@@ -94,6 +126,8 @@ class AdamW(torch.optim.Optimizer):
         if gs is not None and (gs.dtype != torch.float32 or not gs.is_cuda):
             raise TypeError("grad_scale must be a CUDA fp32 scalar (torch.cuda.amp.GradScaler's)")
         hp.found_inf = self._found_inf_ptr()
+        eng = self._model._engine
+        hp.skip_flags = self._state()["skip"].data_ptr() if getattr(eng, "fused_adamw_active", False) else None
         return hp
 
     def _found_inf_ptr(self):
