@@ -28,7 +28,7 @@ extern "C" {
 /* ------------------------------------------------------------------------------------------------------ */
 const char* b2_last_error(void);
 int32_t b2_abi_version(void);             /* bumped when a struct below changes */
-#define B2_ABI_VERSION 11
+#define B2_ABI_VERSION 12
 int64_t b2_launch_count(void);            /* kernels launched by this library so far (process-wide) */
 
 /* ------------------------------------------------------------------------------------------------------ */
@@ -229,7 +229,8 @@ int32_t b2_gemm_bf16_grouped_adamw(const b2_gemm_args_t* args, const b2_fused_ad
 /* Fused update of one contiguous slice [begin, end) (element indices, multiples of 8) of the flat parameter
  * space.  world == 1: grads read from `grad_local`.  world > 1: element-wise mean over `peer_grads[0..world)`
  * (peer-mapped bf16 buffers, fixed rank order => bit-identical on every rank), then the HF AdamW update on the
- * fp32 master / moments, then the bf16 shadow weights are stored to every `peer_shadow[r]`.
+ * fp32 master / moments, then the bf16 shadow weights are stored to every non-NULL `peer_shadow[r]`
+ * (peer_shadow[rank] must be set; NULL elsewhere = that peer's copy travels by b2_copy_async).
  * decay_flags: uint8 per 8-element vector (1 = apply weight decay).  step_counter: device int64, read here
  * (t = *step_counter + 1 for the bias correction); bumped separately by b2_step_advance.                     */
 int32_t b2_bucket_reduce_adamw(const void* const* peer_grads, void* const* peer_shadow, int32_t world,
@@ -252,6 +253,9 @@ int32_t b2_accum_finish(float* src, void* dst, const int64_t* segments /* device
 int32_t b2_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream);
 int32_t b2_cast_bf16_to_f32(const void* src, float* dst, int64_t n, void* stream);
 int32_t b2_zero(void* dst, int64_t bytes, void* stream);
+/* stream-ordered device-to-device copy; with an IPC-mapped peer pointer on one side it is a copy-engine transfer
+ * over NVLink (the DMA form of the gradient exchange: peers' slices in, updated bf16 weights out)             */
+int32_t b2_copy_async(void* dst, const void* src, int64_t bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------ */
 /* peer memory over NVLink / NVSwitch (one process per GPU; handles exchanged by the host through           */

@@ -8,7 +8,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libb2ddpbert.so")
-ABI_VERSION = 11
+ABI_VERSION = 12
 
 MAJOR_K, MAJOR_MN = 0, 1
 EPI_NONE, EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_DROPOUT_RESIDUAL, EPI_RESIDUAL, EPI_GELU_BWD = 0, 1, 2, 3, 4, 5
@@ -70,6 +70,7 @@ _SIGNATURES = {
     "b2_cast_f32_to_bf16": [vp, vp, i64, vp],
     "b2_cast_bf16_to_f32": [vp, vp, i64, vp],
     "b2_zero": [vp, i64, vp],
+    "b2_copy_async": [vp, vp, i64, vp],
     "b2_comm_alloc": [i64, C.POINTER(vp)],
     "b2_comm_free": [vp],
     "b2_comm_export": [vp, C.c_char_p],

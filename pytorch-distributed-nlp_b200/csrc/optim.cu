@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(256) reduce_adamw_kernel(const ReduceAdamWPara
     o.z = pack_bf16(w[4], w[5]); o.w = pack_bf16(w[6], w[7]);
 #pragma unroll
     for (int r = 0; r < MAX_WORLD; ++r)
-      if (r < p.world) *reinterpret_cast<uint4*>(p.shadow[r] + e) = o;
+      if (r < p.world && p.shadow[r] != nullptr) *reinterpret_cast<uint4*>(p.shadow[r] + e) = o;
   }
 }
 
@@ -172,7 +172,8 @@ extern "C" int32_t b2_bucket_reduce_adamw(const void* const* peer_grads, void* c
   for (int r = 0; r < MAX_WORLD; ++r) {
     p.grads[r] = r < world ? (const __nv_bfloat16*)peer_grads[r] : nullptr;
     p.shadow[r] = r < world ? (__nv_bfloat16*)peer_shadow[r] : nullptr;
-    if (r < world) B2_REQUIRE(p.grads[r] && p.shadow[r], "bucket_reduce_adamw: null peer pointer for rank %d", r);
+    // a NULL shadow entry = that peer's copy is delivered some other way (copy-engine all-gather)
+    if (r < world) B2_REQUIRE(p.grads[r] && (p.shadow[r] || r != rank), "bucket_reduce_adamw: null peer pointer for rank %d", r);
   }
   p.world = world;
   p.master = master; p.m = exp_avg; p.v = exp_avg_sq; p.decay = decay_flags;
@@ -237,5 +238,14 @@ extern "C" int32_t b2_zero(void* dst, int64_t bytes, void* stream_) {
   B2_REQUIRE(dst && bytes >= 0, "zero: bad args");
   if (bytes == 0) return 0;
   B2_CUDA(cudaMemsetAsync(dst, 0, (size_t)bytes, (cudaStream_t)stream_));
+  return 0;
+}
+
+extern "C" int32_t b2_copy_async(void* dst, const void* src, int64_t bytes, void* stream_) {
+  B2_REQUIRE(dst && src && bytes >= 0, "copy_async: bad args");
+  if (bytes == 0) return 0;
+  // device-to-device: between a local buffer and an IPC-mapped peer buffer this is a copy-engine transfer over
+  // NVLink that runs beside the SM kernels of other streams (a memcpy node when captured in a graph)
+  B2_CUDA(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream_));
   return 0;
 }

@@ -102,6 +102,7 @@ class DistributedDataParallel(nn.Module):
         else:
             self.world, self.rank = 1, 0
         self.overlap = overlap
+        self.dma = False
         self.comm = None
         self._master_stale = False
         self._side = None
@@ -121,6 +122,18 @@ class DistributedDataParallel(nn.Module):
             eng.rebind(shadow, grads)
             eng.refresh_shadow()
             self._slices = self._make_slices()
+            # staging for the DMA form of the exchange: my slice of every bucket as held by each peer
+            import os
+            self.dma = os.environ.get("B2_DDP_DMA", "1") != "0"
+            self._stage_off, off = [], 0
+            for (sb, se) in self._slices:
+                row = {}
+                for r in range(self.world):
+                    if r != self.rank:
+                        row[r] = off
+                        off += (2 * (se - sb) + 255) // 256 * 256
+                self._stage_off.append(row)
+            self._stage = torch.empty(max(off, 256), dtype=torch.uint8, device=eng.dev)
             self._side = torch.cuda.Stream(device=eng.dev)
             torch.cuda.synchronize(eng.dev)
             dist.barrier(group=process_group)
@@ -151,11 +164,41 @@ class DistributedDataParallel(nn.Module):
         self._side.wait_event(ev)
         s = self._side.cuda_stream
         self.comm.barrier(_SLOT_BUCKET0 + idx, s)
-        sb, se = self._slices[idx]
-        opt.update_range(sb, se, self.world, self.rank, self.comm.peers["grads"], self.comm.peers["shadow"], s)
+        self._exchange_update(opt, idx, s)
         if self._pending is None:
             self._pending = set()
         self._pending.add(idx)
+
+    def _exchange_update(self, opt, idx, s):
+        """Mean over ranks + HF-AdamW on my slice of bucket `idx` + delivery of the new bf16 weights to every rank.
+        Kernel form: the reduce kernel loads the peers' slices / stores the peers' shadows itself through the mapped
+        pointers.  DMA form (default for every bucket but the last one produced): the transfers are copy-engine
+        copies over NVLink -- they run beside the GEMM CTAs instead of time-slicing with them (a 640-thread GEMM CTA
+        owns its SM's registers, so an SM-driven exchange kernel can only run between them) -- and the reduce kernel
+        works on local memory only."""
+        sb, se = self._slices[idx]
+        if se <= sb:
+            return
+        peers_g, peers_s = self.comm.peers["grads"], self.comm.peers["shadow"]
+        if not self.dma or idx == 0:
+            opt.update_range(sb, se, self.world, self.rank, peers_g, peers_s, s)
+            return
+        nbytes = 2 * (se - sb)
+        g_ptrs, s_ptrs = [], []
+        for r in range(self.world):
+            if r == self.rank:
+                g_ptrs.append(peers_g[r])
+                s_ptrs.append(peers_s[r])
+                continue
+            st = self._stage.data_ptr() + self._stage_off[idx][r]
+            L.call("b2_copy_async", st, peers_g[r] + 2 * sb, nbytes, s)
+            g_ptrs.append(st - 2 * sb)        # the kernel indexes base + absolute element index
+            s_ptrs.append(None)
+        opt.update_range(sb, se, self.world, self.rank, g_ptrs, s_ptrs, s)
+        mine = peers_s[self.rank] + 2 * sb
+        for r in range(self.world):
+            if r != self.rank:
+                L.call("b2_copy_async", peers_s[r] + 2 * sb, mine, nbytes, s)
 
     def _on_backward_done(self):
         pass
@@ -184,9 +227,7 @@ class DistributedDataParallel(nn.Module):
             for idx in range(nb):
                 if idx in done:
                     continue
-                sb, se = self._slices[idx]
-                opt.update_range(sb, se, self.world, self.rank, self.comm.peers["grads"],
-                                 self.comm.peers["shadow"], s)
+                self._exchange_update(opt, idx, s)
             self.comm.barrier(_SLOT_UPDATE_DONE, s)
             opt.advance(s)
         self._pending = None
