@@ -230,7 +230,7 @@ def run_b200(args):
     import torch.distributed as dist
     import pytorch_distributed_nlp_b200 as b2
     from pytorch_distributed_nlp_b200 import _lib as L
-    from oracle import bert_ref  # synthetic-batch generator only (SURVEY.md §8d inputs); no oracle compute on this arm
+    from pytorch_distributed_nlp_b200 import synthetic_batch   # SURVEY.md §8d inputs (nothing of oracle/ on this arm)
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -253,7 +253,7 @@ def run_b200(args):
     trainer = b2.Trainer(targs, cfg, net, torch.nn.CrossEntropyLoss(), optimizer)
     eng = model._engine
 
-    ring = [bert_ref.synthetic_batch(cfg, BATCH, SEQ, 1000 + rank + 64 * i) for i in range(16)]
+    ring = [synthetic_batch(cfg, BATCH, SEQ, 1000 + rank + 64 * i) for i in range(16)]
 
     def barrier():
         torch.cuda.synchronize(dev)

@@ -7,6 +7,7 @@ from .modeling import (BertConfig, BertForSequenceClassification, SequenceClassi
                        bert_large_config, chinese_bert_wwm_ext_config)
 from .optim import AdamW, build_optimizer
 from .ddp import DistributedDataParallel
+from .synthetic import synthetic_batch
 from .trainer import Args, FusedEvalStep, FusedTrainStep, Trainer
 
 
@@ -23,5 +24,5 @@ def set_seed(seed=123):
 
 
 __all__ = ["BertConfig", "BertForSequenceClassification", "SequenceClassifierOutput", "AdamW", "build_optimizer",
-           "DistributedDataParallel", "Args", "Trainer", "FusedTrainStep", "FusedEvalStep", "set_seed", "bert_base_config",
+           "DistributedDataParallel", "Args", "Trainer", "FusedTrainStep", "FusedEvalStep", "synthetic_batch", "set_seed", "bert_base_config",
            "bert_large_config", "chinese_bert_wwm_ext_config"]

@@ -134,3 +134,16 @@ def test_output_object_indexing():
     assert o[0] is o.loss and o[1] is o.logits and len(o) == 2 and o["logits"] is o.logits
     o2 = b2.SequenceClassifierOutput(logits=torch.zeros(2, 6))
     assert o2[0] is o2.logits and len(o2) == 1
+
+
+def test_package_synthetic_batch_is_the_oracles():
+    """bench.py's b200 arm draws its inputs from the package (nothing of oracle/ on that arm); the parity tests draw
+    theirs from the oracle: same generator, same tensors"""
+    from oracle import bert_ref
+    cfg = b2.chinese_bert_wwm_ext_config(num_labels=6)
+    for padded in (False, True):
+        a = b2.synthetic_batch(cfg, 5, 128, 1234, padded=padded)
+        b = bert_ref.synthetic_batch(cfg, 5, 128, 1234, padded=padded)
+        assert set(a) == set(b) == {"input_ids", "token_type_ids", "attention_mask", "label"}
+        for k in a:
+            assert a[k].dtype == torch.int64 and torch.equal(a[k], b[k])

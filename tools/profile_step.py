@@ -4,7 +4,6 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch
 import pytorch_distributed_nlp_b200 as b2
-from oracle import bert_ref
 
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 3
 torch.cuda.set_device(0)
@@ -15,5 +14,5 @@ args = b2.Args()
 opt = b2.build_optimizer(model, args)
 step = b2.FusedTrainStep(model, opt, 32, 128, use_graph=False)
 for i in range(steps):
-    step(bert_ref.synthetic_batch(cfg, 32, 128, 1000 + i))
+    step(b2.synthetic_batch(cfg, 32, 128, 1000 + i))
 print("loss", step.loss_to_host())

@@ -12,5 +12,5 @@ except Exception as e:
 PY
 timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; echo "bench ref exit $?"; tail -c 400 gpurun_out/bench_ref.json
 timeout 600 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 224 -c 224 --csv --log-file gpurun_out/launches_r01k.csv python tools/profile_step.py 3 > gpurun_out/prof_k.log 2>&1; echo "ncu list exit $?"
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:"gemm2_bf16_kernel|gemm2_grouped" -s 30 -c 10 -o gpurun_out/prof_gemm_k python tools/profile_step.py 2 > gpurun_out/prof_gemm_k.log 2>&1; echo "ncu full exit $?"
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 222 -c 222 --csv --log-file gpurun_out/launches_r01n.csv python tools/profile_step.py 3 > gpurun_out/prof_n.log 2>&1; echo "ncu list exit $?"
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:"gemm2_bf16_kernel|gemm2_grouped" -s 30 -c 10 -o gpurun_out/prof_gemm_n python tools/profile_step.py 2 > gpurun_out/prof_gemm_n.log 2>&1; echo "ncu full exit $?"
