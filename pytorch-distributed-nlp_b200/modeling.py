@@ -11,8 +11,6 @@ The arithmetic follows HF ``BertForSequenceClassification`` (SP/transformers/mod
 1077-1154, eager attention) in bf16 with fp32 accumulation/statistics; fp32 master weights stay the parameters
 the user sees.  There is no PyTorch fallback: without the CUDA library every call raises.
 """
-import ctypes
-import math
 import os
 from collections import OrderedDict
 

@@ -14,7 +14,6 @@ import time
 import numpy as np
 import torch
 
-from . import _lib as L
 from .ddp import DistributedDataParallel
 
 

@@ -242,7 +242,6 @@ def test_grouped_weight_gradients(cuda_dev, shapes):
 def test_grouped_weight_gradients_with_fused_adamw(cuda_dev):
     """b2_gemm_bf16_grouped_adamw: gradient (bf16, still written) + HF-AdamW on the same elements in the epilogue,
     against the restated HF update applied to the reference gradient"""
-    from oracle import adamw_ref
     K, lr, wd, t_prev = 1024, 3e-3, 0.01, 4
     shapes = [(768, 512), (256, 768)]
     probs = [_tn_problem(m, n, K, cuda_dev, 60 + i) for i, (m, n) in enumerate(shapes)]
