@@ -28,7 +28,7 @@ extern "C" {
 /* ------------------------------------------------------------------------------------------------------ */
 const char* b2_last_error(void);
 int32_t b2_abi_version(void);             /* bumped when a struct below changes */
-#define B2_ABI_VERSION 12
+#define B2_ABI_VERSION 13
 int64_t b2_launch_count(void);            /* kernels launched by this library so far (process-wide) */
 
 /* ------------------------------------------------------------------------------------------------------ */
@@ -157,16 +157,19 @@ int32_t b2_colsum(const void* x, int64_t rows, int64_t cols, int64_t ldx, void* 
 /*   qkv  bf16 [batch*seq, 3*hidden]  (Q | K | V column blocks, heads of 64 inside each)                    */
 /*   mask int64 [batch, seq] of {0,1} as produced by the reference Collate, or NULL (= all ones)            */
 /*   ctx  bf16 [batch*seq, hidden]    lse fp32 [batch, heads, seq]                                          */
+/*   keep_bits  NULL, or uint64 [batch, heads, seq, seq/64]: cache of the forward's dropout decisions; used  */
+/*              (written by fwd, read by bwd instead of regenerating Philox) when seq == 128 and dropout_p > 0,*/
+/*              ignored otherwise.  Pass the same buffer to both calls of a step, or NULL to both.            */
 /* ------------------------------------------------------------------------------------------------------ */
 int32_t b2_attention_fwd(const void* qkv, const int64_t* attention_mask, int64_t batch, int64_t seq,
                          int64_t heads, int64_t head_dim, float dropout_p, const void* rng_state,
-                         uint32_t rng_site, void* ctx, float* lse, void* stream);
+                         uint32_t rng_site, void* ctx, float* lse, uint64_t* keep_bits, void* stream);
 int32_t b2_attention_bwd(const void* qkv, const int64_t* attention_mask, const void* ctx, const void* d_ctx,
                          const float* lse, int64_t batch, int64_t seq, int64_t heads, int64_t head_dim,
                          float dropout_p, const void* rng_state, uint32_t rng_site, void* d_qkv,
                          float* dq_accum /* fp32 [batch*seq, hidden], only for seq > 128 */,
                          float* dbias_accum /* NULL, or fp32 [3*hidden]: += column sums of d_qkv (QKV bias grad) */,
-                         void* stream);
+                         const uint64_t* keep_bits, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------ */
 /* head: BertPooler (modeling_bert.py:462-468) + dropout + classifier (:1123-1124) + CrossEntropyLoss       */

@@ -8,7 +8,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libb2ddpbert.so")
-ABI_VERSION = 12
+ABI_VERSION = 13
 
 MAJOR_K, MAJOR_MN = 0, 1
 EPI_NONE, EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_DROPOUT_RESIDUAL, EPI_RESIDUAL, EPI_GELU_BWD = 0, 1, 2, 3, 4, 5
@@ -57,8 +57,8 @@ _SIGNATURES = {
     "b2_layernorm_bwd_accum": [vp, vp, vp, vp, vp, i64, i64, f32, vp, u32, vp, vp, vp, vp],
     "b2_colsum_finish": [vp, i32, i32, i64, vp, vp, vp, vp],
     "b2_colsum": [vp, i64, i64, i64, vp, vp, i64, vp],
-    "b2_attention_fwd": [vp, vp, i64, i64, i64, i64, f32, vp, u32, vp, vp, vp],
-    "b2_attention_bwd": [vp, vp, vp, vp, vp, i64, i64, i64, i64, f32, vp, u32, vp, vp, vp, vp],
+    "b2_attention_fwd": [vp, vp, i64, i64, i64, i64, f32, vp, u32, vp, vp, vp, vp],
+    "b2_attention_bwd": [vp, vp, vp, vp, vp, i64, i64, i64, i64, f32, vp, u32, vp, vp, vp, vp, vp],
     "b2_accum_finish": [vp, vp, vp, i64, i64, vp],
     "b2_head_fwd": [vp, i64, i64, i64, vp, vp, vp, vp, i64, f32, vp, u32, vp, vp, vp],
     "b2_ce_fwd_bwd": [vp, vp, i64, i64, vp, vp, vp],

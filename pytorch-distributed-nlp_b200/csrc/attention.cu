@@ -40,6 +40,9 @@ struct AttnParams {
   const __nv_bfloat16* ctx_in; const __nv_bfloat16* d_ctx;
   __nv_bfloat16* d_qkv; float* dq_accum;
   float* dbias;                   // optional fp32 [3*hidden]: += column sums of d_qkv (QKV bias gradient)
+  // optional (seq == 128, dropout on): the forward's dropout decisions, one 64-bit word per (b, h, query row, key
+  // half) -- written by the forward, read by the backward instead of regenerating Philox (38 % of its instructions)
+  unsigned long long* keep_bits;
 };
 
 // Sum v[j] over the 32 lanes for every j: 31 shuffles (butterfly with halving); lane l returns the total of column l.
@@ -365,6 +368,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 4) attention_fwd128_kernel(const 
   float l_loc = 0.f;
   uint8_t* sP = half ? sK : sQ;
   const int q_row = row;
+  unsigned long long kept = 0ull;   // keep decisions of this thread's 64 key columns
 #pragma unroll 1
   for (int c = 0; c < 4; ++c) {
     const uint32_t mbits = (c < 2 ? mb0 : mb1) >> ((c & 1) * 16);
@@ -384,6 +388,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 4) attention_fwd128_kernel(const 
       const unsigned long long idx =
           (((unsigned long long)(b * p.heads + h) * 128 + q_row) * 128) + half * 64 + c * 16 + g * 8;
       const uint32_t keep = dropout_keep8(drop, idx);
+      kept |= (unsigned long long)(keep & 0xffu) << (c * 16 + g * 8);
       float q8[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) q8[i] = ((keep >> i) & 1u) ? pr[g * 8 + i] * drop.scale : 0.f;
@@ -393,6 +398,8 @@ __global__ void __launch_bounds__(ATT_THREADS, 4) attention_fwd128_kernel(const 
       st_tile_chunk(sP, row, c * 2 + g, o);
     }
   }
+  if (p.keep_bits != nullptr)
+    p.keep_bits[(((size_t)b * p.heads + h) * 128 + q_row) * 2 + half] = kept;
   s_red[half * 128 + row] = l_loc;
   fence_proxy_async_smem();
   tc_fence_before();
@@ -577,6 +584,9 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_
                bf16_lo(a.w) * bf16_lo(g.w) + bf16_hi(a.w) * bf16_hi(g.w);
     }
     const float lse2 = p.lse[((size_t)b * p.heads + h) * p.seq + q_row] * kLog2e;
+    const bool have_bits = kOneQ && p.keep_bits != nullptr;
+    unsigned long long kept = ~0ull;
+    if (have_bits) kept = p.keep_bits[(((size_t)b * p.heads + h) * 128 + q_row) * 2 + half];
     __syncthreads();   // every thread has read its O row: P may overwrite the tile in the pass below
 
     mbar_wait(bar_s, ph_s);
@@ -594,7 +604,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_
       for (int g = 0; g < 4; ++g) {
         const unsigned long long idx =
             (((unsigned long long)(b * p.heads + h) * p.seq + q_row) * p.seq) + jb * 128 + cb + g * 8;
-        const uint32_t keep = dropout_keep8(drop, idx);
+        const uint32_t keep = have_bits ? (uint32_t)(kept >> (c * 32 + g * 8)) & 0xffu : dropout_keep8(drop, idx);
         float pd[8], ds[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
@@ -774,7 +784,7 @@ using namespace b2;
 
 extern "C" int32_t b2_attention_fwd(const void* qkv, const int64_t* attention_mask, int64_t batch, int64_t seq,
                                     int64_t heads, int64_t head_dim, float dropout_p, const void* rng_state,
-                                    uint32_t rng_site, void* ctx, float* lse, void* stream_) {
+                                    uint32_t rng_site, void* ctx, float* lse, uint64_t* keep_bits, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   B2_REQUIRE(qkv && ctx, "attention_fwd: null pointer");
   int32_t st = check_attn_shapes("attention_fwd", batch, seq, heads, head_dim);
@@ -790,6 +800,8 @@ extern "C" int32_t b2_attention_fwd(const void* qkv, const int64_t* attention_ma
   p.dropout_p = dropout_p; p.rng = (const unsigned long long*)rng_state; p.rng_site = rng_site;
   p.mask = (const long long*)attention_mask;
   p.ctx = (__nv_bfloat16*)ctx; p.lse = lse;
+  // the keep-bit cache exists for the seq == 128 kernel pair only (and only when there is dropout to remember)
+  p.keep_bits = (seq == 128 && dropout_p > 0.f && fwd128_enabled()) ? (unsigned long long*)keep_bits : nullptr;
   static bool attr = false;
   if (!attr) {
     B2_CUDA(cudaFuncSetAttribute(attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmem));
@@ -821,7 +833,7 @@ extern "C" int32_t b2_attention_fwd(const void* qkv, const int64_t* attention_ma
 extern "C" int32_t b2_attention_bwd(const void* qkv, const int64_t* attention_mask, const void* ctx, const void* d_ctx,
                                     const float* lse, int64_t batch, int64_t seq, int64_t heads, int64_t head_dim,
                                     float dropout_p, const void* rng_state, uint32_t rng_site, void* d_qkv,
-                                    float* dq_accum, float* dbias_accum, void* stream_) {
+                                    float* dq_accum, float* dbias_accum, const uint64_t* keep_bits, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   B2_REQUIRE(qkv && ctx && d_ctx && lse && d_qkv, "attention_bwd: null pointer");
   int32_t st = check_attn_shapes("attention_bwd", batch, seq, heads, head_dim);
@@ -851,6 +863,7 @@ extern "C" int32_t b2_attention_bwd(const void* qkv, const int64_t* attention_ma
   B2_REQUIRE(dbias_accum == nullptr || seq == 128,
              "attention_bwd: the fused QKV bias gradient covers seq == 128 (longer sequences: use b2_colsum)");
   p.dbias = dbias_accum;
+  p.keep_bits = (seq == 128 && dropout_p > 0.f && fwd128_enabled()) ? (unsigned long long*)keep_bits : nullptr;
   if (p.dq_accum) B2_CUDA(cudaMemsetAsync(p.dq_accum, 0, (size_t)tokens * hidden * 4, stream));
   static bool attr = false;
   if (!attr) {

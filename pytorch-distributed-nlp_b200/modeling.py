@@ -416,6 +416,9 @@ class _Engine:
         # optimizer-state round trips (one 4 KB staging tile per warp) keep too few bytes in flight; see DESIGN.md 4.3
         self.fused_adamw = os.environ.get("B2_FUSED_ADAMW", "0") == "1"
         self.fused_adamw_active = False
+        # cache of the forward's attention-dropout decisions for the backward: measured neutral (3.96 vs 3.95 ms/step --
+        # the backward is latency-, not Philox-bound), so off by default; the kernels and tests keep the path alive
+        self.attn_keep_bits = os.environ.get("B2_ATTN_KEEP_BITS", "0") == "1"
         self.use_wgrad_stream = os.environ.get("B2_WGRAD_STREAM", "1") != "0"
         # fp32 accumulators for the bias gradients that kernels produce as a side effect of their epilogues (QKV bias
         # from attention backward, intermediate bias from the GELU' dgrad): per layer [3H | I]; one finishing launch
@@ -483,7 +486,11 @@ class _Engine:
             "emb_out": e(M, H), "emb_pre": e(M, H), "emb_mean": e(M, dtype=f32), "emb_rstd": e(M, dtype=f32),
             "ids32": e(M, dtype=torch.int32), "tt32": e(M, dtype=torch.int32),
             "layers": [
-                {"qkv": e(M, 3 * H), "ctx": e(M, H), "lse": e(B * self.heads * S, dtype=f32), "z1": e(M, H),
+                {"qkv": e(M, 3 * H), "ctx": e(M, H), "lse": e(B * self.heads * S, dtype=f32),
+                 # attention-dropout decisions of the forward, 1 bit per (b, h, q, k): read back by the backward
+                 "keep": (e(B * self.heads * S * (S // 64), dtype=torch.int64)
+                          if (S == 128 and self.attn_keep_bits) else None),
+                 "z1": e(M, H),
                  "x1": e(M, H), "mean1": e(M, dtype=f32), "rstd1": e(M, dtype=f32), "u": e(M, I), "h": e(M, I),
                  "z2": e(M, H), "x2": e(M, H), "mean2": e(M, dtype=f32), "rstd2": e(M, dtype=f32)}
                 for _ in range(nl)],
@@ -576,7 +583,7 @@ class _Engine:
             self.gemm(M, 3 * H, H, x.data_ptr(), H, KM, w(pre + "attention.self.query.weight"), H, KM,
                       a["qkv"].data_ptr(), 3 * H, L.EPI_BIAS, bias=w(pre + "attention.self.query.bias"))
             L.call("b2_attention_fwd", a["qkv"].data_ptr(), L.ptr(mask), B, S, self.heads, 64, p_a, rng, 1 + 3 * l,
-                   a["ctx"].data_ptr(), a["lse"].data_ptr(), s)
+                   a["ctx"].data_ptr(), a["lse"].data_ptr(), L.ptr(a["keep"]) if need_backward else None, s)
             self.gemm(M, H, H, a["ctx"].data_ptr(), H, KM, w(pre + "attention.output.dense.weight"), H, KM,
                       a["z1"].data_ptr(), H, L.EPI_BIAS_DROPOUT_RESIDUAL, bias=w(pre + "attention.output.dense.bias"),
                       aux_in=x.data_ptr(), ld_aux_in=H, p=p_h, site=2 + 3 * l)
@@ -750,7 +757,7 @@ class _Engine:
             # --- BertSelfAttention
             L.call("b2_attention_bwd", a["qkv"].data_ptr(), L.ptr(mask), a["ctx"].data_ptr(), ws["dctx"].data_ptr(),
                    a["lse"].data_ptr(), B, S, self.heads, 64, p_a, rng, 1 + 3 * l, dqkv.data_ptr(),
-                   L.ptr(ws["dq_accum"]), acc_l if S == 128 else None, s)
+                   L.ptr(ws["dq_accum"]), acc_l if S == 128 else None, L.ptr(a["keep"]), s)
             if S != 128:   # long-sequence parity configs: separate column-sum pass into the same accumulator slot
                 L.call("b2_colsum", dqkv.data_ptr(), M, 3 * H, 3 * H, g(pre + "attention.self.query.bias"),
                        scratch, scratch_bytes, s)

@@ -185,8 +185,12 @@ def _attn_ref(qkv, mask, B, Sq, nh, keep=None, p=0.0):
     return (pr @ v).transpose(1, 2).reshape(B * Sq, H), lse
 
 
-@pytest.mark.parametrize("Sq,masked,p", [(128, False, 0.0), (128, True, 0.1), (256, True, 0.0), (512, True, 0.1)])
-def test_attention_fwd_bwd(cuda_dev, Sq, masked, p):
+@pytest.mark.parametrize("Sq,masked,p,cache", [(128, False, 0.0, False), (128, True, 0.1, False), (128, True, 0.1, True),
+                                               (128, False, 0.1, True), (256, True, 0.0, False),
+                                               (512, True, 0.1, True)])
+def test_attention_fwd_bwd(cuda_dev, Sq, masked, p, cache):
+    """cache: hand both calls a keep-bit buffer (the forward's dropout decisions, re-read by the backward at seq 128;
+    ignored at other lengths) -- results must not depend on it"""
     dev = cuda_dev
     B, nh = 3, 4
     H = nh * 64
@@ -200,8 +204,9 @@ def test_attention_fwd_bwd(cuda_dev, Sq, masked, p):
     rs = rng_state(dev)
     ctx = torch.empty(M, H, dtype=bf, device=dev)
     lse = torch.empty(B * nh * Sq, dtype=torch.float32, device=dev)
+    kb = torch.zeros(B * nh * Sq * (Sq // 64), dtype=torch.int64, device=dev) if cache else None
     L.call("b2_attention_fwd", qkv.data_ptr(), L.ptr(mask), B, Sq, nh, 64, p, rs.data_ptr(), 4, ctx.data_ptr(),
-           lse.data_ptr(), S())
+           lse.data_ptr(), L.ptr(kb), S())
     torch.cuda.synchronize()
     keep = None
     if p > 0:
@@ -216,8 +221,12 @@ def test_attention_fwd_bwd(cuda_dev, Sq, masked, p):
     dq_acc = torch.empty(M, H, dtype=torch.float32, device=dev) if Sq > 128 else None
     dbias = torch.zeros(3 * H, dtype=torch.float32, device=dev) if Sq == 128 else None
     L.call("b2_attention_bwd", qkv.data_ptr(), L.ptr(mask), ctx.data_ptr(), dctx.data_ptr(), lse.data_ptr(), B, Sq,
-           nh, 64, p, rs.data_ptr(), 4, dqkv.data_ptr(), L.ptr(dq_acc), L.ptr(dbias), S())
+           nh, 64, p, rs.data_ptr(), 4, dqkv.data_ptr(), L.ptr(dq_acc), L.ptr(dbias), L.ptr(kb), S())
     torch.cuda.synchronize()
+    if cache and Sq == 128 and p > 0:   # the cached bits are exactly the Philox decisions
+        bits = kb.view(B, nh, Sq, 2).cpu().numpy().astype("uint64")
+        got = ((bits[..., None] >> np.arange(64, dtype="uint64")) & np.uint64(1)).reshape(B, nh, Sq, 128).astype(bool)
+        assert np.array_equal(got, keep.cpu().numpy().astype(bool))
     if dbias is not None:   # fused QKV bias gradient == column sums of what was written
         assert rel_l2(dbias, dqkv.float().sum(0)) < 1e-4
     ref.backward(dctx.float())
@@ -229,9 +238,9 @@ def test_attention_fwd_bwd(cuda_dev, Sq, masked, p):
 def test_attention_rejects_bad_shapes(cuda_dev):
     qkv = rnd((100, 768), cuda_dev)
     with pytest.raises(RuntimeError, match="multiple of 128"):
-        L.call("b2_attention_fwd", qkv.data_ptr(), None, 1, 100, 4, 64, 0.0, None, 0, qkv.data_ptr(), None, S())
+        L.call("b2_attention_fwd", qkv.data_ptr(), None, 1, 100, 4, 64, 0.0, None, 0, qkv.data_ptr(), None, None, S())
     with pytest.raises(RuntimeError, match="head_dim"):
-        L.call("b2_attention_fwd", qkv.data_ptr(), None, 1, 128, 4, 32, 0.0, None, 0, qkv.data_ptr(), None, S())
+        L.call("b2_attention_fwd", qkv.data_ptr(), None, 1, 128, 4, 32, 0.0, None, 0, qkv.data_ptr(), None, None, S())
 
 
 @pytest.mark.parametrize("p", [0.0, 0.1])
