@@ -131,9 +131,9 @@ def run_reference(args):
 
 
 def time_gemm_family(eng, cfg, B, S, peaks):
-    """Live roofline of the dominant kernel family: every GEMM shape of one encoder-layer step (4 fwd, 4 dgrad,
-    4 wgrad), each timed as a loop of launches between two CUDA events on the launching stream, operand sets rotated
-    so that the loop's footprint exceeds L2."""
+    """Live roofline of the dominant kernel family: every GEMM launch of one encoder-layer step as the engine issues it
+    (4 forward, 4 dgrad, the grouped launch of the 4 weight gradients), each timed as a loop of launches between two
+    CUDA events on the launching stream, operand sets rotated so that the loop's footprint exceeds L2."""
     import torch
     from pytorch_distributed_nlp_b200 import _lib as L
     H, I, M = cfg.hidden_size, cfg.intermediate_size, B * S
@@ -150,14 +150,35 @@ def time_gemm_family(eng, cfg, B, S, peaks):
         ("dgrad ffn1   [M,H](fp32)+=[M,I]x[I,H] split-K in place", M, H, I, KM, MN, L.EPI_ACCUM_F32),
         ("dgrad attn-o [M,H]<-[M,H]x[H,H]", M, H, H, KM, MN, L.EPI_NONE),
         ("dgrad qkv    [M,H](fp32)+=[M,3H]x[3H,H] split-K in place", M, H, 3 * H, KM, MN, L.EPI_ACCUM_F32),
-        ("wgrad ffn2   [H,I]<-[M,H]^Tx[M,I]", H, I, M, MN, MN, L.EPI_NONE),
-        ("wgrad ffn1   [I,H]<-[M,I]^Tx[M,H]", I, H, M, MN, MN, L.EPI_NONE),
-        ("wgrad attn-o [H,H]<-[M,H]^Tx[M,H]", H, H, M, MN, MN, L.EPI_NONE),
-        ("wgrad qkv    [3H,H]<-[M,3H]^Tx[M,H]", 3 * H, H, M, MN, MN, L.EPI_NONE),
     ]
+    # the four weight gradients of a layer: ONE grouped launch in the step (b2_gemm_bf16_grouped), timed as such
+    wgrads = [("ffn2 [H,I]", H, I), ("ffn1 [I,H]", I, H), ("attn-o [H,H]", H, H), ("qkv [3H,H]", 3 * H, H)]
     F32_OUT = (L.EPI_RESIDUAL_F32, L.EPI_ACCUM_F32)
     detail, tot_flops, tot_ms = [], 0.0, 0.0
-    stream = torch.cuda.current_stream(dev)
+
+    def timed_loop(launch_one, sets_):
+        """mean device time of one launch: the loop over REP x len(sets_) launches is captured once (the launches go
+        through Python/ctypes, ~10 us of host time each) so that the events bracket device time"""
+        for s_ in sets_:
+            launch_one(s_)
+        torch.cuda.synchronize(dev)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for _ in range(REP):
+                for s_ in sets_:
+                    launch_one(s_)
+        g.replay()
+        torch.cuda.synchronize(dev)
+        st_ = torch.cuda.current_stream(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(st_)
+        g.replay()
+        e1.record(st_)
+        torch.cuda.synchronize(dev)
+        ms_ = e0.elapsed_time(e1) / (REP * len(sets_))
+        del g
+        return ms_
+
     for (name, m, n, k, am, bm, epi) in shapes:
         a_shape = (m, k) if am == KM else (k, m)
         b_shape = (n, k) if bm == KM else (k, n)
@@ -182,31 +203,33 @@ def time_gemm_family(eng, cfg, B, S, peaks):
             eng.gemm(m, n, k, s["A"].data_ptr(), a_shape[1], am, s["B"].data_ptr(), b_shape[1], bm,
                      s["D"].data_ptr(), n, epi, split=(am == MN), **kw)
 
-        for s in sets:
-            launch(s)
-        torch.cuda.synchronize(dev)
-        # the launches go through Python/ctypes (~10 us of host time each): capture the loop once so that the events
-        # bracket device time, not host launch latency
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
-            for _ in range(REP):
-                for s in sets:
-                    launch(s)
-        g.replay()
-        torch.cuda.synchronize(dev)
-        stream = torch.cuda.current_stream(dev)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        g.replay()
-        e1.record(stream)
-        torch.cuda.synchronize(dev)
-        ms = e0.elapsed_time(e1) / (REP * NSET)
-        del g
+        ms = timed_loop(launch, sets)
         flops = 2.0 * m * n * k
         detail.append({"gemm": name, "us": round(ms * 1e3, 2), "tflops": round(flops / ms / 1e9, 1)})
         tot_flops += flops
         tot_ms += ms
         del sets
+
+    gsets = []
+    for _ in range(NSET):
+        gsets.append([dict(A=torch.randn(M, m, device=dev).to(bf), B=(torch.randn(M, n, device=dev) * 0.05).to(bf),
+                           D=torch.zeros(m, n, dtype=bf, device=dev)) for (_nm, m, n) in wgrads])
+
+    def launch_grouped(s):
+        probs = []
+        for (_nm, m, n), t in zip(wgrads, s):
+            eng.gemm(m, n, M, t["A"].data_ptr(), m, MN, t["B"].data_ptr(), n, MN, t["D"].data_ptr(), n, L.EPI_NONE,
+                     split=True, defer=probs)
+        probs.sort(key=lambda a: -(a.M * a.N))
+        eng.gemm_grouped(probs, eng.stream())
+
+    ms = timed_loop(launch_grouped, gsets)
+    flops = sum(2.0 * m * n * M for (_nm, m, n) in wgrads)
+    detail.append({"gemm": "wgrad x4 grouped (ffn2, ffn1, qkv, attn-o) [out,in]<-[M,out]^Tx[M,in], one launch",
+                   "us": round(ms * 1e3, 2), "tflops": round(flops / ms / 1e9, 1)})
+    tot_flops += flops
+    tot_ms += ms
+    del gsets
     achieved = tot_flops / tot_ms / 1e9
     peak = peaks["bf16_tflops"]
     traffic = None
@@ -220,7 +243,8 @@ def time_gemm_family(eng, cfg, B, S, peaks):
             traffic = None
     return {"bound": "tensor", "achieved": round(achieved, 1), "peak": peak, "unit": "TFLOP/s",
             "frac": round(achieved / peak, 4), "traffic": traffic, "traffic_detail": traffic_detail,
-            "kernel": "gemm_bf16_kernel (tcgen05/TMA), 12 GEMM shapes of one encoder-layer step, flop-weighted",
+            "kernel": "gemm2_bf16_kernel / gemm2_grouped_tn_kernel (tcgen05 cta_group::2 + TMA): the 9 GEMM launches of one "
+                      "encoder-layer step (4 forward, 4 dgrad, 1 grouped weight-gradient), flop-weighted",
             "peak_source": peaks["source"] + ", burst cuBLAS bf16 (kernels timed in isolation)",
             "detail": detail}
 
