@@ -20,19 +20,32 @@ def _hf_state(cfg, seed=123):
     return hf, {k: v.detach().clone() for k, v in hf.named_parameters()}
 
 
+# the oracle is pinned on the shapes every GPU parity test uses: the tiny config, BASELINE config B's sequence length
+# (512, padded tail blocks) and config C's widths (bert-large: H 1024, 16 heads, I 4096), at reduced depth
+_SHAPES = {
+    "tiny": (dict(), 4, 128),
+    "config-B-shape": (dict(vocab_size=2000, hidden_size=768, num_hidden_layers=1, num_attention_heads=12,
+                            intermediate_size=3072, max_position_embeddings=512), 2, 512),
+    "config-C-shape": (dict(vocab_size=2000, hidden_size=1024, num_hidden_layers=1, num_attention_heads=16,
+                            intermediate_size=4096, max_position_embeddings=512), 2, 128),
+}
+
+
 @pytest.mark.parametrize("padded", [False, True])
-def test_oracle_equals_hf_forward_backward(padded):
-    cfg = tiny_config(hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0)
+@pytest.mark.parametrize("shape", sorted(_SHAPES))
+def test_oracle_equals_hf_forward_backward(padded, shape):
+    kw, batch, seq = _SHAPES[shape]
+    cfg = tiny_config(hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0, **kw)
     hf, state = _hf_state(cfg)
-    b = bert_ref.synthetic_batch(cfg, 4, 128, 1000, padded=padded)
+    b = bert_ref.synthetic_batch(cfg, batch, seq, 1000, padded=padded)
     out = hf(input_ids=b["input_ids"], token_type_ids=b["token_type_ids"], attention_mask=b["attention_mask"],
              labels=b["label"])
     out[0].backward()
     loss, logits, grads = bert_ref.loss_and_grads(state, cfg, b)
-    assert abs(float(out[0].detach()) - float(loss)) < 1e-6
-    assert float((out[1].detach() - logits).abs().max()) < 1e-6
+    assert abs(float(out[0].detach()) - float(loss)) < 2e-6
+    assert float((out[1].detach() - logits).abs().max()) < 2e-6
     for k, p in hf.named_parameters():
-        assert float((grads[k] - p.grad).abs().max()) < 2e-6, k
+        assert float((grads[k] - p.grad).abs().max()) < 2e-6 + 1e-5 * float(p.grad.abs().max()), k
     # reference comment at multi-gpu-distributed-cls.py:168: criterion(logits, label) == output[0]
     assert abs(float(torch.nn.functional.cross_entropy(logits, b["label"])) - float(loss)) < 1e-7
 
