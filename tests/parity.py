@@ -38,21 +38,12 @@ def full_config(**kw):
 
 
 # ---- Philox4x32-10 replica (csrc/common.cuh: philox4x32_10 / dropout_keep8) -------------------------------------------
-def philox_keep_mask(n_elements, seed, step, site, p):
-    """Boolean keep mask for `n_elements` (multiple of 8) consecutive elements of dropout site `site`."""
-    assert n_elements % 8 == 0
-    if p <= 0:
-        return np.ones(n_elements, dtype=bool)
-    thresh = int(p * 65536.0 + 0.5)
-    g = np.arange(n_elements // 8, dtype=np.uint64)
+def philox4x32_10(c0, c1, c2, c3, k0, k1):
+    """Salmon et al., "Parallel random numbers: as easy as 1, 2, 3" (SC'11): counters are uint64 arrays holding 32-bit
+    values, keys python ints.  tests/test_host.py checks it against the published known-answer vectors."""
     M0, M1 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57)
     W0, W1 = 0x9E3779B9, 0xBB67AE85
     mask32 = np.uint64(0xFFFFFFFF)
-    c0 = g & mask32
-    c1 = g >> np.uint64(32)
-    c2 = np.full_like(g, site & 0xFFFFFFFF)
-    c3 = np.full_like(g, step & 0xFFFFFFFF)
-    k0, k1 = seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF
     for _ in range(10):
         p0 = M0 * c0
         p1 = M1 * c2
@@ -63,6 +54,19 @@ def philox_keep_mask(n_elements, seed, step, site, p):
         c0, c1, c2, c3 = n0, lo1, n2, lo0
         k0 = (k0 + W0) & 0xFFFFFFFF
         k1 = (k1 + W1) & 0xFFFFFFFF
+    return c0, c1, c2, c3
+
+
+def philox_keep_mask(n_elements, seed, step, site, p):
+    """Boolean keep mask for `n_elements` (multiple of 8) consecutive elements of dropout site `site`."""
+    assert n_elements % 8 == 0
+    if p <= 0:
+        return np.ones(n_elements, dtype=bool)
+    thresh = int(p * 65536.0 + 0.5)
+    g = np.arange(n_elements // 8, dtype=np.uint64)
+    mask32 = np.uint64(0xFFFFFFFF)
+    c0, c1, c2, c3 = philox4x32_10(g & mask32, g >> np.uint64(32), np.full_like(g, site & 0xFFFFFFFF),
+                                   np.full_like(g, step & 0xFFFFFFFF), seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
     lanes = np.stack([c0 & np.uint64(0xFFFF), c0 >> np.uint64(16), c1 & np.uint64(0xFFFF), c1 >> np.uint64(16),
                       c2 & np.uint64(0xFFFF), c2 >> np.uint64(16), c3 & np.uint64(0xFFFF), c3 >> np.uint64(16)],
                      axis=1)

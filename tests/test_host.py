@@ -147,3 +147,21 @@ def test_package_synthetic_batch_is_the_oracles():
         assert set(a) == set(b) == {"input_ids", "token_type_ids", "attention_mask", "label"}
         for k in a:
             assert a[k].dtype == torch.int64 and torch.equal(a[k], b[k])
+
+
+def test_philox_replica_known_answers():
+    """The numpy Philox4x32-10 that the GPU dropout masks are compared with (tests/parity.py) reproduces the
+    known-answer vectors published with Random123 (kat_vectors: philox4x32, 10 rounds) -- so "the kernels' masks equal
+    the replica's" (asserted bit for bit in the -m gpu tests) means "the kernels run the published generator"."""
+    import numpy as np
+    from parity import philox4x32_10
+    kat = [
+        ((0x00000000,) * 4, (0x00000000,) * 2, (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+        ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+        ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
+         (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1)),
+    ]
+    for ctr, key, want in kat:
+        c = [np.array([v], dtype=np.uint64) for v in ctr]
+        out = philox4x32_10(c[0], c[1], c[2], c[3], key[0], key[1])
+        assert tuple(int(o[0]) for o in out) == want, (ctr, [hex(int(o[0])) for o in out])
