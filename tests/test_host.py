@@ -224,3 +224,42 @@ def test_fused_adamw_skip_flags_cover_exactly_the_encoder_matrices():
     assert torch.equal(flags, want)
     assert int(flags.sum()) * 8 == cfg.num_hidden_layers * (4 * cfg.hidden_size ** 2 +
                                                           2 * cfg.hidden_size * cfg.intermediate_size)
+
+
+def test_sass_carries_tcgen05_tmem_and_tma():
+    """what the compiler actually emitted for sm_100a (cuobjdump -sass of the in-tree library): the GEMM and attention
+    kernels issue tcgen05.mma (UTCHMMA), drain TMEM with tcgen05.ld (LDTM), commit to mbarriers (UTCBAR), allocate TMEM
+    (UTCATOMSWS) and move tiles with TMA (UTMALDG; UTMASTG for the attention stores); the CTA-pair kernels synchronise
+    the cluster (UCGABAR_*).  mma.sync / wgmma-era mnemonics (HMMA) must not appear in them."""
+    import shutil
+    import subprocess
+    exe = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(exe):
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run([exe, "-sass", L.LIB_PATH], capture_output=True, text=True, timeout=600).stdout
+    per_fn, cur = {}, None
+    for line in sass.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            cur = per_fn.setdefault(m.group(1), set())
+            continue
+        m = re.match(r"\s+/\*[0-9a-f]+\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_]+)", line)
+        if m and cur is not None:
+            cur.add(m.group(1))
+
+    def ops(fragment):
+        hit = [v for k, v in per_fn.items() if fragment in k]
+        assert hit, "no kernel matching %s in the library" % fragment
+        return hit
+
+    for frag in ("gemm2_bf16_kernel", "gemm_bf16_kernel", "gemm2_grouped_tn_kernel"):
+        for o in ops(frag):
+            assert {"UTCHMMA", "UTMALDG", "LDTM", "UTCBAR", "UTCATOMSWS"} <= o, (frag, sorted(o))
+            assert "HMMA" not in o
+    for frag in ("gemm2_bf16_kernel", "gemm2_grouped_tn_kernel"):
+        for o in ops(frag):
+            assert "UCGABAR_ARV" in o and "UCGABAR_WAIT" in o          # cta_group::2 pairs
+    for frag in ("attention_fwd_kernel", "attention_fwd128_kernel", "attention_bwd_kernel"):
+        for o in ops(frag):
+            assert {"UTCHMMA", "UTMALDG", "UTMASTG", "LDTM", "UTCBAR"} <= o, (frag, sorted(o))
+            assert "HMMA" not in o
