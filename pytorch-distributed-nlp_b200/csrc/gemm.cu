@@ -4,19 +4,21 @@
 // BertOutput (transformers modeling_bert.py:179-181, :295, :340, :353) and their autograd dgrad / wgrad
 // twins.
 //
-// Two kernels share one epilogue:
+// Three kernels share one epilogue:
 //   gemm2_bf16_kernel  CTA PAIR (cluster of 2, tcgen05 cta_group::2): the pair owns a 256 x BN output tile, each
 //                      CTA stages its own 128 A rows and HALF of the B tile, the leader's single thread issues
 //                      256 x BN x 16 MMAs that read both halves.  Per flop this moves 1/3 fewer bytes out of L2 and
 //                      through shared memory than a 128 x 256 single-CTA tile -- the first profile showed the
 //                      single-CTA kernel pinned at ~10 TB/s of L2->SM traffic (650 TF/s), not at the tensor pipe.
+//   gemm2_grouped_tn_kernel  the same CTA-pair machinery over a table of up to four TN problems: the weight gradients
+//                      of one encoder layer as ONE persistent launch (b2_gemm_bf16_grouped)
 //   gemm_bf16_kernel   single CTA, 128 x BN (BN 128/256): small or oddly shaped problems.
 // Common structure (persistent, warp specialised, one CTA per SM):
 //   warp 0      TMA producer      global -> 128B-swizzled smem ring (full/empty mbarriers)
 //   warp 1      MMA issuer        one lane issues tcgen05.mma, commits to mbarriers
 //   warp 2      TMEM allocator    2 accumulator stages so tile i+1's MMAs overlap tile i's epilogue
-//   warps 4-11  epilogue          tcgen05.ld -> bias / GELU / dropout / residual -> smem staging -> coalesced stores
-//                                 (gemm_epilogue.cuh)
+//   warps 4-19  epilogue          tcgen05.ld -> bias / GELU / dropout / residual -> smem staging -> coalesced stores
+//                                 (gemm_epilogue.cuh); 16 warps by default, 8 (warps 4-11) with B2_GEMM_EPI_WARPS=8
 // Operand layouts are expressed only through the TMA box + UMMA descriptor (no transposes in HBM):
 //   NT  A[M,K] K-major,  B[N,K] K-major   (forward:  y = x W^T)
 //   NN  A[M,K] K-major,  B[K,N] MN-major  (dgrad:    dx = dy W)
