@@ -10,7 +10,10 @@
 // 32*(warp%4)..+31, any columns), which halves the per-row softmax / dS work that bounded the 128-thread version.
 // Tiles move HBM->smem by TMA straight out of the packed [tokens, 3*hidden] QKV activation (128B swizzle);
 // the same smem tile serves as a K-major operand for one product and as an MN-major operand for another
-// (e.g. dO is A of dP = dO V^T and B of dV = P^T dO), so nothing is ever transposed in memory.
+// (e.g. dO is A of dP = dO V^T and B of dV = P^T dO), so nothing is ever transposed in memory.  Results leave the
+// same way: the context tile, dQ, dK and dV are written into operand tiles the last MMAs have released and stored
+// with TMA; the key-padding mask is a 64-bit register pair per thread.  Kernels: attention_fwd128_kernel (seq 128,
+// 4 CTAs/SM), attention_fwd_kernel (any seq <= 512, online softmax), attention_bwd_kernel<kOneQ>.
 #include "common.cuh"
 #include "../../include/b2_ddp_bert.h"
 

@@ -1,10 +1,12 @@
 // BertEmbeddings forward / backward (SP/transformers/models/bert/modeling_bert.py:72-112).
 // forward : word + position + token-type gather, add, LayerNorm, dropout, one warp per token, one pass over HBM.
 // backward: LayerNorm backward, then deterministic scatter-adds:
-//   word rows      one "owner" CTA per touched vocabulary row (lowest token index wins an atomicMin) sums all of
-//                  that row's occurrences in token order -> no float atomics, bit-reproducible;
-//   position rows  row s = sum over the batch of dx[b, s, :];
-//   type rows      filtered column sums.
+//   word rows      keyed by the "owner" token of each touched vocabulary row (lowest token index wins an atomicMin):
+//                  fast path = every token adds its row into fp32 acc[owner] (vector reductions at L2), the owner
+//                  converts; fallback (scratch too small) = the owner CTA scans the later tokens in order
+//                  (no float atomics, bit-reproducible);
+//   position rows  row s = sum over the batch of dx[b, s, :]  } one pass (embed_pos_type_kernel) on the fast path,
+//   type rows      filtered column sums                        } separate kernels on the fallback.
 #include "common.cuh"
 #include "layernorm.cuh"
 #include "../../include/b2_ddp_bert.h"

@@ -1,5 +1,6 @@
-// LayerNorm forward / backward and column sums: HBM-bound, one warp per row, 16-byte vector accesses,
-// fp32 statistics.  Replaces ATen native_layer_norm (+backward) issued by BertSelfOutput / BertOutput
+// LayerNorm forward / backward and column sums: HBM-bound, 16-byte vector accesses, fp32 statistics.  Forward and the
+// generic backward: one warp per row.  The training engine's backward (layernorm_bwd_pair_kernel): a warp PAIR per
+// row with cp.async operand rings, column sums added straight into caller-owned fp32 accumulators.  Replaces ATen native_layer_norm (+backward) issued by BertSelfOutput / BertOutput
 // (SP/transformers/models/bert/modeling_bert.py:297, :355) and the bias-gradient reductions autograd runs
 // for the dense layers.
 #include "common.cuh"
