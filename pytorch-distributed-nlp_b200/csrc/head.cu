@@ -88,20 +88,45 @@ __global__ void __launch_bounds__(256) ce_fwd_bwd_kernel(const float* __restrict
                                                         float* __restrict__ loss, float* __restrict__ dlogits) {
   pdl_wait();               // PDL: predecessors complete + visible before any global access
   pdl_launch_dependents();  // let the next kernel in the stream begin launching
+  // torch.nn.CrossEntropyLoss semantics (multi-gpu-distributed-cls.py:343, defaults): labels equal to ignore_index
+  // (-100) contribute nothing and the mean runs over the other samples; any other label outside [0, C) is an error
+  // (torch raises a device-side assert: here a message + trap)
   __shared__ float red[256];
+  __shared__ int cnt[256];
+  int valid = 0;
+  for (int b = threadIdx.x; b < batch; b += blockDim.x) {
+    const long long y = labels[b];
+    if (y == -100) continue;
+    if (y < 0 || y >= C) {
+      printf("b2 ce_fwd_bwd: label %lld of sample %d is outside [0, %d) (and is not ignore_index -100)\n", y, b, C);
+      __trap();
+    }
+    ++valid;
+  }
+  cnt[threadIdx.x] = valid;
+  __syncthreads();
+  for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+    if ((int)threadIdx.x < s) cnt[threadIdx.x] += cnt[threadIdx.x + s];
+    __syncthreads();
+  }
+  const int n_valid = cnt[0];
+  const float inv = n_valid > 0 ? 1.0f / (float)n_valid : 0.f;
   float local = 0.f;
   for (int b = threadIdx.x; b < batch; b += blockDim.x) {
     const float* z = logits + (size_t)b * C;
+    const long long y = labels[b];
+    if (y == -100) {
+      if (dlogits != nullptr)
+        for (int c = 0; c < C; ++c) dlogits[(size_t)b * C + c] = 0.f;
+      continue;
+    }
     float mx = -INFINITY;
     for (int c = 0; c < C; ++c) mx = fmaxf(mx, z[c]);
     float se = 0.f;
     for (int c = 0; c < C; ++c) se += expf(z[c] - mx);
     const float lse = mx + logf(se);
-    long long y = labels[b];
-    y = y < 0 ? 0 : (y >= C ? C - 1 : y);
     local += lse - z[y];
     if (dlogits != nullptr) {
-      const float inv = 1.0f / (float)batch;
       for (int c = 0; c < C; ++c)
         dlogits[(size_t)b * C + c] = (expf(z[c] - lse) - (c == (int)y ? 1.f : 0.f)) * inv;
     }
@@ -112,7 +137,8 @@ __global__ void __launch_bounds__(256) ce_fwd_bwd_kernel(const float* __restrict
     if ((int)threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
     __syncthreads();
   }
-  if (threadIdx.x == 0) *loss = red[0] / (float)batch;
+  // all samples ignored: torch returns nan (0 / 0)
+  if (threadIdx.x == 0) *loss = n_valid > 0 ? red[0] * inv : __int_as_float(0x7fc00000);
 }
 
 // ---- backward ----

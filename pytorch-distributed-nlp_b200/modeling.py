@@ -191,11 +191,19 @@ class _StepFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, d_logits, d_loss):
-        eng = ctx.model._engine
+        model = ctx.model
+        eng = model._engine
         if d_logits is None and (d_loss is None or not ctx.has_loss):
             raise RuntimeError("backward reached the model without any gradient")
+        if model._optimizer is not None:
+            # gradients are OVERWRITTEN by every backward (bf16 bucket space, zero_grad is a no-op): a second backward
+            # before optimizer.step() would silently drop the first one's gradients where torch would accumulate
+            if model._grads_live:
+                raise RuntimeError("backward() called twice without optimizer.step() in between: gradient "
+                                   "accumulation is not supported on this path (gradients are overwritten, not summed)")
+            model._grads_live = True
         eng.backward(d_logits, d_loss if ctx.has_loss else None)
-        ctx.model._notify_backward_done()
+        model._notify_backward_done()
         # Gradients live in the engine's bf16 bucket space, not in `.grad`.  The anchor (classifier.bias) gets its
         # true gradient as a 6-float fp32 probe: it is the column sum of d_logits, so an inf/nan anywhere upstream
         # of the model shows up in it -- which is what torch.cuda.amp.GradScaler's inf check needs to see.
@@ -203,7 +211,10 @@ class _StepFn(torch.autograd.Function):
         n = 1
         for d in shape:
             n *= d
-        return eng.grads[off:off + n].float().view(shape), None, None, None, None, None
+        probe = eng.grads[off:off + n].float().view(shape)
+        if model._ddp is not None:
+            probe = model._ddp.consensus_probe(probe)
+        return probe, None, None, None, None, None
 
 
 class BertForSequenceClassification(nn.Module):
@@ -226,6 +237,7 @@ class BertForSequenceClassification(nn.Module):
         self._engine = None
         self._optimizer = None
         self._ddp = None
+        self._grads_live = False     # an eager backward has produced gradients no optimizer.step() has consumed yet
 
     # ---- module skeleton reproducing HF parameter paths -------------------------------------------------------
     def _build_skeleton(self):
@@ -326,6 +338,17 @@ class BertForSequenceClassification(nn.Module):
         else:
             self._engine = None
         return self
+
+    def _rebind_flat(self, new_flat):
+        """moves the fp32 masters into `new_flat` (same size; e.g. the DDP wrapper's peer-visible buffer) and re-points
+        every nn.Parameter view at it"""
+        if new_flat.dtype != torch.float32 or new_flat.numel() != self._flat.numel():
+            raise ValueError("_rebind_flat: need an fp32 buffer of %d elements" % self._flat.numel())
+        new_flat.copy_(self._flat)
+        self._flat = new_flat
+        for name, p in self._params_by_name.items():
+            off, shape = self._layout.entries[name]
+            p.data = self._flat[off:off + p.numel()].view(shape)
 
     # ---- state dict -----------------------------------------------------------------------------------------------
     def load_state_dict(self, state_dict, strict=True, assign=False):

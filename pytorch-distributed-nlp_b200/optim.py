@@ -185,6 +185,7 @@ class AdamW(torch.optim.Optimizer):
                         self.update_range(b0, e0, 1, 0, [eng.grads.data_ptr()], [eng.shadow.data_ptr()], s)
             self._pending = set()
             self.advance(s)
+        model._grads_live = False
         # the inf-check probe has served its purpose (GradScaler reads it before calling step); the -amp scripts never
         # call zero_grad, so drop it here or it would accumulate
         model._params_by_name["classifier.bias"].grad = None

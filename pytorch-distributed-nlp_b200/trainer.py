@@ -182,7 +182,7 @@ class FusedEvalStep(_StagedGraphStep):
 class Trainer:
     def __init__(self, args, config, model, criterion, optimizer):
         self.args = args
-        self.config = config,
+        self.config = config          # (the reference's `self.config = config,` stores a 1-tuple by accident, :121)
         self.model = model
         self.criterion = criterion
         self.optimizer = optimizer
@@ -293,17 +293,17 @@ class Trainer:
                             print("【dev】 loss：{:.6f} accuracy：{:.4f}".format(float(loss), accuracy))
                         if improved:
                             best_acc = accuracy
-                            sd = self.model.state_dict()  # collective under DDP: every rank takes part
                             if self.args.local_rank == 0:
                                 print("【best accuracy】 {:.4f}".format(best_acc))
-                                torch.save(sd, self.args.ckpt_path)
+                                # rank 0 alone, as in the reference [:190-192]: under DDP state_dict() pulls the fp32
+                                # slices other ranks own out of their HBM one-sidedly (ddp.py::_gather_master)
+                                torch.save(self.model.state_dict(), self.args.ckpt_path)
         if self.args.local_rank == 0:
             end = time.time()
             print("耗时：{}分钟".format((end - start) / 60))
         if not self.args.dev:
-            sd = self.model.state_dict()  # collective under DDP (re-assembles fp32 masters): every rank calls it
             if self.args.local_rank == 0:
-                torch.save(sd, self.args.ckpt_path)
+                torch.save(self.model.state_dict(), self.args.ckpt_path)
 
     def dev(self, dev_loader):
         self.model.eval()

@@ -10,6 +10,7 @@ autocast + GradScaler.scale(loss).backward() / scaler.step / scaler.update, mult
 """
 import os
 import sys
+import tempfile
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -82,11 +83,46 @@ def main(local=None, world=None, init_method=None):
             lv, rv = float(loss), float(red)
             assert abs(lv - float(hist[s]["loss_per_rank"][rank])) <= TOL_TRAJ, (mode, s, rank, lv)
             assert abs(rv - float(hist[s]["loss_mean"])) <= TOL_TRAJ, (mode, s, rank, rv)
-        sd = ddp.state_dict()
-        assert all(k.startswith("module.") for k in sd)
+        # the reference's checkpoint idiom: ONLY rank 0 calls state_dict() (`if local_rank == 0: torch.save(
+        # self.model.state_dict(), ...)`, multi-gpu-distributed-cls.py:190-197) -- it must not need the other ranks
+        # (fp32 slices owned by peers are pulled one-sidedly out of their HBM)
+        ckpt = os.path.join(tempfile.gettempdir(), "b2_ddp_worker_%s_%d.pt" % (mode, os.getppid()))
+        if rank == 0:
+            sd = ddp.state_dict()
+            assert all(k.startswith("module.") for k in sd)
+            for k, v in ref.items():
+                err = float((sd["module." + k].cpu() - v).abs().max())
+                assert err <= 2e-4, (mode, k, err)
+            torch.save(sd, ckpt)
+        torch.cuda.synchronize()
+        dist.barrier()
+        # ... and the reference's test phase (:357-363): fresh model -> cuda -> DDP wrap -> load_state_dict(torch.load(ckpt))
+        # on the WRAPPED model -> eval.  The kernels must see the loaded weights (bf16 shadow refreshed), on every rank.
+        fresh = b2.BertForSequenceClassification(cfg)
+        fresh.load_state_dict(state_from_hf_init(cfg, seed=555))
+        fresh.cuda()
+        ddp2 = b2.DistributedDataParallel(fresh, device_ids=[local])
+        eb = {k: v.to(dev) for k, v in batches[0][rank].items()}
+        ddp2.eval()
+        with torch.no_grad():
+            before = ddp2(input_ids=eb["input_ids"], token_type_ids=eb["token_type_ids"],
+                          attention_mask=eb["attention_mask"]).logits.clone()
+        res = ddp2.load_state_dict(torch.load(ckpt))
+        assert not res.missing_keys and not res.unexpected_keys, res
+        with torch.no_grad():
+            after = ddp2(input_ids=eb["input_ids"], token_type_ids=eb["token_type_ids"],
+                         attention_mask=eb["attention_mask"]).logits.clone()
+        _, want = bert_ref.forward(ref, cfg, batches[0][rank]["input_ids"], batches[0][rank]["token_type_ids"],
+                                   batches[0][rank]["attention_mask"])
+        assert float((after.cpu() - want).abs().max()) <= 1e-2, (mode, "loaded weights not in effect")
+        assert float((before.cpu() - want).abs().max()) > 1e-2, (mode, "test is vacuous")
+        sd2 = ddp2.state_dict()
         for k, v in ref.items():
-            err = float((sd["module." + k].cpu() - v).abs().max())
-            assert err <= 2e-4, (mode, k, err)
+            assert float((sd2["module." + k].cpu() - v).abs().max()) <= 2e-4, (mode, k)
+        dist.barrier()
+        if rank == 0:
+            os.remove(ckpt)
+        del ddp2, fresh
         # every rank holds identical bf16 weights after the exchange
         chk = model._engine.shadow.float().sum().reshape(1)
         allc = [torch.zeros_like(chk) for _ in range(world)]

@@ -24,6 +24,29 @@ TOL_LOSS = 2e-3          # |loss - loss_ref|
 TOL_LOGITS = 1e-2        # max |logit - logit_ref|
 TOL_GRAD_REL = 2e-2      # per-tensor ||g - g_ref|| / ||g_ref||  (tensors with a non-negligible reference norm)
 TOL_TRAJ = 1e-2          # per-step |loss - loss_ref| along a short trajectory
+# The attention query / key projection gradients are the one stated exception: their
+# gradient is P * (dP - delta) with dP - delta = dO . (V_j - O_i), and at random initialisation the value rows of a
+# sequence are nearly collinear in the upper layers, so the 2^-9 rounding of bf16 V / dO operands is amplified ~10x.
+# tests/test_trainer.py::test_full_size_gradients_per_tensor_vs_oracle measures the same tensors of stock HF BERT under
+# torch.autocast(bf16) on the same batch next to ours and asserts ours is no worse.
+TOL_GRAD_REL_QK = 4e-2
+
+
+def is_qk(name):
+    return ".attention.self.query." in name or ".attention.self.key." in name
+
+
+def grad_tol(name):
+    return TOL_GRAD_REL_QK if is_qk(name) else TOL_GRAD_REL
+
+
+def report(tag, obj):
+    """appends one JSON line to $B2_PARITY_REPORT (the GPU runs collect their measured parity tables there)"""
+    import json
+    path = os.environ.get("B2_PARITY_REPORT")
+    if path:
+        with open(path, "a") as f:
+            f.write(json.dumps({"tag": tag, **obj}) + "\n")
 
 
 def tiny_config(**kw):
@@ -109,6 +132,17 @@ def grad_report(got, ref, floor_frac=1e-3):
     return worst, rows
 
 
+def assert_grads_within_tolerance(got, ref, floor_frac=1e-3):
+    """every tensor within its stated tolerance (TOL_GRAD_REL; TOL_GRAD_REL_QK for the query / key projections);
+    returns (worst q/k, worst other)"""
+    _, rows = grad_report(got, ref, floor_frac)
+    bad = [(k, rel) for (k, rel, _rn) in rows if rel > grad_tol(k)]
+    assert not bad, sorted(bad, key=lambda r: -r[1])[:5]
+    qk = max([rel for (k, rel, _rn) in rows if is_qk(k)] or [0.0])
+    other = max([rel for (k, rel, _rn) in rows if not is_qk(k)] or [0.0])
+    return qk, other
+
+
 def state_from_hf_init(cfg, seed=123):
     """Initial fp32 weights: HF ``_init_weights`` under set_seed(seed) (what from_pretrained leaves for a fresh head)."""
     from oracle import cpu_step
@@ -145,6 +179,20 @@ def run_smoke():
     ref_loss, ref_logits, ref_grads = bert_ref.loss_and_grads(state, cfg, batch, masks=masks)
     dl = abs(float(loss) - float(ref_loss))
     dz = float((out[1].detach().cpu() - ref_logits).abs().max())
-    worst, _ = grad_report(model.grad_dict(), ref_grads)
-    print("smoke: |dloss|=%.2e max|dlogit|=%.2e worst grad rel-L2=%.2e" % (dl, dz, worst))
-    assert dl <= TOL_LOSS and dz <= TOL_LOGITS and worst <= 2 * TOL_GRAD_REL, "smoke parity failed"
+    qk, other = assert_grads_within_tolerance(model.grad_dict(), ref_grads)
+    print("smoke: |dloss|=%.2e max|dlogit|=%.2e worst grad rel-L2: q/k %.2e, others %.2e" % (dl, dz, qk, other))
+    assert dl <= TOL_LOSS and dz <= TOL_LOGITS, "smoke parity failed"
+    if torch.cuda.device_count() >= 2:
+        run_smoke_ddp(2)
+
+
+def run_smoke_ddp(world=2):
+    """>= 2 GPUs visible: the peer-HBM gradient exchange + partitioned AdamW + loss_reduce / output_reduce of
+    tests/ddp_worker.py (eager, GradScaler and CUDA-graph loops vs the oracle's DDP restatement) on `world` ranks."""
+    import subprocess
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
+           "--master-addr", "127.0.0.1", "--master-port", "29571", os.path.join(ROOT, "tests", "ddp_worker.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    tail = (r.stdout[-2000:] + r.stderr[-2000:])
+    assert r.returncode == 0 and "mode fused OK" in r.stdout, "smoke: %d-rank DDP parity failed:\n%s" % (world, tail)
+    print("smoke: %d-rank peer-HBM DDP parity OK" % world)

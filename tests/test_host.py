@@ -190,7 +190,11 @@ def test_bench_reference_arm_contract():
     assert d["value"] > 0 and d["steps"] == 1 and d["n_gpus"] == 1 and d["gpu_launches"] == 0
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"] == {"value": d["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
-    assert "workload" in d["config"]
+    # the `config` object has the same keys (and, for N = 1, values) on both arms: the driver's same_config check
+    sys.path.insert(0, root)
+    import bench
+    assert d["config"] == bench.config_dict(bench.CONFIGS["A"], 1)
+    assert set(d["config"]) == {"workload", "global_batch", "seq_len", "parallelism", "dropout", "optimizer"}
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")

@@ -294,6 +294,29 @@ def test_head_and_ce(cuda_dev, p):
     assert float(dh[:, 1:].float().abs().max()) == 0.0
 
 
+def test_ce_ignore_index_matches_torch(cuda_dev):
+    """torch.nn.CrossEntropyLoss defaults (multi-gpu-distributed-cls.py:343): label -100 is ignored and the mean runs
+    over the remaining samples; all-ignored -> nan."""
+    dev = cuda_dev
+    B, C = 32, 6
+    torch.manual_seed(5)
+    logits = torch.randn(B, C, device=dev)
+    labels = torch.randint(0, C, (B,), device=dev)
+    labels[::5] = -100
+    loss = torch.empty((), dtype=torch.float32, device=dev)
+    dlog = torch.empty(B, C, dtype=torch.float32, device=dev)
+    L.call("b2_ce_fwd_bwd", logits.data_ptr(), labels.data_ptr(), B, C, loss.data_ptr(), dlog.data_ptr(), S())
+    lg = logits.clone().requires_grad_(True)
+    ref = F.cross_entropy(lg, labels)
+    ref.backward()
+    assert abs(loss.item() - ref.item()) < 1e-5
+    assert (dlog - lg.grad).abs().max().item() < 1e-6
+    assert float(dlog[::5].abs().max()) == 0.0
+    labels[:] = -100
+    L.call("b2_ce_fwd_bwd", logits.data_ptr(), labels.data_ptr(), B, C, loss.data_ptr(), dlog.data_ptr(), S())
+    assert torch.isnan(loss).item() and float(dlog.abs().max()) == 0.0
+
+
 def test_adamw_matches_hf_restatement(cuda_dev):
     """Fused kernel vs oracle/adamw_ref.HFAdamW over several steps, decay and no-decay vectors, world == 1."""
     from oracle import adamw_ref

@@ -5,8 +5,9 @@ import pytest
 import torch
 import torch.nn.functional as F
 
-from parity import (TOL_GRAD_REL, TOL_LOGITS, TOL_LOSS, TOL_TRAJ, adamw_ref, b2, bert_ref, full_config, grad_report,
-                    make_model, oracle_masks, state_from_hf_init, tiny_config, to_dev)
+from parity import (TOL_GRAD_REL, TOL_LOGITS, TOL_LOSS, TOL_TRAJ, adamw_ref, assert_grads_within_tolerance, b2, bert_ref,
+                    full_config, grad_report, grad_tol, make_model, oracle_masks, report, state_from_hf_init,
+                    tiny_config, to_dev)
 
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
@@ -65,8 +66,8 @@ def test_other_baseline_shapes_match_oracle(cuda_dev, name, cfg_kw, batch, seq, 
     rl, rz, rg = bert_ref.loss_and_grads(state, cfg, b, masks=masks)
     assert abs(float(loss) - float(rl)) <= TOL_LOSS
     assert float((out[1].detach().cpu() - rz).abs().max()) <= TOL_LOGITS
-    worst, rows = grad_report(model.grad_dict(), rg)
-    assert worst <= 2 * TOL_GRAD_REL, sorted(rows, key=lambda r: -r[1])[:5]   # q/k projections: see DESIGN.md §2
+    qk, other = assert_grads_within_tolerance(model.grad_dict(), rg)   # 2e-2; query / key projections 4e-2 (parity.py)
+    report("shape_grads", {"name": name, "dropout": dropout, "worst_qk": qk, "worst_other": other})
 
 
 def test_eval_forward_and_output_surface(cuda_dev):
@@ -262,3 +263,92 @@ def test_dropout_statistics_and_determinism(cuda_dev):
     a, b, c = run(0), run(0), run(1)
     assert torch.equal(a, b)
     assert not torch.equal(a, c)
+
+
+@pytest.mark.parametrize("name", ["A", "B", "C"])
+def test_full_depth_step0_matches_ddp_fixture(cuda_dev, name):
+    """BASELINE.json configs A / B / C at FULL depth (12 / 12 / 24 layers, seq 128 / 512 / 128), dropout off: rank 0's
+    step-0 loss, logits and every gradient tensor (norm + 64 strided values) against tests/golden/config_<x>_ddp.pt
+    (HF transformers fp32 on CPU, tests/golden/make_golden_full.py).  Weights: the package initialiser under
+    set_seed(123), as the fixture generator used."""
+    sys_path = os.path.join(GOLD, "config_%s_ddp.pt" % name.lower())
+    if not os.path.exists(sys_path):
+        pytest.skip("fixture not generated")
+    fx = torch.load(sys_path)
+    preset = {"A": b2.chinese_bert_wwm_ext_config, "B": b2.bert_base_config, "C": b2.bert_large_config}[name]
+    cfg = preset(num_labels=6, hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0)
+    b2.set_seed(123)
+    model = b2.BertForSequenceClassification(cfg)
+    chk = float(sum(p.detach().double().sum() for p in model.parameters()))
+    assert abs(chk - fx["init_checksum"]) <= 1e-6 * max(1.0, abs(fx["init_checksum"])), "initialiser drifted"
+    model.to(cuda_dev).train()
+    B, S = fx["batch"], fx["seq"]
+    batch = bert_ref.synthetic_batch(cfg, B, S, 5000, padded=False)
+    assert torch.equal(batch["input_ids"], fx["input_ids_step0_rank0"])
+    out, loss = _fwd_bwd(model, batch, cuda_dev)
+    w1 = fx["worlds"][1]
+    assert abs(float(loss) - float(w1["loss"][0][0])) <= TOL_LOSS
+    assert float((out[1].detach().cpu() - w1["logits"][0][0]).abs().max()) <= TOL_LOGITS
+    g = model.grad_dict()
+    gold = fx["step0_rank0"]
+    scale = max(gold["grad_norms"].values())
+    worst = {"qk": 0.0, "other": 0.0}
+    for k, n in gold["grad_norms"].items():
+        got = float(g[k].double().norm())
+        rel = abs(got - n) / max(n, 1e-3 * scale)
+        worst["qk" if ".query." in k or ".key." in k else "other"] = max(
+            worst["qk" if ".query." in k or ".key." in k else "other"], rel)
+        assert rel <= grad_tol(k), (k, got, n)
+    # strided 64-value samples guard layout / indexing (bf16 noise does not average out over 64 values: 3x tolerance)
+    for k, ref in gold["grad_samples"].items():
+        f = g[k].flatten()
+        if f.numel() > ref.numel():
+            f = f[(torch.arange(ref.numel(), dtype=torch.int64) * (f.numel() - 1) // (ref.numel() - 1)).to(f.device)]
+        assert float((f.cpu() - ref).norm()) <= 3 * grad_tol(k) * max(float(ref.norm()), 1e-3 * scale), k
+    report("full_depth_step0", {"config": name, "dloss": abs(float(loss) - float(w1["loss"][0][0])),
+                                "dlogit": float((out[1].detach().cpu() - w1["logits"][0][0]).abs().max()),
+                                "worst_norm_rel": worst})
+
+
+def test_from_pretrained_with_a_checkpoint_directory(cuda_dev, tmp_path):
+    """The reference's model construction (multi-gpu-distributed-cls.py:336-338):
+        config = BertConfig.from_pretrained(model_path, num_labels=6)
+        model  = BertForSequenceClassification.from_pretrained(model_path, config=config)
+    against a synthetic HF checkpoint directory (config.json + pytorch_model.bin holding the ENCODER only, as the
+    real chinese-bert-wwm-ext checkpoint does: `bert.*` keys plus the pre-training heads `cls.*`, no classifier)."""
+    import json
+    cfg = tiny_config()
+    state = state_from_hf_init(cfg, seed=321)
+    ckpt_dir = tmp_path / "model_hub" / "tiny-bert"
+    ckpt_dir.mkdir(parents=True)
+    with open(ckpt_dir / "config.json", "w") as f:
+        json.dump({k: getattr(cfg, k) for k in ("vocab_size", "hidden_size", "num_hidden_layers", "num_attention_heads",
+                                                "intermediate_size", "max_position_embeddings", "type_vocab_size",
+                                                "hidden_dropout_prob", "attention_probs_dropout_prob",
+                                                "layer_norm_eps", "hidden_act", "initializer_range",
+                                                "pad_token_id")}, f)
+    sd = {k: v for k, v in state.items() if k.startswith("bert.")}
+    sd["cls.predictions.bias"] = torch.zeros(cfg.vocab_size)                 # pre-training head: must be ignored
+    sd["bert.embeddings.position_ids"] = torch.arange(cfg.max_position_embeddings)[None]
+    torch.save(sd, ckpt_dir / "pytorch_model.bin")
+    config = b2.BertConfig.from_pretrained(str(ckpt_dir), num_labels=6)
+    assert config.num_labels == 6 and config.hidden_size == cfg.hidden_size
+    torch.manual_seed(11)
+    model = b2.BertForSequenceClassification.from_pretrained(str(ckpt_dir), config=config)
+    got = dict(model.named_parameters())
+    for k, v in state.items():
+        if k.startswith("bert."):
+            assert torch.equal(got[k].detach(), v), k                        # encoder: the checkpoint's tensors
+    # the classifier is absent from the checkpoint: freshly initialised (N(0, 0.02) weight, zero bias), like HF
+    assert got["classifier.weight"].shape == (6, cfg.hidden_size)
+    assert 0.005 < float(got["classifier.weight"].std()) < 0.05 and float(got["classifier.bias"].abs().max()) == 0.0
+    model.to(cuda_dev).eval()
+    batch = bert_ref.synthetic_batch(cfg, 4, 128, 77, padded=True)
+    d = to_dev(batch, cuda_dev)
+    with torch.no_grad():
+        out = model(input_ids=d["input_ids"], token_type_ids=d["token_type_ids"], attention_mask=d["attention_mask"])
+    ref_state = {k: v.detach().cpu() for k, v in model.named_parameters()}
+    _, rz = bert_ref.forward(ref_state, cfg, batch["input_ids"], batch["token_type_ids"], batch["attention_mask"])
+    assert float((out.logits.cpu() - rz).abs().max()) <= TOL_LOGITS
+    with pytest.raises(FileNotFoundError):
+        b2.BertForSequenceClassification.from_pretrained(str(tmp_path / "model_hub"), config=config)

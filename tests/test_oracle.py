@@ -96,6 +96,39 @@ def test_config_a_fixture_matches_oracle():
         assert abs(float(grads[k].double().norm()) - n) < 1e-4 * max(n, 1e-4 * scale), k
 
 
+def test_config_a_ddp_fixture_matches_oracle_world2():
+    """The full-size multi-rank fixture bench.py's `parity` block is judged against (tests/golden/config_a_ddp.pt: HF
+    fp32 per rank + DDP mean + HF AdamW, package initialiser under set_seed(123)) vs the oracle restatement: world 2,
+    step 0 (both ranks) and, through ddp_ref.mean_grads + adamw_ref, the rank-0 loss of step 1."""
+    import pytorch_distributed_nlp_b200 as b2
+    path = os.path.join(GOLD, "config_a_ddp.pt")
+    if not os.path.exists(path):
+        pytest.skip("fixture not generated")
+    fx = torch.load(path)
+    cfg = full_config(hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0)
+    b2.set_seed(123)
+    state = {k: v.detach().clone() for k, v in b2.BertForSequenceClassification(cfg).named_parameters()}
+    chk = float(sum(v.double().sum() for v in state.values()))
+    assert abs(chk - fx["init_checksum"]) <= 1e-6 * max(1.0, abs(fx["init_checksum"]))
+    torch.set_num_threads(os.cpu_count() or 1)
+    B, S = fx["batch"], fx["seq"]
+    mk = lambda s, r: bert_ref.synthetic_batch(cfg, B, S, 5000 + 100 * s + r, padded=(s % 2 == 1))
+    assert torch.equal(mk(0, 0)["input_ids"], fx["input_ids_step0_rank0"])
+    w2 = fx["worlds"][2]
+    res = [bert_ref.loss_and_grads(state, cfg, mk(0, r)) for r in range(2)]
+    for r in range(2):
+        assert abs(float(res[r][0]) - float(w2["loss"][0][r])) < 5e-6
+        assert float((res[r][1] - w2["logits"][0][r]).abs().max()) < 1e-5
+    scale = max(fx["step0_rank0"]["grad_norms"].values())
+    for k, n in fx["step0_rank0"]["grad_norms"].items():
+        assert abs(float(res[0][2][k].double().norm()) - n) < 1e-4 * max(n, 1e-4 * scale), k
+    opt = adamw_ref.HFAdamW(state, lr=3e-5, weight_decay=0.01)
+    opt.step(ddp_ref.mean_grads([res[0][2], res[1][2]]))
+    l1, z1, _ = bert_ref.loss_and_grads(state, cfg, mk(1, 0))
+    assert abs(float(l1) - float(w2["loss"][1][0])) < 2e-5
+    assert float((z1 - w2["logits"][1][0]).abs().max()) < 5e-5
+
+
 def test_hf_adamw_restatement_hand_case():
     """One scalar, two steps, worked by hand from transformers 4.28.1 optimization.py::AdamW.step."""
     p = {"w.weight": torch.tensor([1.0]), "w.bias": torch.tensor([1.0])}

@@ -7,7 +7,8 @@ import pytest
 import torch
 import torch.nn.functional as F
 
-from parity import (TOL_GRAD_REL, b2, bert_ref, full_config, make_model, state_from_hf_init, tiny_config, to_dev)
+from parity import (TOL_GRAD_REL, TOL_TRAJ, b2, bert_ref, full_config, grad_tol, is_qk, make_model, report,
+                    state_from_hf_init, tiny_config, to_dev)
 
 pytestmark = pytest.mark.gpu
 
@@ -87,10 +88,13 @@ def test_trainer_train_dev_test(cuda_dev, tmp_path, capsys, fused):
 
 def test_full_size_gradients_per_tensor_vs_oracle(cuda_dev):
     """BASELINE config A, dropout off: every one of the 201 gradient tensors against the fp32 oracle (run here on the
-    host cores).  Stated tolerance: rel-L2 <= 2e-2 (BASELINE.md §4), except the attention query/key projections:
+    host cores).  Stated tolerance (BASELINE.md §4): rel-L2 <= 2e-2, except the attention query/key projections:
     <= 4e-2.  Their gradient is P * (dP - delta) with dP - delta = dO . (V_j - O_i): at initialisation the value rows of
-    a sequence are nearly collinear, so the bf16 rounding of V (2^-9 relative) is amplified by |V| / |V_j - O_i| ~ 10.
-    bf16 autocast of the reference has the same property; fp32 Q/K/V activations would be needed to remove it."""
+    a sequence are nearly collinear in the upper layers, so the bf16 rounding of the V / dO operands (2^-9 relative) is
+    amplified by |V| / |V_j - O_i| ~ 10.  That this is a property of bf16 Q/K/V activations and not of these kernels is
+    MEASURED here: stock HF BERT (eager attention, cuBLAS) under torch.autocast(bf16) on the same weights and batch is
+    compared with the same oracle, and ours must not be worse than it on the q/k tensors by more than 15 %."""
+    from oracle import cpu_step
     cfg = full_config(hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0)
     state = state_from_hf_init(cfg)
     model = make_model(cfg, state, cuda_dev).train()
@@ -103,15 +107,98 @@ def test_full_size_gradients_per_tensor_vs_oracle(cuda_dev):
     torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
     _, _, ref = bert_ref.loss_and_grads(state, cfg, batch)
     got = model.grad_dict()
+    # the comparison stack: HF's own module, bf16 autocast (fp32 parameters and gradients, bf16 matmuls, fp32 softmax)
+    hf = cpu_step.build_hf_model(cfg, seed=123)
+    hf.load_state_dict(state, strict=False)
+    hf.to(cuda_dev).train()
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        ho = hf(input_ids=d["input_ids"], token_type_ids=d["token_type_ids"], attention_mask=d["attention_mask"])
+        hl = F.cross_entropy(ho.logits.float(), d["label"])
+    hl.backward()
+    auto = {k: v.grad.detach() for k, v in hf.named_parameters()}
     scale = max(float(v.double().norm()) for v in ref.values())
-    worst = {"qk": 0.0, "other": 0.0}
+    worst = {"qk": 0.0, "other": 0.0, "auto_qk": 0.0, "auto_other": 0.0}
+    rows = []
     for k, r in ref.items():
         rn = float(r.double().norm())
         if rn < 1e-6 * scale:          # analytically zero (key.bias: softmax shift invariance)
             assert float(got[k].double().norm()) < 1e-3 * scale, k
             continue
         rel = float((got[k].cpu().double() - r.double()).norm()) / rn
-        qk = ".attention.self.query." in k or ".attention.self.key." in k
-        worst["qk" if qk else "other"] = max(worst["qk" if qk else "other"], rel)
-        assert rel <= (4e-2 if qk else TOL_GRAD_REL), (k, rel)
-    print("worst rel-L2: q/k %.4f, others %.4f" % (worst["qk"], worst["other"]))
+        rel_a = float((auto[k].cpu().double() - r.double()).norm()) / rn
+        grp = "qk" if is_qk(k) else "other"
+        worst[grp] = max(worst[grp], rel)
+        worst["auto_" + grp] = max(worst["auto_" + grp], rel_a)
+        rows.append((k, round(rel, 5), round(rel_a, 5)))
+        assert rel <= grad_tol(k), (k, rel)
+    print("worst rel-L2 vs fp32 oracle: q/k %.4f (torch bf16 autocast: %.4f), others %.4f (autocast: %.4f)"
+          % (worst["qk"], worst["auto_qk"], worst["other"], worst["auto_other"]))
+    report("config_a_grads", {"worst": worst, "qk_rows": [r for r in rows if is_qk(r[0])]})
+    assert worst["qk"] <= 1.15 * worst["auto_qk"], worst
+
+
+@pytest.mark.parametrize("dropout,steps", [(False, 20), (True, 8)])
+def test_config_a_loss_trajectory_vs_oracle(cuda_dev, dropout, steps):
+    """BASELINE.md §4 "loss trajectory, 20 steps": config A (B=32, S=128, HF AdamW lr 3e-5), the fused CUDA-graph step
+    against the fp32 oracle stepping the same batches on the host cores.  dropout=True: the reference's training mode,
+    the oracle replays the kernels' Philox keep-masks (fewer steps: the numpy replica draws 150 M mask bits per step).
+    For dropout=False the same trajectory is also run by stock HF BERT under torch.autocast(bf16) with the restated HF
+    AdamW -- the deviation bf16 compute itself causes on this chaotic early trajectory (AdamW's first updates are
+    lr * sign(g) on every one of 102 M weights) -- and ours must stay within max(1e-2, 1.25x that)."""
+    from oracle import adamw_ref, cpu_step
+    from parity import oracle_masks
+    kw = {} if dropout else dict(hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0)
+    cfg = full_config(**kw)
+    state = state_from_hf_init(cfg)
+    B, S, seed = 32, 128, 777
+    batches = [bert_ref.synthetic_batch(cfg, B, S, 8000 + i, padded=(i % 2 == 1)) for i in range(steps)]
+
+    class A:
+        weight_decay, learning_rate = 0.01, 3e-5
+
+    model = make_model(cfg, state, cuda_dev).train()
+    model._engine.seed_dropout(seed, 0)
+    opt = b2.build_optimizer(model, A)
+    step = b2.FusedTrainStep(model, opt, B, S)
+    ours = []
+    for b in batches:
+        step(b)
+        ours.append(step.loss_to_host())
+    assert step.graph is not None
+
+    auto = None
+    if not dropout:
+        hf = cpu_step.build_hf_model(cfg, seed=123)
+        hf.load_state_dict(state, strict=False)
+        hf.to(cuda_dev).train()
+        hopt = cpu_step._HFOpt(hf, 3e-5, 0.01)
+        auto = []
+        for b in batches:
+            d = to_dev(b, cuda_dev)
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                ho = hf(input_ids=d["input_ids"], token_type_ids=d["token_type_ids"],
+                        attention_mask=d["attention_mask"])
+                hl = F.cross_entropy(ho.logits.float(), d["label"])
+            hopt.zero_grad()
+            hl.backward()
+            hopt.step()
+            auto.append(float(hl))
+        del hf, hopt
+
+    torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
+    params = {k: v.clone() for k, v in state.items()}
+    ropt = adamw_ref.HFAdamW(params, lr=3e-5, weight_decay=0.01)
+    ref = []
+    for s, b in enumerate(batches):
+        masks = oracle_masks(cfg, B, S, seed, s) if dropout else None
+        l, _z, g = bert_ref.loss_and_grads(params, cfg, b, masks=masks)
+        ropt.step(g)
+        ref.append(float(l))
+    dev_ours = [abs(a - r) for a, r in zip(ours, ref)]
+    dev_auto = [abs(a - r) for a, r in zip(auto, ref)] if auto is not None else None
+    report("config_a_trajectory", {"dropout": dropout, "steps": steps, "ref": ref, "ours": ours, "autocast": auto,
+                                   "max_dev_ours": max(dev_ours), "max_dev_autocast": max(dev_auto) if dev_auto else None})
+    print("trajectory (dropout=%s): max |dloss| ours %.4f%s" % (dropout, max(dev_ours),
+          "" if dev_auto is None else ", torch bf16 autocast %.4f" % max(dev_auto)))
+    bound = TOL_TRAJ if dev_auto is None else max(TOL_TRAJ, 1.25 * max(dev_auto))
+    assert max(dev_ours) <= bound, (dev_ours, dev_auto)
