@@ -28,7 +28,7 @@ extern "C" {
 /* ------------------------------------------------------------------------------------------------------ */
 const char* b2_last_error(void);
 int32_t b2_abi_version(void);             /* bumped when a struct below changes */
-#define B2_ABI_VERSION 13
+#define B2_ABI_VERSION 14
 int64_t b2_launch_count(void);            /* kernels launched by this library so far (process-wide) */
 
 /* ------------------------------------------------------------------------------------------------------ */
@@ -86,6 +86,18 @@ int32_t b2_gemm_bf16(const b2_gemm_args_t* args, void* stream);
  * addmm backward nodes for BertSelfAttention/BertSelfOutput/BertIntermediate/BertOutput, modeling_bert.py:179-356).
  * Other mixes are issued one by one; results are identical either way.                                         */
 int32_t b2_gemm_bf16_grouped(const b2_gemm_args_t* args, int32_t count, void* stream);
+
+/* BertSelfOutput.forward / BertOutput.forward in ONE launch (SP/transformers/models/bert/modeling_bert.py:294-298,
+ * :352-356): y = LayerNorm(dropout(x W^T + b) + residual).  `args` as for b2_gemm_bf16 with epilogue
+ * B2_EPI_BIAS_DROPOUT_RESIDUAL, NT layouts, N = hidden in {768, 1024}: D receives the pre-LayerNorm sum (bf16, kept
+ * for the backward), y the normalised output, mean / rstd (fp32 [M]) the row statistics.  A row's N columns are
+ * spread over a cluster of 4 CTA pairs; the row statistics travel through distributed shared memory.  Same arithmetic
+ * as b2_gemm_bf16 followed by b2_layernorm_fwd, up to the summation order of the statistics.
+ * b2_gemm_ln_max_clusters(hidden): how many such clusters the device can hold at once (0 = shape / device not
+ * supported: issue the two separate kernels instead).                                                          */
+int32_t b2_gemm_ln_fwd(const b2_gemm_args_t* args, const void* gamma, const void* beta, float eps, void* y,
+                       int64_t ldy, float* mean, float* rstd, void* stream);
+int32_t b2_gemm_ln_max_clusters(int64_t hidden);
 
 /* ------------------------------------------------------------------------------------------------------ */
 /* memory-bound kernels                                                                                   */

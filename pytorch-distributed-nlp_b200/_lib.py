@@ -8,7 +8,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libb2ddpbert.so")
-ABI_VERSION = 13
+ABI_VERSION = 14
 
 MAJOR_K, MAJOR_MN = 0, 1
 EPI_NONE, EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_DROPOUT_RESIDUAL, EPI_RESIDUAL, EPI_GELU_BWD = 0, 1, 2, 3, 4, 5
@@ -47,6 +47,7 @@ _SIGNATURES = {
     "b2_gemm_bf16_grouped": [C.POINTER(GemmArgs), i32, vp],
     "b2_gemm_bf16_grouped_adamw": [C.POINTER(GemmArgs), C.POINTER(FusedAdamWTarget), i32, C.POINTER(AdamWHParams), vp,
                                    vp],
+    "b2_gemm_ln_fwd": [C.POINTER(GemmArgs), vp, vp, f32, vp, i64, vp, vp, vp],
     "b2_embed_fwd": [vp, vp, i64, i64, vp, vp, vp, vp, vp, i64, i64, i64, f32, f32, vp, u32, vp, vp, vp, vp, vp, vp,
                      vp],
     "b2_embed_owner_init": [vp, i64, vp],
@@ -80,7 +81,8 @@ _SIGNATURES = {
     "b2_allgather_rows": [vp, i64, C.POINTER(vp), C.POINTER(vp), i32, i32, i32, vp, vp],
     "b2_scalar_allreduce_mean": [vp, vp, C.POINTER(vp), C.POINTER(vp), i32, i32, i32, vp, vp],
 }
-EXPORTED_SYMBOLS = sorted(list(_SIGNATURES) + ["b2_last_error", "b2_abi_version", "b2_launch_count"])
+EXPORTED_SYMBOLS = sorted(list(_SIGNATURES) + ["b2_last_error", "b2_abi_version", "b2_launch_count",
+                                              "b2_gemm_ln_max_clusters"])
 
 _lib = None
 
@@ -101,6 +103,8 @@ def load():
     lib.b2_abi_version.argtypes = []
     lib.b2_launch_count.restype = i64
     lib.b2_launch_count.argtypes = []
+    lib.b2_gemm_ln_max_clusters.restype = i32     # a count, not a status
+    lib.b2_gemm_ln_max_clusters.argtypes = [i64]
     if lib.b2_abi_version() != ABI_VERSION:
         raise RuntimeError("libb2ddpbert.so ABI %d != expected %d: rebuild" % (lib.b2_abi_version(), ABI_VERSION))
     for name, argtypes in _SIGNATURES.items():

@@ -443,6 +443,11 @@ class _Engine:
         # the backward is latency-, not Philox-bound), so off by default; the kernels and tests keep the path alive
         self.attn_keep_bits = os.environ.get("B2_ATTN_KEEP_BITS", "0") == "1"
         self.use_wgrad_stream = os.environ.get("B2_WGRAD_STREAM", "1") != "0"
+        # dense + bias + dropout + residual + LayerNorm as ONE cluster kernel (b2_gemm_ln_fwd) for the two N = hidden
+        # GEMMs of a layer, when the hidden size has a row-cluster tiling (768, 1024) and the device can co-schedule
+        # the 8-CTA clusters; otherwise (and with B2_FUSED_LN=0) the GEMM epilogue + separate LayerNorm launch
+        self.fused_ln = (os.environ.get("B2_FUSED_LN", "1") != "0" and self.H in (768, 1024) and
+                         int(L.load().b2_gemm_ln_max_clusters(self.H)) > 0)
         # fp32 accumulators for the bias gradients that kernels produce as a side effect of their epilogues (QKV bias
         # from attention backward, intermediate bias from the GELU' dgrad): per layer [3H | I]; one finishing launch
         # per step turns them into bf16 gradients and re-zeroes them
@@ -562,6 +567,29 @@ class _Engine:
             return
         L.call("b2_gemm_bf16", a, stream if stream is not None else self.stream())
 
+    def dense_dropout_residual_layernorm(self, M, K, A, W, bias, resid, p, site, gamma, beta, z, y, mean, rstd):
+        """y = LayerNorm(dropout(A W^T + bias) + resid) with z = the pre-LN sum kept for the backward
+        (BertSelfOutput / BertOutput, modeling_bert.py:294-298, :352-356)"""
+        H = self.H
+        s = self.stream()
+        eps = float(self.cfg.layer_norm_eps)
+        if self.fused_ln:
+            a = L.GemmArgs()
+            a.M, a.N, a.K = M, H, K
+            a.A, a.lda, a.a_major = A, K, L.MAJOR_K
+            a.B, a.ldb, a.b_major = W, K, L.MAJOR_K
+            a.D, a.ldd, a.epilogue = z, H, L.EPI_BIAS_DROPOUT_RESIDUAL
+            a.bias, a.aux_in, a.ld_aux_in, a.aux_out, a.ld_aux_out = bias, resid, H, None, 0
+            a.dropout_p, a.rng_state, a.rng_site = p, self.rng.data_ptr(), site
+            a.workspace, a.workspace_bytes = None, 0
+            a.force_bn = a.force_splits = a.force_kernel = 0
+            a.debug_timing, a.colsum_out = None, None
+            L.call("b2_gemm_ln_fwd", a, gamma, beta, eps, y, H, mean, rstd, s)
+            return
+        self.gemm(M, H, K, A, K, L.MAJOR_K, W, K, L.MAJOR_K, z, H, L.EPI_BIAS_DROPOUT_RESIDUAL, bias=bias,
+                  aux_in=resid, ld_aux_in=H, p=p, site=site)
+        L.call("b2_layernorm_fwd", z, gamma, beta, M, H, eps, y, mean, rstd, s)
+
     # ---- forward --------------------------------------------------------------------------------------------------------
     def forward(self, input_ids, token_type_ids, attention_mask, labels, training, need_backward):
         cfg, H, I = self.cfg, self.H, self.I
@@ -607,21 +635,19 @@ class _Engine:
                       a["qkv"].data_ptr(), 3 * H, L.EPI_BIAS, bias=w(pre + "attention.self.query.bias"))
             L.call("b2_attention_fwd", a["qkv"].data_ptr(), L.ptr(mask), B, S, self.heads, 64, p_a, rng, 1 + 3 * l,
                    a["ctx"].data_ptr(), a["lse"].data_ptr(), L.ptr(a["keep"]) if need_backward else None, s)
-            self.gemm(M, H, H, a["ctx"].data_ptr(), H, KM, w(pre + "attention.output.dense.weight"), H, KM,
-                      a["z1"].data_ptr(), H, L.EPI_BIAS_DROPOUT_RESIDUAL, bias=w(pre + "attention.output.dense.bias"),
-                      aux_in=x.data_ptr(), ld_aux_in=H, p=p_h, site=2 + 3 * l)
-            L.call("b2_layernorm_fwd", a["z1"].data_ptr(), w(pre + "attention.output.LayerNorm.weight"),
-                   w(pre + "attention.output.LayerNorm.bias"), M, H, float(cfg.layer_norm_eps), a["x1"].data_ptr(),
-                   a["mean1"].data_ptr(), a["rstd1"].data_ptr(), s)
+            self.dense_dropout_residual_layernorm(
+                M, H, a["ctx"].data_ptr(), w(pre + "attention.output.dense.weight"),
+                w(pre + "attention.output.dense.bias"), x.data_ptr(), p_h, 2 + 3 * l,
+                w(pre + "attention.output.LayerNorm.weight"), w(pre + "attention.output.LayerNorm.bias"),
+                a["z1"].data_ptr(), a["x1"].data_ptr(), a["mean1"].data_ptr(), a["rstd1"].data_ptr())
             self.gemm(M, I, H, a["x1"].data_ptr(), H, KM, w(pre + "intermediate.dense.weight"), H, KM,
                       a["h"].data_ptr(), I, L.EPI_BIAS_GELU, bias=w(pre + "intermediate.dense.bias"),
                       aux_out=a["u"].data_ptr(), ld_aux_out=I)
-            self.gemm(M, H, I, a["h"].data_ptr(), I, KM, w(pre + "output.dense.weight"), I, KM,
-                      a["z2"].data_ptr(), H, L.EPI_BIAS_DROPOUT_RESIDUAL, bias=w(pre + "output.dense.bias"),
-                      aux_in=a["x1"].data_ptr(), ld_aux_in=H, p=p_h, site=3 + 3 * l)
-            L.call("b2_layernorm_fwd", a["z2"].data_ptr(), w(pre + "output.LayerNorm.weight"),
-                   w(pre + "output.LayerNorm.bias"), M, H, float(cfg.layer_norm_eps), a["x2"].data_ptr(),
-                   a["mean2"].data_ptr(), a["rstd2"].data_ptr(), s)
+            self.dense_dropout_residual_layernorm(
+                M, I, a["h"].data_ptr(), w(pre + "output.dense.weight"), w(pre + "output.dense.bias"),
+                a["x1"].data_ptr(), p_h, 3 + 3 * l, w(pre + "output.LayerNorm.weight"),
+                w(pre + "output.LayerNorm.bias"), a["z2"].data_ptr(), a["x2"].data_ptr(), a["mean2"].data_ptr(),
+                a["rstd2"].data_ptr())
             x = a["x2"]
         L.call("b2_head_fwd", x.data_ptr(), B, S, H, w("bert.pooler.dense.weight"), w("bert.pooler.dense.bias"),
                w("classifier.weight"), w("classifier.bias"), self.C, p_c, rng, 1 + 3 * self.nl,
