@@ -28,7 +28,7 @@ extern "C" {
 /* ------------------------------------------------------------------------------------------------------ */
 const char* b2_last_error(void);
 int32_t b2_abi_version(void);             /* bumped when a struct below changes */
-#define B2_ABI_VERSION 14
+#define B2_ABI_VERSION 15
 int64_t b2_launch_count(void);            /* kernels launched by this library so far (process-wide) */
 
 /* ------------------------------------------------------------------------------------------------------ */
@@ -202,6 +202,44 @@ int32_t b2_head_bwd(const float* dlogits, const void* hidden_states, const void*
                     void* d_cls_w, void* d_cls_b, void* d_hidden /* [batch*seq, hidden], rows != CLS zeroed */,
                     int32_t d_hidden_fp32 /* 0: bf16, 1: fp32 */, float* scratch /* fp32 [2, batch, hidden] */,
                     void* stream);
+
+/* ------------------------------------------------------------------------------------------------------ */
+/* packed bins: the reference tokenises with padding="max_length" (multi-gpu-distributed-cls.py */
+/* :76) although its rows average 18 of 128 tokens.  The host packs the valid prefixes of several sequences into  */
+/* 128-token bins (pytorch-distributed-nlp_b200/packing.py); these variants of the entry points above take        */
+/*   position_ids  int64 [bins * 128]   position of every token inside its own sequence                           */
+/*   segments      int32 [bins * 128]   lo | hi << 16: the row may attend to rows [lo, hi) of its bin only        */
+/*   cls_rows      int64 [batch]        flat row of every sequence's first token (what the pooler reads)          */
+/* Everything else (GEMMs, LayerNorm, GELU) is token-wise and simply runs on bins * 128 rows.                     */
+/* ------------------------------------------------------------------------------------------------------ */
+int32_t b2_embed_fwd_packed(const int64_t* input_ids, const int64_t* token_type_ids, const int64_t* position_ids,
+                            int64_t max_positions, int64_t bins, int64_t seq, const void* word_emb,
+                            const void* pos_emb, const void* type_emb, const void* gamma, const void* beta,
+                            int64_t hidden, int64_t vocab, int64_t type_vocab, float eps, float dropout_p,
+                            const void* rng_state, uint32_t rng_site, void* y, void* pre_ln, float* mean, float* rstd,
+                            int32_t* ids32, int32_t* tt32, int32_t* pos32, void* stream);
+int32_t b2_embed_bwd_packed(const void* dy, int32_t dy_fp32, const void* pre_ln, const float* mean, const float* rstd,
+                            const void* gamma, const int32_t* ids32, const int32_t* tt32, const int32_t* pos32,
+                            int64_t bins, int64_t seq, int64_t hidden, int64_t vocab, int64_t type_vocab,
+                            int64_t pad_token_id, float dropout_p, const void* rng_state, uint32_t rng_site,
+                            void* d_word, void* d_pos, void* d_type, void* d_gamma, void* d_beta, void* scratch_dx,
+                            float* scratch_partials, int64_t scratch_partials_bytes, int32_t* owner, void* stream);
+int32_t b2_attention_fwd_packed(const void* qkv, const int32_t* segments, int64_t bins, int64_t heads,
+                                int64_t head_dim, float dropout_p, const void* rng_state, uint32_t rng_site,
+                                void* ctx, float* lse, uint64_t* keep_bits, void* stream);
+int32_t b2_attention_bwd_packed(const void* qkv, const int32_t* segments, const void* ctx, const void* d_ctx,
+                                const float* lse, int64_t bins, int64_t heads, int64_t head_dim, float dropout_p,
+                                const void* rng_state, uint32_t rng_site, void* d_qkv, float* dbias_accum,
+                                const uint64_t* keep_bits, void* stream);
+int32_t b2_head_fwd_packed(const void* hidden_states, const int64_t* cls_rows, int64_t batch, int64_t hidden,
+                           const void* pool_w, const void* pool_b, const void* cls_w, const void* cls_b,
+                           int64_t num_labels, float dropout_p, const void* rng_state, uint32_t rng_site,
+                           void* pooled, float* logits, void* stream);
+int32_t b2_head_bwd_packed(const float* dlogits, const void* hidden_states, const void* pooled,
+                           const int64_t* cls_rows, int64_t tokens, int64_t batch, int64_t hidden,
+                           const void* pool_w, const void* cls_w, int64_t num_labels, float dropout_p,
+                           const void* rng_state, uint32_t rng_site, void* d_pool_w, void* d_pool_b, void* d_cls_w,
+                           void* d_cls_b, void* d_hidden, int32_t d_hidden_fp32, float* scratch, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------ */
 /* optimizer + gradient exchange                                                                          */

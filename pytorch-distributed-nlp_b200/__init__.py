@@ -8,7 +8,8 @@ from .modeling import (BertConfig, BertForSequenceClassification, SequenceClassi
 from .optim import AdamW, build_optimizer
 from .ddp import DistributedDataParallel
 from .synthetic import synthetic_batch
-from .trainer import Args, FusedEvalStep, FusedTrainStep, Trainer
+from .packing import pack_batch
+from .trainer import Args, FusedEvalStep, FusedTrainStep, PackedTrainStep, Trainer
 
 
 def set_seed(seed=123):
@@ -24,5 +25,5 @@ def set_seed(seed=123):
 
 
 __all__ = ["BertConfig", "BertForSequenceClassification", "SequenceClassifierOutput", "AdamW", "build_optimizer",
-           "DistributedDataParallel", "Args", "Trainer", "FusedTrainStep", "FusedEvalStep", "synthetic_batch", "set_seed", "bert_base_config",
+           "DistributedDataParallel", "Args", "Trainer", "FusedTrainStep", "FusedEvalStep", "PackedTrainStep", "pack_batch", "synthetic_batch", "set_seed", "bert_base_config",
            "bert_large_config", "chinese_bert_wwm_ext_config"]

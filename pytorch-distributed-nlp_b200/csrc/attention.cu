@@ -46,7 +46,26 @@ struct AttnParams {
   // optional (seq == 128, dropout on): the forward's dropout decisions, one 64-bit word per (b, h, query row, key
   // half) -- written by the forward, read by the backward instead of regenerating Philox (38 % of its instructions)
   unsigned long long* keep_bits;
+  // optional (seq == 128): packed bins -- row r of bin b may attend to keys [lo, hi) of the same bin only,
+  // seg[b * 128 + r] = lo | hi << 16 (pytorch-distributed-nlp_b200/packing.py); replaces the key-padding mask
+  const int* seg;
 };
+
+// masked-key bits (1 = masked) of the 64 key columns [half * 64, half * 64 + 64) for a row whose keys are [lo, hi)
+__device__ __forceinline__ void seg_key_bits(int seg_word, int half, uint32_t& mb0, uint32_t& mb1) {
+  int lo = (seg_word & 0xffff) - half * 64, hi = (seg_word >> 16) - half * 64;
+  lo = lo < 0 ? 0 : (lo > 64 ? 64 : lo);
+  hi = hi < 0 ? 0 : (hi > 64 ? 64 : hi);
+  unsigned long long allowed = 0ull;
+  if (hi > lo) {
+    const unsigned long long upto_hi = hi == 64 ? ~0ull : ((1ull << hi) - 1ull);
+    const unsigned long long upto_lo = lo == 64 ? ~0ull : ((1ull << lo) - 1ull);
+    allowed = upto_hi & ~upto_lo;
+  }
+  const unsigned long long masked = ~allowed;
+  mb0 = (uint32_t)masked;
+  mb1 = (uint32_t)(masked >> 32);
+}
 
 // Sum v[j] over the 32 lanes for every j: 31 shuffles (butterfly with halving); lane l returns the total of column l.
 __device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
@@ -276,6 +295,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_fwd_kernel(const __grid
 // once S = QK^T has completed), 128 TMEM columns (O overwrites the drained S columns), 16-column register passes
 // (62 registers).  Same arithmetic, same Philox indexing as attention_fwd_kernel.
 // ------------------------------------------------------------------------------------------------------------
+template <bool kSeg>   // kSeg: packed bins (per-row segment mask, p.seg) instead of the key-padding mask
 __global__ void __launch_bounds__(ATT_THREADS, 4) attention_fwd128_kernel(const __grid_constant__ CUtensorMap tmap_qkv,
                                                                          const __grid_constant__ CUtensorMap tmap_ctx,
                                                                          const AttnParams p) {
@@ -322,8 +342,12 @@ __global__ void __launch_bounds__(ATT_THREADS, 4) attention_fwd128_kernel(const 
   const int col_q = h * 64, col_k = p.hidden + h * 64, col_v = 2 * p.hidden + h * 64;
   const DropCtx drop = make_drop_ctx(p.rng, p.rng_site, p.dropout_p);
   const float c2 = p.scale * kLog2e;
-  const uint32_t mb0 = s_mbits[half * 2], mb1 = s_mbits[half * 2 + 1];
-  const bool any_masked = (mb0 | mb1) != 0u;   // warp-uniform
+  uint32_t mb0 = s_mbits[half * 2], mb1 = s_mbits[half * 2 + 1];
+  bool any_masked = (mb0 | mb1) != 0u;   // warp-uniform
+  if (kSeg) {                            // packed bins: the keys of this thread's own sequence only
+    seg_key_bits(p.seg[(size_t)b * 128 + row], half, mb0, mb1);
+    any_masked = __any_sync(0xffffffffu, (mb0 | mb1) != 0u);
+  }
 
   if (tid == 0) {
     mbar_expect_tx(bar_load, 3 * TILE_BYTES);
@@ -469,7 +493,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 4) attention_fwd128_kernel(const 
 // the operand tiles that the last MMAs have released, as TMA tile stores; the key mask is a 64-bit register pair per
 // thread (bit tests, and a warp-uniform fast path when the block has no masked key) instead of a shared-memory
 // float per element.
-template <bool kOneQ>
+template <bool kOneQ, bool kSeg = false>   // kSeg (with kOneQ): packed bins, per-row segment mask (p.seg)
 __global__ void __launch_bounds__(ATT_THREADS, kOneQ ? 2 : 1)
 attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_do,
                      const __grid_constant__ CUtensorMap tmap_o, const __grid_constant__ CUtensorMap tmap_dqkv,
@@ -532,8 +556,12 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_
   const uint32_t tm_s = tmem, tm_dp = tmem + 128;
   const uint32_t tm_dq = tmem + (kOneQ ? 0 : 384), tm_dv = tmem + (kOneQ ? 64 : 256), tm_dk = tmem + (kOneQ ? 128 : 320);
   const uint32_t lane_base = ((uint32_t)((warp & 3) * 32)) << 16;
-  const uint32_t mb0 = s_mbits[half * 2], mb1 = s_mbits[half * 2 + 1];   // this thread's 64 key columns
-  const bool any_masked = (mb0 | mb1) != 0u;                              // warp-uniform
+  uint32_t mb0 = s_mbits[half * 2], mb1 = s_mbits[half * 2 + 1];   // this thread's 64 key columns
+  bool any_masked = (mb0 | mb1) != 0u;                              // warp-uniform
+  if (kOneQ && kSeg) {               // packed bins (seq == 128): `row` is this thread's query row of the only block
+    seg_key_bits(p.seg[(size_t)b * 128 + row], half, mb0, mb1);
+    any_masked = __any_sync(0xffffffffu, (mb0 | mb1) != 0u);
+  }
 
   const int row0 = b * p.seq;
   const int col_q = h * 64, col_k = p.hidden + h * 64, col_v = 2 * p.hidden + h * 64;
@@ -785,11 +813,14 @@ static int32_t check_attn_shapes(const char* who, int64_t batch, int64_t seq, in
 
 using namespace b2;
 
-extern "C" int32_t b2_attention_fwd(const void* qkv, const int64_t* attention_mask, int64_t batch, int64_t seq,
-                                    int64_t heads, int64_t head_dim, float dropout_p, const void* rng_state,
-                                    uint32_t rng_site, void* ctx, float* lse, uint64_t* keep_bits, void* stream_) {
+static int32_t attention_fwd_impl(const void* qkv, const int64_t* attention_mask, const int32_t* segments,
+                                  int64_t batch, int64_t seq, int64_t heads, int64_t head_dim, float dropout_p,
+                                  const void* rng_state, uint32_t rng_site, void* ctx, float* lse,
+                                  uint64_t* keep_bits, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   B2_REQUIRE(qkv && ctx, "attention_fwd: null pointer");
+  B2_REQUIRE(segments == nullptr || (seq == 128 && fwd128_enabled()),
+             "attention_fwd: packed bins are 128 tokens long (seq=%lld)", (long long)seq);
   int32_t st = check_attn_shapes("attention_fwd", batch, seq, heads, head_dim);
   if (st) return st;
   B2_REQUIRE(!(dropout_p > 0.f) || rng_state, "attention_fwd: dropout needs rng_state");
@@ -802,6 +833,7 @@ extern "C" int32_t b2_attention_fwd(const void* qkv, const int64_t* attention_ma
   p.scale = 0.125f;
   p.dropout_p = dropout_p; p.rng = (const unsigned long long*)rng_state; p.rng_site = rng_site;
   p.mask = (const long long*)attention_mask;
+  p.seg = segments;
   p.ctx = (__nv_bfloat16*)ctx; p.lse = lse;
   // the keep-bit cache exists for the seq == 128 kernel pair only (and only when there is dropout to remember)
   p.keep_bits = (seq == 128 && dropout_p > 0.f && fwd128_enabled()) ? (unsigned long long*)keep_bits : nullptr;
@@ -817,12 +849,21 @@ extern "C" int32_t b2_attention_fwd(const void* qkv, const int64_t* attention_ma
   if (seq == 128 && fwd128_enabled()) {
     static bool attr128 = false;
     if (!attr128) {
-      B2_CUDA(cudaFuncSetAttribute(attention_fwd128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwd128Smem));
-      B2_CUDA(cudaFuncSetAttribute(attention_fwd128_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+      B2_CUDA(cudaFuncSetAttribute(attention_fwd128_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   kFwd128Smem));
+      B2_CUDA(cudaFuncSetAttribute(attention_fwd128_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                   cudaSharedmemCarveoutMaxShared));
+      B2_CUDA(cudaFuncSetAttribute(attention_fwd128_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   kFwd128Smem));
+      B2_CUDA(cudaFuncSetAttribute(attention_fwd128_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                    cudaSharedmemCarveoutMaxShared));
       attr128 = true;
     }
-    B2_LAUNCH(attention_fwd128_kernel, grid, ATT_THREADS, kFwd128Smem, stream, tm, tm_ctx, p);
+    if (segments != nullptr) {
+      B2_LAUNCH(attention_fwd128_kernel<true>, grid, ATT_THREADS, kFwd128Smem, stream, tm, tm_ctx, p);
+    } else {
+      B2_LAUNCH(attention_fwd128_kernel<false>, grid, ATT_THREADS, kFwd128Smem, stream, tm, tm_ctx, p);
+    }
     B2_CUDA(cudaGetLastError());
     count_launches(1);
     return 0;
@@ -833,12 +874,31 @@ extern "C" int32_t b2_attention_fwd(const void* qkv, const int64_t* attention_ma
   return 0;
 }
 
-extern "C" int32_t b2_attention_bwd(const void* qkv, const int64_t* attention_mask, const void* ctx, const void* d_ctx,
-                                    const float* lse, int64_t batch, int64_t seq, int64_t heads, int64_t head_dim,
-                                    float dropout_p, const void* rng_state, uint32_t rng_site, void* d_qkv,
-                                    float* dq_accum, float* dbias_accum, const uint64_t* keep_bits, void* stream_) {
+extern "C" int32_t b2_attention_fwd(const void* qkv, const int64_t* attention_mask, int64_t batch, int64_t seq,
+                                    int64_t heads, int64_t head_dim, float dropout_p, const void* rng_state,
+                                    uint32_t rng_site, void* ctx, float* lse, uint64_t* keep_bits, void* stream_) {
+  return attention_fwd_impl(qkv, attention_mask, nullptr, batch, seq, heads, head_dim, dropout_p, rng_state, rng_site,
+                            ctx, lse, keep_bits, stream_);
+}
+
+extern "C" int32_t b2_attention_fwd_packed(const void* qkv, const int32_t* segments, int64_t bins, int64_t heads,
+                                           int64_t head_dim, float dropout_p, const void* rng_state,
+                                           uint32_t rng_site, void* ctx, float* lse, uint64_t* keep_bits,
+                                           void* stream_) {
+  B2_REQUIRE(segments != nullptr, "attention_fwd_packed: null segments");
+  return attention_fwd_impl(qkv, nullptr, segments, bins, 128, heads, head_dim, dropout_p, rng_state, rng_site, ctx,
+                            lse, keep_bits, stream_);
+}
+
+static int32_t attention_bwd_impl(const void* qkv, const int64_t* attention_mask, const int32_t* segments,
+                                  const void* ctx, const void* d_ctx, const float* lse, int64_t batch, int64_t seq,
+                                  int64_t heads, int64_t head_dim, float dropout_p, const void* rng_state,
+                                  uint32_t rng_site, void* d_qkv, float* dq_accum, float* dbias_accum,
+                                  const uint64_t* keep_bits, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   B2_REQUIRE(qkv && ctx && d_ctx && lse && d_qkv, "attention_bwd: null pointer");
+  B2_REQUIRE(segments == nullptr || seq == 128, "attention_bwd: packed bins are 128 tokens long (seq=%lld)",
+             (long long)seq);
   int32_t st = check_attn_shapes("attention_bwd", batch, seq, heads, head_dim);
   if (st) return st;
   B2_REQUIRE(!(dropout_p > 0.f) || rng_state, "attention_bwd: dropout needs rng_state");
@@ -859,6 +919,7 @@ extern "C" int32_t b2_attention_bwd(const void* qkv, const int64_t* attention_ma
   p.scale = 0.125f;
   p.dropout_p = dropout_p; p.rng = (const unsigned long long*)rng_state; p.rng_site = rng_site;
   p.mask = (const long long*)attention_mask;
+  p.seg = segments;
   p.lse = const_cast<float*>(lse);
   p.ctx_in = (const __nv_bfloat16*)ctx; p.d_ctx = (const __nv_bfloat16*)d_ctx;
   p.d_qkv = (__nv_bfloat16*)d_qkv;
@@ -875,10 +936,17 @@ extern "C" int32_t b2_attention_bwd(const void* qkv, const int64_t* attention_ma
                                  kBwdSmemOneQ));
     B2_CUDA(cudaFuncSetAttribute(attention_bwd_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                  cudaSharedmemCarveoutMaxShared));
+    B2_CUDA((cudaFuncSetAttribute(attention_bwd_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  kBwdSmemOneQ)));
+    B2_CUDA((cudaFuncSetAttribute(attention_bwd_kernel<true, true>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                  cudaSharedmemCarveoutMaxShared)));
     attr = true;
   }
   dim3 grid((unsigned)(seq / 128), (unsigned)heads, (unsigned)batch);
-  if (seq == 128) {
+  if (seq == 128 && segments != nullptr) {
+    B2_LAUNCH((attention_bwd_kernel<true, true>), grid, ATT_THREADS, kBwdSmemOneQ, stream, tm_qkv, tm_do, tm_o, tm_dqkv,
+              p);
+  } else if (seq == 128) {
     B2_LAUNCH(attention_bwd_kernel<true>, grid, ATT_THREADS, kBwdSmemOneQ, stream, tm_qkv, tm_do, tm_o, tm_dqkv, p);
   } else {
     B2_LAUNCH(attention_bwd_kernel<false>, grid, ATT_THREADS, kBwdSmem, stream, tm_qkv, tm_do, tm_o, tm_dqkv, p);
@@ -893,4 +961,21 @@ extern "C" int32_t b2_attention_bwd(const void* qkv, const int64_t* attention_ma
     count_launches(1);
   }
   return 0;
+}
+
+extern "C" int32_t b2_attention_bwd(const void* qkv, const int64_t* attention_mask, const void* ctx, const void* d_ctx,
+                                    const float* lse, int64_t batch, int64_t seq, int64_t heads, int64_t head_dim,
+                                    float dropout_p, const void* rng_state, uint32_t rng_site, void* d_qkv,
+                                    float* dq_accum, float* dbias_accum, const uint64_t* keep_bits, void* stream_) {
+  return attention_bwd_impl(qkv, attention_mask, nullptr, ctx, d_ctx, lse, batch, seq, heads, head_dim, dropout_p,
+                            rng_state, rng_site, d_qkv, dq_accum, dbias_accum, keep_bits, stream_);
+}
+
+extern "C" int32_t b2_attention_bwd_packed(const void* qkv, const int32_t* segments, const void* ctx,
+                                           const void* d_ctx, const float* lse, int64_t bins, int64_t heads,
+                                           int64_t head_dim, float dropout_p, const void* rng_state, uint32_t rng_site,
+                                           void* d_qkv, float* dbias_accum, const uint64_t* keep_bits, void* stream_) {
+  B2_REQUIRE(segments != nullptr, "attention_bwd_packed: null segments");
+  return attention_bwd_impl(qkv, nullptr, segments, ctx, d_ctx, lse, bins, 128, heads, head_dim, dropout_p, rng_state,
+                            rng_site, d_qkv, nullptr, dbias_accum, keep_bits, stream_);
 }

@@ -8,6 +8,7 @@
 // monotonically increasing epoch into flags[slot][q] with a system-scope release; r spins (bounded) with
 // system-scope acquire loads.  Epochs live in device memory so CUDA-graph replays stay in lock step.
 #include "common.cuh"
+#include <cstdlib>
 #include <cstring>
 #include "../../include/b2_ddp_bert.h"
 
@@ -28,25 +29,40 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
   return v;
 }
 
-// executed by threads 0..world-1 of ONE block; all earlier writes of this block must be fenced by the caller
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// executed by threads 0..world-1 of ONE block; all earlier writes of this block must be fenced by the caller.
+// Bounded by WALL-CLOCK time (timeout_ns, default 30 s, B2_BARRIER_TIMEOUT_S): a rank that died or diverged must
+// surface as a trapped kernel (-> CUDA error -> RuntimeError on the host) within seconds, not hang the job; a peer
+// that is legitimately late (rank 0 writing a checkpoint between two steps) gets that long.
 __device__ __forceinline__ void barrier_signal_wait(const PeerPtrs& flags, int world, int rank, int slot,
-                                                    uint32_t epoch) {
+                                                    uint32_t epoch, unsigned long long timeout_ns) {
   const int r = threadIdx.x;
   if (r < world) {
     uint32_t* remote = reinterpret_cast<uint32_t*>(flags.p[r]) + slot * world + rank;
     st_release_sys(remote, epoch);
     const uint32_t* mine = reinterpret_cast<const uint32_t*>(flags.p[rank]) + slot * world + r;
-    unsigned long long spins = 0;
+    unsigned long long t0 = 0;
+    uint32_t spins = 0;
     while ((int32_t)(ld_acquire_sys(mine) - epoch) < 0) {
-      if (++spins > (1ull << 31)) {
-        printf("b2: peer barrier timed out (rank %d waiting for rank %d, slot %d, epoch %u)\n", rank, r, slot, epoch);
-        __trap();
+      if ((++spins & 0x3ffu) == 0) {          // look at the clock every 1024 polls
+        const unsigned long long now = global_timer_ns();
+        if (t0 == 0) t0 = now;
+        if (now - t0 > timeout_ns) {
+          printf("b2: peer barrier timed out after %.1f s (rank %d waiting for rank %d, slot %d, epoch %u)\n",
+                 (double)(now - t0) * 1e-9, rank, r, slot, epoch);
+          __trap();
+        }
       }
     }
   }
 }
 
-__global__ void peer_barrier_kernel(PeerPtrs flags, int world, int rank, int slot, uint32_t* epoch_ctr) {
+__global__ void peer_barrier_kernel(PeerPtrs flags, int world, int rank, int slot, uint32_t* epoch_ctr,
+                                    unsigned long long timeout_ns) {
   pdl_wait();               // PDL: predecessors complete + visible before any global access
   pdl_launch_dependents();  // let the next kernel in the stream begin launching
   __shared__ uint32_t epoch;
@@ -56,12 +72,13 @@ __global__ void peer_barrier_kernel(PeerPtrs flags, int world, int rank, int slo
   }
   __syncthreads();
   __threadfence_system();
-  barrier_signal_wait(flags, world, rank, slot, epoch);
+  barrier_signal_wait(flags, world, rank, slot, epoch, timeout_ns);
 }
 
 // every rank stores `bytes` (multiple of 4) into slot `rank` of every peer's buffer, then barrier
 __global__ void allgather_rows_kernel(const uint32_t* __restrict__ src, long long words, PeerPtrs dst,
-                                      PeerPtrs flags, int world, int rank, int slot, uint32_t* epoch_ctr) {
+                                      PeerPtrs flags, int world, int rank, int slot, uint32_t* epoch_ctr,
+                                      unsigned long long timeout_ns) {
   pdl_wait();               // PDL: predecessors complete + visible before any global access
   pdl_launch_dependents();  // let the next kernel in the stream begin launching
   __shared__ uint32_t epoch;
@@ -75,12 +92,13 @@ __global__ void allgather_rows_kernel(const uint32_t* __restrict__ src, long lon
   }
   __threadfence_system();
   __syncthreads();
-  barrier_signal_wait(flags, world, rank, slot, epoch);
+  barrier_signal_wait(flags, world, rank, slot, epoch, timeout_ns);
 }
 
 // mean of one fp32 scalar over ranks; scratch is float[2][world] on every rank (double-buffered by epoch parity)
 __global__ void scalar_allreduce_mean_kernel(const float* __restrict__ src, float* __restrict__ dst, PeerPtrs scratch,
-                                             PeerPtrs flags, int world, int rank, int slot, uint32_t* epoch_ctr) {
+                                             PeerPtrs flags, int world, int rank, int slot, uint32_t* epoch_ctr,
+                                      unsigned long long timeout_ns) {
   pdl_wait();               // PDL: predecessors complete + visible before any global access
   pdl_launch_dependents();  // let the next kernel in the stream begin launching
   __shared__ uint32_t epoch;
@@ -94,7 +112,7 @@ __global__ void scalar_allreduce_mean_kernel(const float* __restrict__ src, floa
     reinterpret_cast<float*>(scratch.p[threadIdx.x])[par * world + rank] = *src;
   __threadfence_system();
   __syncthreads();
-  barrier_signal_wait(flags, world, rank, slot, epoch);
+  barrier_signal_wait(flags, world, rank, slot, epoch, timeout_ns);
   __syncthreads();
   if (threadIdx.x == 0) {
     const volatile float* mine = reinterpret_cast<const volatile float*>(scratch.p[rank]) + par * world;
@@ -102,6 +120,17 @@ __global__ void scalar_allreduce_mean_kernel(const float* __restrict__ src, floa
     for (int r = 0; r < world; ++r) s += mine[r];  // fixed order: identical result on every rank
     *dst = s / (float)world;
   }
+}
+
+static unsigned long long barrier_timeout_ns() {
+  static unsigned long long v = 0;
+  if (v == 0) {
+    const char* e = getenv("B2_BARRIER_TIMEOUT_S");
+    double sec = e != nullptr ? atof(e) : 30.0;
+    if (!(sec > 0.0)) sec = 30.0;
+    v = (unsigned long long)(sec * 1e9);
+  }
+  return v;
 }
 
 static int32_t fill_peers(PeerPtrs* out, void* const* in, int world, const char* what) {
@@ -159,7 +188,8 @@ extern "C" int32_t b2_peer_barrier(void* const* peer_flags, int32_t world, int32
   PeerPtrs f;
   int32_t st = fill_peers(&f, peer_flags, world, "peer_barrier");
   if (st) return st;
-  B2_LAUNCH(peer_barrier_kernel, 1, 32, 0, (cudaStream_t)stream_, f, world, rank, slot, epoch);
+  B2_LAUNCH(peer_barrier_kernel, 1, 32, 0, (cudaStream_t)stream_, f, world, rank, slot, epoch,
+            barrier_timeout_ns());
   B2_CUDA(cudaGetLastError());
   count_launches(1);
   return 0;
@@ -179,7 +209,7 @@ extern "C" int32_t b2_allgather_rows(const void* src, int64_t bytes, void* const
   st = fill_peers(&f, peer_flags, world, "allgather_rows(flags)");
   if (st) return st;
   B2_LAUNCH(allgather_rows_kernel, 1, 256, 0, (cudaStream_t)stream_, (const uint32_t*)src, bytes / 4, d, f, world, rank, slot,
-                                                              epoch);
+                                                              epoch, barrier_timeout_ns());
   B2_CUDA(cudaGetLastError());
   count_launches(1);
   return 0;
@@ -197,7 +227,8 @@ extern "C" int32_t b2_scalar_allreduce_mean(const float* src, float* dst, float*
   if (st) return st;
   st = fill_peers(&f, peer_flags, world, "scalar_allreduce_mean(flags)");
   if (st) return st;
-  B2_LAUNCH(scalar_allreduce_mean_kernel, 1, 32, 0, (cudaStream_t)stream_, src, dst, s, f, world, rank, slot, epoch);
+  B2_LAUNCH(scalar_allreduce_mean_kernel, 1, 32, 0, (cudaStream_t)stream_, src, dst, s, f, world, rank, slot, epoch,
+            barrier_timeout_ns());
   B2_CUDA(cudaGetLastError());
   count_launches(1);
   return 0;

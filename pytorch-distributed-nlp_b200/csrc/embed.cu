@@ -17,7 +17,9 @@ namespace b2 {
 
 template <int VPL>
 __global__ void __launch_bounds__(128) embed_fwd_kernel(
-    const long long* __restrict__ input_ids, const long long* __restrict__ token_type_ids, int tokens, int seq,
+    const long long* __restrict__ input_ids, const long long* __restrict__ token_type_ids,
+    const long long* __restrict__ position_ids /* null: position = token index % seq */, int max_pos,
+    int* __restrict__ pos32 /* null unless position_ids */, int tokens, int seq,
     const __nv_bfloat16* __restrict__ word, const __nv_bfloat16* __restrict__ pos,
     const __nv_bfloat16* __restrict__ type, const __nv_bfloat16* __restrict__ gamma,
     const __nv_bfloat16* __restrict__ beta, int vocab, int type_vocab, float eps, float dropout_p,
@@ -35,7 +37,11 @@ __global__ void __launch_bounds__(128) embed_fwd_kernel(
   // out-of-range ids would be a host bug; clamp so a bad batch cannot fault the GPU (host validates too)
   id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
   tt = tt < 0 ? 0 : (tt >= type_vocab ? type_vocab - 1 : tt);
-  const int s = t % seq;
+  int s = t % seq;
+  if (position_ids != nullptr) {       // packed bins: every token keeps the position it had in its own sequence
+    const long long ps = position_ids[t];
+    s = ps < 0 ? 0 : (ps >= max_pos ? max_pos - 1 : (int)ps);
+  }
   float v[VPL * 8], a[VPL * 8];
   load_row<VPL>(word + (size_t)id * H, lane, v);
   load_row<VPL>(pos + (size_t)s * H, lane, a);
@@ -63,6 +69,7 @@ __global__ void __launch_bounds__(128) embed_fwd_kernel(
     rstd_out[t] = rstd;
     ids32[t] = (int)id;
     tt32[t] = (int)tt;
+    if (pos32 != nullptr) pos32[t] = s;
   }
 }
 
@@ -182,8 +189,9 @@ __global__ void embed_word_finish_kernel(const float* __restrict__ acc, const in
 // position rows and per-position token-type partial sums in one pass: CTA s walks the batch once.
 //   d_pos[s] = sum_b dx[b*seq + s];  type_part[s][ty] = sum over the same rows with tt == ty (fp32, ty < T <= 3)
 constexpr int kMaxTypeFast = 3;
-__global__ void embed_pos_type_kernel(const __nv_bfloat16* __restrict__ dx, const int* __restrict__ tt32, int batch,
-                                      int seq, int H, int T, __nv_bfloat16* __restrict__ d_pos,
+__global__ void embed_pos_type_kernel(const __nv_bfloat16* __restrict__ dx, const int* __restrict__ tt32,
+                                      const int* __restrict__ pos32 /* null: position = token index % seq */,
+                                      int batch, int seq, int H, int T, __nv_bfloat16* __restrict__ d_pos,
                                       float* __restrict__ type_part /* [seq][T][H] */) {
   pdl_wait();               // PDL: predecessors complete + visible before any global access
   pdl_launch_dependents();  // let the next kernel in the stream begin launching
@@ -194,8 +202,11 @@ __global__ void embed_pos_type_kernel(const __nv_bfloat16* __restrict__ dx, cons
   for (int k = 0; k < kMaxTypeFast; ++k)
 #pragma unroll
     for (int i = 0; i < 8; ++i) ty[k][i] = 0.f;
-  for (int b = 0; b < batch; ++b) {
-    const size_t r = (size_t)b * seq + s;
+  // packed bins (pos32): the rows with position s are scattered -- walk every token, block-uniform test
+  const int nrows = pos32 != nullptr ? batch * seq : batch;
+  for (int b = 0; b < nrows; ++b) {
+    const size_t r = pos32 != nullptr ? (size_t)b : (size_t)b * seq + s;
+    if (pos32 != nullptr && pos32[r] != s) continue;
     const int tt = tt32[r];
     const uint4 v = ldg16(dx + r * H + threadIdx.x * 8);
     const float f[8] = {bf16_lo(v.x), bf16_hi(v.x), bf16_lo(v.y), bf16_hi(v.y),
@@ -233,11 +244,12 @@ __global__ void fill_int_kernel(int* p, int n, int v) {
 
 using namespace b2;
 
-extern "C" int32_t b2_embed_fwd(const int64_t* input_ids, const int64_t* token_type_ids, int64_t batch, int64_t seq,
-                                const void* word_emb, const void* pos_emb, const void* type_emb, const void* gamma,
-                                const void* beta, int64_t hidden, int64_t vocab, int64_t type_vocab, float eps,
-                                float dropout_p, const void* rng_state, uint32_t rng_site, void* y, void* pre_ln,
-                                float* mean, float* rstd, int32_t* ids32, int32_t* tt32, void* stream_) {
+static int32_t embed_fwd_impl(const int64_t* input_ids, const int64_t* token_type_ids, const int64_t* position_ids,
+                              int64_t max_pos, int32_t* pos32, int64_t batch, int64_t seq, const void* word_emb,
+                              const void* pos_emb, const void* type_emb, const void* gamma, const void* beta,
+                              int64_t hidden, int64_t vocab, int64_t type_vocab, float eps, float dropout_p,
+                              const void* rng_state, uint32_t rng_site, void* y, void* pre_ln, float* mean,
+                              float* rstd, int32_t* ids32, int32_t* tt32, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   B2_REQUIRE(input_ids && word_emb && pos_emb && type_emb && gamma && beta && y && pre_ln && mean && rstd && ids32 &&
                  tt32,
@@ -251,7 +263,8 @@ extern "C" int32_t b2_embed_fwd(const int64_t* input_ids, const int64_t* token_t
 #define B2_EMB(VPL_)                                                                                              \
   case VPL_:                                                                                                      \
     B2_LAUNCH((embed_fwd_kernel<VPL_>), grid, 128, 0, stream,                                                              \
-        (const long long*)input_ids, (const long long*)token_type_ids, tokens, (int)seq,                          \
+        (const long long*)input_ids, (const long long*)token_type_ids, (const long long*)position_ids,            \
+        (int)max_pos, pos32, tokens, (int)seq,                                                                    \
         (const __nv_bfloat16*)word_emb, (const __nv_bfloat16*)pos_emb, (const __nv_bfloat16*)type_emb,            \
         (const __nv_bfloat16*)gamma, (const __nv_bfloat16*)beta, (int)vocab, (int)type_vocab, eps, dropout_p,     \
         (const unsigned long long*)rng_state, rng_site, (__nv_bfloat16*)y, (__nv_bfloat16*)pre_ln, mean, rstd,    \
@@ -264,9 +277,33 @@ extern "C" int32_t b2_embed_fwd(const int64_t* input_ids, const int64_t* token_t
   return 0;
 }
 
-extern "C" int32_t b2_embed_bwd(const void* dy, int32_t dy_fp32, const void* pre_ln, const float* mean,
+extern "C" int32_t b2_embed_fwd(const int64_t* input_ids, const int64_t* token_type_ids, int64_t batch, int64_t seq,
+                                const void* word_emb, const void* pos_emb, const void* type_emb, const void* gamma,
+                                const void* beta, int64_t hidden, int64_t vocab, int64_t type_vocab, float eps,
+                                float dropout_p, const void* rng_state, uint32_t rng_site, void* y, void* pre_ln,
+                                float* mean, float* rstd, int32_t* ids32, int32_t* tt32, void* stream_) {
+  return embed_fwd_impl(input_ids, token_type_ids, nullptr, 0, nullptr, batch, seq, word_emb, pos_emb, type_emb, gamma,
+                        beta, hidden, vocab, type_vocab, eps, dropout_p, rng_state, rng_site, y, pre_ln, mean, rstd,
+                        ids32, tt32, stream_);
+}
+
+extern "C" int32_t b2_embed_fwd_packed(const int64_t* input_ids, const int64_t* token_type_ids,
+                                       const int64_t* position_ids, int64_t max_positions, int64_t bins, int64_t seq,
+                                       const void* word_emb, const void* pos_emb, const void* type_emb,
+                                       const void* gamma, const void* beta, int64_t hidden, int64_t vocab,
+                                       int64_t type_vocab, float eps, float dropout_p, const void* rng_state,
+                                       uint32_t rng_site, void* y, void* pre_ln, float* mean, float* rstd,
+                                       int32_t* ids32, int32_t* tt32, int32_t* pos32, void* stream_) {
+  B2_REQUIRE(position_ids && pos32 && max_positions > 0, "embed_fwd_packed: position ids / pos32 / max_positions");
+  return embed_fwd_impl(input_ids, token_type_ids, position_ids, max_positions, pos32, bins, seq, word_emb, pos_emb,
+                        type_emb, gamma, beta, hidden, vocab, type_vocab, eps, dropout_p, rng_state, rng_site, y,
+                        pre_ln, mean, rstd, ids32, tt32, stream_);
+}
+
+static int32_t embed_bwd_impl(const void* dy, int32_t dy_fp32, const void* pre_ln, const float* mean,
                                 const float* rstd,
-                                const void* gamma, const int32_t* ids32, const int32_t* tt32, int64_t batch,
+                                const void* gamma, const int32_t* ids32, const int32_t* tt32, const int32_t* pos32,
+                                int64_t batch,
                                 int64_t seq, int64_t hidden, int64_t vocab, int64_t type_vocab, int64_t pad_token_id,
                                 float dropout_p, const void* rng_state, uint32_t rng_site, void* d_word, void* d_pos,
                                 void* d_type,
@@ -303,13 +340,15 @@ extern "C" int32_t b2_embed_bwd(const void* dy, int32_t dy_fp32, const void* pre
     B2_CUDA(cudaGetLastError());
     count_launches(1);
     B2_LAUNCH(embed_pos_type_kernel, (unsigned)seq, (unsigned)(hidden / 8), 0, stream, (const __nv_bfloat16*)scratch_dx,
-              tt32, (int)batch, (int)seq, (int)hidden, (int)type_vocab, (__nv_bfloat16*)d_pos, type_part);
+              tt32, pos32, (int)batch, (int)seq, (int)hidden, (int)type_vocab, (__nv_bfloat16*)d_pos, type_part);
     B2_CUDA(cudaGetLastError());
     count_launches(1);
     __nv_bfloat16* dt = (__nv_bfloat16*)d_type;
     return b2_colsum_finish(type_part, (int32_t)seq, (int32_t)type_vocab, hidden, dt,
                             type_vocab > 1 ? dt + hidden : nullptr, type_vocab > 2 ? dt + 2 * hidden : nullptr, stream_);
   }
+  B2_REQUIRE(pos32 == nullptr, "embed_bwd_packed: scratch too small for the packed path (%lld bytes needed)",
+             (long long)fast_bytes);
   B2_LAUNCH(embed_word_scatter_kernel, tokens, 128, 0, stream, (const __nv_bfloat16*)scratch_dx, ids32, tokens, (int)hidden,
                                                         (int)pad_token_id, owner, (__nv_bfloat16*)d_word);
   B2_CUDA(cudaGetLastError());
@@ -327,6 +366,32 @@ extern "C" int32_t b2_embed_bwd(const void* dy, int32_t dy_fp32, const void* pre
     if (st) return st;
   }
   return 0;
+}
+
+extern "C" int32_t b2_embed_bwd(const void* dy, int32_t dy_fp32, const void* pre_ln, const float* mean,
+                                const float* rstd, const void* gamma, const int32_t* ids32, const int32_t* tt32,
+                                int64_t batch, int64_t seq, int64_t hidden, int64_t vocab, int64_t type_vocab,
+                                int64_t pad_token_id, float dropout_p, const void* rng_state, uint32_t rng_site,
+                                void* d_word, void* d_pos, void* d_type, void* d_gamma, void* d_beta, void* scratch_dx,
+                                float* scratch_partials, int64_t scratch_partials_bytes, int32_t* owner,
+                                void* stream_) {
+  return embed_bwd_impl(dy, dy_fp32, pre_ln, mean, rstd, gamma, ids32, tt32, nullptr, batch, seq, hidden, vocab,
+                        type_vocab, pad_token_id, dropout_p, rng_state, rng_site, d_word, d_pos, d_type, d_gamma,
+                        d_beta, scratch_dx, scratch_partials, scratch_partials_bytes, owner, stream_);
+}
+
+extern "C" int32_t b2_embed_bwd_packed(const void* dy, int32_t dy_fp32, const void* pre_ln, const float* mean,
+                                       const float* rstd, const void* gamma, const int32_t* ids32,
+                                       const int32_t* tt32, const int32_t* pos32, int64_t bins, int64_t seq,
+                                       int64_t hidden, int64_t vocab, int64_t type_vocab, int64_t pad_token_id,
+                                       float dropout_p, const void* rng_state, uint32_t rng_site, void* d_word,
+                                       void* d_pos, void* d_type, void* d_gamma, void* d_beta, void* scratch_dx,
+                                       float* scratch_partials, int64_t scratch_partials_bytes, int32_t* owner,
+                                       void* stream_) {
+  B2_REQUIRE(pos32 != nullptr, "embed_bwd_packed: null pos32");
+  return embed_bwd_impl(dy, dy_fp32, pre_ln, mean, rstd, gamma, ids32, tt32, pos32, bins, seq, hidden, vocab,
+                        type_vocab, pad_token_id, dropout_p, rng_state, rng_site, d_word, d_pos, d_type, d_gamma,
+                        d_beta, scratch_dx, scratch_partials, scratch_partials_bytes, owner, stream_);
 }
 
 // arms the owner table (INT_MAX) once; the scatter kernel re-arms what it touched

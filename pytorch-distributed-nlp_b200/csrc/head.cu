@@ -22,7 +22,9 @@ __device__ __forceinline__ float warp_dot_bf16(const __nv_bfloat16* __restrict__
 
 // pooled[b, j] = tanh(h[b*seq, :] . Wp[j, :] + bp[j]); one warp per (j, group of 8 batch rows): the weight row is
 // read once per warp and reused for the 8 dot products.  grid = (H/8, ceil(batch/8))
-__global__ void __launch_bounds__(256) pooler_fwd_kernel(const __nv_bfloat16* __restrict__ h, int batch, int seq,
+// cls_rows (optional, packed bins): row of sequence b's first token; default b * seq
+__global__ void __launch_bounds__(256) pooler_fwd_kernel(const __nv_bfloat16* __restrict__ h,
+                                                        const long long* __restrict__ cls_rows, int batch, int seq,
                                                         int H, const __nv_bfloat16* __restrict__ Wp,
                                                         const __nv_bfloat16* __restrict__ bp,
                                                         __nv_bfloat16* __restrict__ pooled) {
@@ -40,7 +42,8 @@ __global__ void __launch_bounds__(256) pooler_fwd_kernel(const __nv_bfloat16* __
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       if (b0 + i < batch) {
-        const uint4 x = ldg16(h + (size_t)(b0 + i) * seq * H + c);
+        const size_t r = cls_rows != nullptr ? (size_t)cls_rows[b0 + i] : (size_t)(b0 + i) * seq;
+        const uint4 x = ldg16(h + r * H + c);
         acc[i] += wv[0] * bf16_lo(x.x) + wv[1] * bf16_hi(x.x) + wv[2] * bf16_lo(x.y) + wv[3] * bf16_hi(x.y) +
                   wv[4] * bf16_lo(x.z) + wv[5] * bf16_hi(x.z) + wv[6] * bf16_lo(x.w) + wv[7] * bf16_hi(x.w);
       }
@@ -187,8 +190,9 @@ __global__ void __launch_bounds__(256) head_bwd_k1b(const float* __restrict__ dl
 
 // k2: d_pool_w[j, k] = sum_b d_pre[b, j] * h0[b, k];  d_pool_b[j] = sum_b d_pre[b, j].
 //     grid = H rows (j), threads = H/8 (each 8 consecutive k)
-__global__ void head_bwd_k2(const float* __restrict__ d_pre, const __nv_bfloat16* __restrict__ h, int batch, int seq,
-                            int H, __nv_bfloat16* __restrict__ d_pool_w, __nv_bfloat16* __restrict__ d_pool_b) {
+__global__ void head_bwd_k2(const float* __restrict__ d_pre, const __nv_bfloat16* __restrict__ h,
+                            const long long* __restrict__ cls_rows, int batch, int seq, int H,
+                            __nv_bfloat16* __restrict__ d_pool_w, __nv_bfloat16* __restrict__ d_pool_b) {
   pdl_wait();               // PDL: predecessors complete + visible before any global access
   pdl_launch_dependents();  // let the next kernel in the stream begin launching
   const int j = blockIdx.x;
@@ -198,7 +202,8 @@ __global__ void head_bwd_k2(const float* __restrict__ d_pre, const __nv_bfloat16
   for (int b = 0; b < batch; ++b) {
     const float d = d_pre[(size_t)b * H + j];
     sb += d;
-    const uint4 x = ldg16(h + (size_t)b * seq * H + k);
+    const size_t r = cls_rows != nullptr ? (size_t)cls_rows[b] : (size_t)b * seq;
+    const uint4 x = ldg16(h + r * H + k);
     acc[0] += d * bf16_lo(x.x); acc[1] += d * bf16_hi(x.x); acc[2] += d * bf16_lo(x.y); acc[3] += d * bf16_hi(x.y);
     acc[4] += d * bf16_lo(x.z); acc[5] += d * bf16_hi(x.z); acc[6] += d * bf16_lo(x.w); acc[7] += d * bf16_hi(x.w);
   }
@@ -212,7 +217,8 @@ __global__ void head_bwd_k2(const float* __restrict__ d_pre, const __nv_bfloat16
 // k3: d_h0[b, k] = sum_j d_pre[b, j] * Wp[j, k]  -> written into row b*seq of d_hidden (other rows pre-zeroed)
 //     grid = (batch, H/64), 8 warps: warp w sums its eighth of the j range for 64 columns (2 per lane), smem reduce
 __global__ void __launch_bounds__(256) head_bwd_k3(const float* __restrict__ d_pre,
-                                                  const __nv_bfloat16* __restrict__ Wp, int seq, int H,
+                                                  const __nv_bfloat16* __restrict__ Wp,
+                                                  const long long* __restrict__ cls_rows, int seq, int H,
                                                   void* __restrict__ d_hidden, int out_f32) {
   pdl_wait();               // PDL: predecessors complete + visible before any global access
   pdl_launch_dependents();  // let the next kernel in the stream begin launching
@@ -235,7 +241,8 @@ __global__ void __launch_bounds__(256) head_bwd_k3(const float* __restrict__ d_p
     float s = 0.f;
 #pragma unroll
     for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
-    const size_t o = (size_t)b * seq * H + blockIdx.y * 64 + threadIdx.x;
+    const size_t r = cls_rows != nullptr ? (size_t)cls_rows[b] : (size_t)b * seq;
+    const size_t o = r * H + blockIdx.y * 64 + threadIdx.x;
     if (out_f32) reinterpret_cast<float*>(d_hidden)[o] = s;
     else reinterpret_cast<__nv_bfloat16*>(d_hidden)[o] = __float2bfloat16_rn(s);
   }
@@ -245,18 +252,18 @@ __global__ void __launch_bounds__(256) head_bwd_k3(const float* __restrict__ d_p
 
 using namespace b2;
 
-extern "C" int32_t b2_head_fwd(const void* hidden_states, int64_t batch, int64_t seq, int64_t hidden,
-                               const void* pool_w, const void* pool_b, const void* cls_w, const void* cls_b,
-                               int64_t num_labels, float dropout_p, const void* rng_state, uint32_t rng_site,
-                               void* pooled, float* logits, void* stream_) {
+static int32_t head_fwd_impl(const void* hidden_states, const int64_t* cls_rows, int64_t batch, int64_t seq,
+                             int64_t hidden, const void* pool_w, const void* pool_b, const void* cls_w,
+                             const void* cls_b, int64_t num_labels, float dropout_p, const void* rng_state,
+                             uint32_t rng_site, void* pooled, float* logits, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   B2_REQUIRE(hidden_states && pool_w && pool_b && cls_w && cls_b && pooled && logits, "head_fwd: null pointer");
   B2_REQUIRE(batch > 0 && seq > 0 && num_labels > 0, "head_fwd: empty problem");
   B2_REQUIRE(hidden % 256 == 0, "head_fwd: hidden=%lld must be a multiple of 256", (long long)hidden);
   B2_REQUIRE(!(dropout_p > 0.f) || rng_state, "head_fwd: dropout needs rng_state");
   B2_LAUNCH(pooler_fwd_kernel, dim3((unsigned)((hidden + 7) / 8), (unsigned)((batch + 7) / 8)), 256, 0, stream, 
-      (const __nv_bfloat16*)hidden_states, (int)batch, (int)seq, (int)hidden, (const __nv_bfloat16*)pool_w,
-      (const __nv_bfloat16*)pool_b, (__nv_bfloat16*)pooled);
+      (const __nv_bfloat16*)hidden_states, (const long long*)cls_rows, (int)batch, (int)seq, (int)hidden,
+      (const __nv_bfloat16*)pool_w, (const __nv_bfloat16*)pool_b, (__nv_bfloat16*)pooled);
   B2_CUDA(cudaGetLastError());
   count_launches(1);
   B2_LAUNCH(classifier_fwd_kernel, (unsigned)((batch * num_labels + 7) / 8), 256, 0, stream, 
@@ -265,6 +272,23 @@ extern "C" int32_t b2_head_fwd(const void* hidden_states, int64_t batch, int64_t
   B2_CUDA(cudaGetLastError());
   count_launches(1);
   return 0;
+}
+
+extern "C" int32_t b2_head_fwd(const void* hidden_states, int64_t batch, int64_t seq, int64_t hidden,
+                               const void* pool_w, const void* pool_b, const void* cls_w, const void* cls_b,
+                               int64_t num_labels, float dropout_p, const void* rng_state, uint32_t rng_site,
+                               void* pooled, float* logits, void* stream_) {
+  return head_fwd_impl(hidden_states, nullptr, batch, seq, hidden, pool_w, pool_b, cls_w, cls_b, num_labels,
+                       dropout_p, rng_state, rng_site, pooled, logits, stream_);
+}
+
+extern "C" int32_t b2_head_fwd_packed(const void* hidden_states, const int64_t* cls_rows, int64_t batch,
+                                      int64_t hidden, const void* pool_w, const void* pool_b, const void* cls_w,
+                                      const void* cls_b, int64_t num_labels, float dropout_p, const void* rng_state,
+                                      uint32_t rng_site, void* pooled, float* logits, void* stream_) {
+  B2_REQUIRE(cls_rows != nullptr, "head_fwd_packed: null cls_rows");
+  return head_fwd_impl(hidden_states, cls_rows, batch, 1, hidden, pool_w, pool_b, cls_w, cls_b, num_labels,
+                       dropout_p, rng_state, rng_site, pooled, logits, stream_);
 }
 
 extern "C" int32_t b2_ce_fwd_bwd(const float* logits, const int64_t* labels, int64_t batch, int64_t num_labels,
@@ -278,7 +302,8 @@ extern "C" int32_t b2_ce_fwd_bwd(const float* logits, const int64_t* labels, int
   return 0;
 }
 
-extern "C" int32_t b2_head_bwd(const float* dlogits, const void* hidden_states, const void* pooled, int64_t batch,
+static int32_t head_bwd_impl(const float* dlogits, const void* hidden_states, const void* pooled,
+                             const int64_t* cls_rows, int64_t tokens, int64_t batch,
                                int64_t seq, int64_t hidden, const void* pool_w, const void* cls_w, int64_t num_labels,
                                float dropout_p, const void* rng_state, uint32_t rng_site, void* d_pool_w,
                                void* d_pool_b, void* d_cls_w, void* d_cls_b, void* d_hidden, int32_t d_hidden_fp32,
@@ -290,7 +315,7 @@ extern "C" int32_t b2_head_bwd(const float* dlogits, const void* hidden_states, 
   B2_REQUIRE(batch > 0 && seq > 0, "head_bwd: empty batch");
   B2_REQUIRE(hidden % 256 == 0 && hidden / 8 <= 1024, "head_bwd: hidden=%lld unsupported", (long long)hidden);
   B2_REQUIRE(num_labels >= 1 && num_labels <= 65535, "head_bwd: num_labels=%lld", (long long)num_labels);
-  B2_CUDA(cudaMemsetAsync(d_hidden, 0, (size_t)batch * seq * hidden * (d_hidden_fp32 ? 4 : 2), stream));
+  B2_CUDA(cudaMemsetAsync(d_hidden, 0, (size_t)tokens * hidden * (d_hidden_fp32 ? 4 : 2), stream));
   float* pm = scratch + (size_t)batch * hidden;   // second scratch plane: dropout(pooled)
   B2_LAUNCH(head_bwd_k1, dim3((unsigned)((hidden + 255) / 256), (unsigned)batch), 256, 0, stream, dlogits,
             (const __nv_bfloat16*)pooled, (int)batch, (int)hidden, (const __nv_bfloat16*)cls_w, (int)num_labels,
@@ -299,7 +324,8 @@ extern "C" int32_t b2_head_bwd(const float* dlogits, const void* hidden_states, 
   count_launches(1);
   // the critical path continues with k3 (d_hidden); the two weight-gradient kernels follow it
   B2_LAUNCH(head_bwd_k3, dim3((unsigned)batch, (unsigned)(hidden / 64)), 256, 0, stream, scratch,
-            (const __nv_bfloat16*)pool_w, (int)seq, (int)hidden, d_hidden, d_hidden_fp32 ? 1 : 0);
+            (const __nv_bfloat16*)pool_w, (const long long*)cls_rows, (int)seq, (int)hidden, d_hidden,
+            d_hidden_fp32 ? 1 : 0);
   B2_CUDA(cudaGetLastError());
   count_launches(1);
   B2_LAUNCH(head_bwd_k1b, dim3((unsigned)((hidden + 255) / 256), (unsigned)num_labels), 256, 0, stream, dlogits, pm,
@@ -307,9 +333,31 @@ extern "C" int32_t b2_head_bwd(const float* dlogits, const void* hidden_states, 
   B2_CUDA(cudaGetLastError());
   count_launches(1);
   B2_LAUNCH(head_bwd_k2, (unsigned)hidden, (unsigned)(hidden / 8), 0, stream, 
-      scratch, (const __nv_bfloat16*)hidden_states, (int)batch, (int)seq, (int)hidden, (__nv_bfloat16*)d_pool_w,
-      (__nv_bfloat16*)d_pool_b);
+      scratch, (const __nv_bfloat16*)hidden_states, (const long long*)cls_rows, (int)batch, (int)seq, (int)hidden,
+      (__nv_bfloat16*)d_pool_w, (__nv_bfloat16*)d_pool_b);
   B2_CUDA(cudaGetLastError());
   count_launches(1);
   return 0;
+}
+
+extern "C" int32_t b2_head_bwd(const float* dlogits, const void* hidden_states, const void* pooled, int64_t batch,
+                               int64_t seq, int64_t hidden, const void* pool_w, const void* cls_w, int64_t num_labels,
+                               float dropout_p, const void* rng_state, uint32_t rng_site, void* d_pool_w,
+                               void* d_pool_b, void* d_cls_w, void* d_cls_b, void* d_hidden, int32_t d_hidden_fp32,
+                               float* scratch, void* stream_) {
+  return head_bwd_impl(dlogits, hidden_states, pooled, nullptr, batch * seq, batch, seq, hidden, pool_w, cls_w,
+                       num_labels, dropout_p, rng_state, rng_site, d_pool_w, d_pool_b, d_cls_w, d_cls_b, d_hidden,
+                       d_hidden_fp32, scratch, stream_);
+}
+
+extern "C" int32_t b2_head_bwd_packed(const float* dlogits, const void* hidden_states, const void* pooled,
+                                      const int64_t* cls_rows, int64_t tokens, int64_t batch, int64_t hidden,
+                                      const void* pool_w, const void* cls_w, int64_t num_labels, float dropout_p,
+                                      const void* rng_state, uint32_t rng_site, void* d_pool_w, void* d_pool_b,
+                                      void* d_cls_w, void* d_cls_b, void* d_hidden, int32_t d_hidden_fp32,
+                                      float* scratch, void* stream_) {
+  B2_REQUIRE(cls_rows != nullptr && tokens > 0, "head_bwd_packed: null cls_rows / no tokens");
+  return head_bwd_impl(dlogits, hidden_states, pooled, cls_rows, tokens, batch, 1, hidden, pool_w, cls_w, num_labels,
+                       dropout_p, rng_state, rng_site, d_pool_w, d_pool_b, d_cls_w, d_cls_b, d_hidden, d_hidden_fp32,
+                       scratch, stream_);
 }

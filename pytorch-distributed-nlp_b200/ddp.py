@@ -256,9 +256,11 @@ class DistributedDataParallel(nn.Module):
             pass
 
     # ---- hooks called by the engine during backward (autograd thread) -----------------------------------------------
-    def _bucket_ready(self, idx):
-        """Bucket `idx` holds this rank's final local gradients.  With an optimizer attached and overlap on, start
-        its exchange + update on the side stream right away so it hides behind the rest of backward."""
+    def _bucket_ready(self, idx, wg_event=None):
+        """Bucket `idx` holds this rank's final local gradients once the main stream reaches this point and `wg_event`
+        (the weight-gradient stream's marker for the layer) has fired.  With an optimizer attached and overlap on,
+        start its exchange + update on the side stream right away so it hides behind the rest of backward.  Only the
+        SIDE stream waits for the weight gradients: the main stream's dgrad chain never parks behind them."""
         opt = self.module._optimizer
         if self.world == 1 or not self.overlap or opt is None or not getattr(opt, "_armed", False):
             return
@@ -267,6 +269,8 @@ class DistributedDataParallel(nn.Module):
         ev = torch.cuda.Event()
         ev.record(main)
         self._side.wait_event(ev)
+        if wg_event is not None:
+            self._side.wait_event(wg_event)
         s = self._side.cuda_stream
         self.comm.barrier(_SLOT_BUCKET0 + idx, s)
         self._exchange_update(opt, idx, s)

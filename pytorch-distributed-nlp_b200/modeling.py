@@ -104,7 +104,10 @@ class _Holder(nn.Module):
 
 class _Layout:
     """Flat parameter space: HF tensors in forward order, each padded to 8 elements, Q/K/V stacked contiguously.
-    Buckets (DDP exchange units) = embeddings | encoder layer 0..L-1 | head."""
+    Buckets (DDP exchange / AdamW launch units) = embeddings | encoder layer 0..L-2 | last layer + head.  The head
+    (pooler + classifier, 0.6 M parameters) rides with the last encoder layer -- they are adjacent in the flat space and
+    final within microseconds of each other at the start of backward -- instead of paying a barrier, an exchange and
+    a kernel launch of its own."""
 
     def __init__(self, cfg):
         H, I, L_ = cfg.hidden_size, cfg.intermediate_size, cfg.num_hidden_layers
@@ -153,7 +156,12 @@ class _Layout:
         add("bert.pooler.dense.bias", (H,))
         add("classifier.weight", (cfg.num_labels, H))
         add("classifier.bias", (cfg.num_labels,))
-        self.buckets.append((b0, off, "head"))
+        if L_ > 0:
+            lb, _le, lbl = self.buckets[-1]
+            self.buckets[-1] = (lb, off, lbl + "+head")
+        else:
+            self.buckets.append((b0, off, "head"))
+        self.head_in_last_layer = L_ > 0
         self.total = off
 
     def off(self, name):
@@ -178,10 +186,10 @@ class _StepFn(torch.autograd.Function):
     """logits (and HF's in-model loss) with a backward that runs the CUDA backward pass."""
 
     @staticmethod
-    def forward(ctx, anchor, model, input_ids, token_type_ids, attention_mask, labels):
+    def forward(ctx, anchor, model, input_ids, token_type_ids, attention_mask, labels, packed=None):
         eng = model._engine
         logits, loss = eng.forward(input_ids, token_type_ids, attention_mask, labels, training=model.training,
-                                   need_backward=True)
+                                   need_backward=True, packed=packed)
         ctx.model = model
         ctx.has_loss = loss is not None
         ctx.set_materialize_grads(False)
@@ -214,7 +222,7 @@ class _StepFn(torch.autograd.Function):
         probe = eng.grads[off:off + n].float().view(shape)
         if model._ddp is not None:
             probe = model._ddp.consensus_probe(probe)
-        return probe, None, None, None, None, None
+        return probe, None, None, None, None, None, None
 
 
 class BertForSequenceClassification(nn.Module):
@@ -375,18 +383,28 @@ class BertForSequenceClassification(nn.Module):
         return super().state_dict(*args, **kwargs)
 
     # ---- forward ------------------------------------------------------------------------------------------------------
-    def forward(self, input_ids=None, token_type_ids=None, attention_mask=None, labels=None, **unused):
+    def forward(self, input_ids=None, token_type_ids=None, attention_mask=None, labels=None, position_ids=None,
+                segments=None, cls_index=None, **unused):
+        """`position_ids` / `segments` / `cls_index` (all three or none): the batch is PACKED -- the rows of
+        `input_ids` are the 128-token bins of `packing.pack_batch`, logits come back one row per original sequence."""
         if self._engine is None:
             raise RuntimeError("BertForSequenceClassification (b200) only runs on CUDA: call model.cuda() first; "
                                "there is no CPU path.")
         if input_ids is None:
             raise ValueError("input_ids is required")
+        packed = None
+        if segments is not None or cls_index is not None:
+            if position_ids is None or segments is None or cls_index is None:
+                raise ValueError("a packed batch needs position_ids, segments and cls_index together")
+            packed = (position_ids, segments, cls_index)
+        elif position_ids is not None:
+            raise ValueError("position_ids are only supported for packed batches (with segments and cls_index)")
         if torch.is_grad_enabled() and self.training:
             anchor = self._params_by_name["classifier.bias"]
-            logits, loss = _StepFn.apply(anchor, self, input_ids, token_type_ids, attention_mask, labels)
+            logits, loss = _StepFn.apply(anchor, self, input_ids, token_type_ids, attention_mask, labels, packed)
             return SequenceClassifierOutput(loss=loss if labels is not None else None, logits=logits)
         logits, loss = self._engine.forward(input_ids, token_type_ids, attention_mask, labels,
-                                            training=self.training, need_backward=False)
+                                            training=self.training, need_backward=False, packed=packed)
         return SequenceClassifierOutput(loss=None if loss is None else loss.clone(), logits=logits.clone())
 
     def _notify_backward_done(self):
@@ -499,8 +517,10 @@ class _Engine:
     def g(self, name):
         return self.grads.data_ptr() + 2 * self.lay.off(name)
 
-    def workspace(self, B, S):
-        key = (B, S)
+    def workspace(self, B, S, Bo=None):
+        """B x S token rows; Bo = number of sequences the head sees (packed bins: B bins carry Bo >= B sequences)"""
+        Bo = B if Bo is None else Bo
+        key = (B, S, Bo)
         ws = self._ws.get(key)
         if ws is not None:
             return ws
@@ -512,7 +532,7 @@ class _Engine:
 
         ws = {
             "emb_out": e(M, H), "emb_pre": e(M, H), "emb_mean": e(M, dtype=f32), "emb_rstd": e(M, dtype=f32),
-            "ids32": e(M, dtype=torch.int32), "tt32": e(M, dtype=torch.int32),
+            "ids32": e(M, dtype=torch.int32), "tt32": e(M, dtype=torch.int32), "pos32": e(M, dtype=torch.int32),
             "layers": [
                 {"qkv": e(M, 3 * H), "ctx": e(M, H), "lse": e(B * self.heads * S, dtype=f32),
                  # attention-dropout decisions of the forward, 1 bit per (b, h, q, k): read back by the backward
@@ -522,12 +542,12 @@ class _Engine:
                  "x1": e(M, H), "mean1": e(M, dtype=f32), "rstd1": e(M, dtype=f32), "u": e(M, I), "h": e(M, I),
                  "z2": e(M, H), "x2": e(M, H), "mean2": e(M, dtype=f32), "rstd2": e(M, dtype=f32)}
                 for _ in range(nl)],
-            "pooled": e(B, H), "logits": e(B, self.C, dtype=f32), "loss": e((), dtype=f32),
-            "dlogits": e(B, self.C, dtype=f32), "dloss_logits": e(B, self.C, dtype=f32),
+            "pooled": e(Bo, H), "logits": e(Bo, self.C, dtype=f32), "loss": e((), dtype=f32),
+            "dlogits": e(Bo, self.C, dtype=f32), "dloss_logits": e(Bo, self.C, dtype=f32),
             # gradient of the residual stream: fp32 (12 layers of residual adds would otherwise each round it to bf16);
             # dzd / dz1d are the bf16 (dropout-masked) copies the tensor cores consume
             "dxA": e(M, H, dtype=f32), "dxB": e(M, H, dtype=f32), "dz": e(M, H, dtype=f32),
-            "dz1": e(M, H, dtype=f32), "emb_dx": e(M, H), "dctx": e(M, H), "head_scratch": e(2 * B, H, dtype=f32),
+            "dz1": e(M, H, dtype=f32), "emb_dx": e(M, H), "dctx": e(M, H), "head_scratch": e(2 * Bo, H, dtype=f32),
             # operands of the weight-gradient GEMMs, double-buffered by layer parity (see _backward_from_dlogits)
             "dzd": [e(M, H), e(M, H)], "dz1d": [e(M, H), e(M, H)], "dU": [e(M, I), e(M, I)],
             "dqkv": [e(M, 3 * H), e(M, 3 * H)],
@@ -591,11 +611,27 @@ class _Engine:
         L.call("b2_layernorm_fwd", z, gamma, beta, M, H, eps, y, mean, rstd, s)
 
     # ---- forward --------------------------------------------------------------------------------------------------------
-    def forward(self, input_ids, token_type_ids, attention_mask, labels, training, need_backward):
+    def forward(self, input_ids, token_type_ids, attention_mask, labels, training, need_backward, packed=None):
+        """packed: None, or (position_ids int64 [bins, 128], segments int32 [bins, 128], cls_index int64 [batch]) --
+        the rows of `input_ids` are then 128-token bins produced by packing.pack_batch, not sequences."""
         cfg, H, I = self.cfg, self.H, self.I
         if input_ids.dim() != 2:
             raise ValueError("input_ids must be [batch, seq]")
         B, S = input_ids.shape
+        Bo = B
+        if packed is not None:
+            pos_ids, segs, cls_rows = packed
+            if S != 128:
+                raise ValueError("packed bins are 128 tokens long (got %d)" % S)
+            if attention_mask is not None:
+                raise ValueError("packed bins carry their own (block-diagonal) mask: pass attention_mask=None")
+            for t, nm, dt, shape in ((pos_ids, "position_ids", torch.int64, (B, S)), (segs, "segments", torch.int32, (B, S)),
+                                     (cls_rows, "cls_index", torch.int64, None)):
+                if t.device != self.dev or t.dtype != dt or (shape is not None and tuple(t.shape) != shape):
+                    raise TypeError("%s must be a %s tensor%s on %s" % (nm, dt, "" if shape is None else " of shape %s"
+                                                                        % (shape,), self.dev))
+            pos_ids, segs, cls_rows = pos_ids.contiguous(), segs.contiguous(), cls_rows.contiguous().view(-1)
+            Bo = cls_rows.numel()
         if B == 0 or S == 0:
             raise ValueError("empty batch")
         if S % 128 != 0 or S > 512 or S > cfg.max_position_embeddings:
@@ -608,7 +644,7 @@ class _Engine:
                     raise RuntimeError("%s is on %s, model on %s" % (nm, t.device, self.dev))
                 if t.dtype != torch.int64:
                     raise TypeError("%s must be int64 (as the reference Collate produces)" % nm)
-        ws = self.workspace(B, S)
+        ws = self.workspace(B, S, Bo)
         M = B * S
         s = self.stream()
         ids = input_ids.contiguous()
@@ -621,20 +657,31 @@ class _Engine:
         w = self.w
         KM, MN = L.MAJOR_K, L.MAJOR_MN
 
-        L.call("b2_embed_fwd", ids.data_ptr(), tt.data_ptr(), B, S, w("bert.embeddings.word_embeddings.weight"),
-               w("bert.embeddings.position_embeddings.weight"), w("bert.embeddings.token_type_embeddings.weight"),
-               w("bert.embeddings.LayerNorm.weight"), w("bert.embeddings.LayerNorm.bias"), H, cfg.vocab_size,
-               cfg.type_vocab_size, float(cfg.layer_norm_eps), p_h, rng, 0, L.ptr(ws["emb_out"]),
-               L.ptr(ws["emb_pre"]), L.ptr(ws["emb_mean"]), L.ptr(ws["emb_rstd"]), L.ptr(ws["ids32"]),
-               L.ptr(ws["tt32"]), s)
+        emb_w = (w("bert.embeddings.word_embeddings.weight"), w("bert.embeddings.position_embeddings.weight"),
+                 w("bert.embeddings.token_type_embeddings.weight"), w("bert.embeddings.LayerNorm.weight"),
+                 w("bert.embeddings.LayerNorm.bias"))
+        emb_out = (L.ptr(ws["emb_out"]), L.ptr(ws["emb_pre"]), L.ptr(ws["emb_mean"]), L.ptr(ws["emb_rstd"]),
+                   L.ptr(ws["ids32"]), L.ptr(ws["tt32"]))
+        if packed is None:
+            L.call("b2_embed_fwd", ids.data_ptr(), tt.data_ptr(), B, S, *emb_w, H, cfg.vocab_size, cfg.type_vocab_size,
+                   float(cfg.layer_norm_eps), p_h, rng, 0, *emb_out, s)
+        else:
+            L.call("b2_embed_fwd_packed", ids.data_ptr(), tt.data_ptr(), pos_ids.data_ptr(),
+                   cfg.max_position_embeddings, B, S, *emb_w, H, cfg.vocab_size, cfg.type_vocab_size,
+                   float(cfg.layer_norm_eps), p_h, rng, 0, *emb_out, L.ptr(ws["pos32"]), s)
         x = ws["emb_out"]
         for l in range(self.nl):
             a = ws["layers"][l]
             pre = "bert.encoder.layer.%d." % l
             self.gemm(M, 3 * H, H, x.data_ptr(), H, KM, w(pre + "attention.self.query.weight"), H, KM,
                       a["qkv"].data_ptr(), 3 * H, L.EPI_BIAS, bias=w(pre + "attention.self.query.bias"))
-            L.call("b2_attention_fwd", a["qkv"].data_ptr(), L.ptr(mask), B, S, self.heads, 64, p_a, rng, 1 + 3 * l,
-                   a["ctx"].data_ptr(), a["lse"].data_ptr(), L.ptr(a["keep"]) if need_backward else None, s)
+            if packed is None:
+                L.call("b2_attention_fwd", a["qkv"].data_ptr(), L.ptr(mask), B, S, self.heads, 64, p_a, rng, 1 + 3 * l,
+                       a["ctx"].data_ptr(), a["lse"].data_ptr(), L.ptr(a["keep"]) if need_backward else None, s)
+            else:
+                L.call("b2_attention_fwd_packed", a["qkv"].data_ptr(), segs.data_ptr(), B, self.heads, 64, p_a, rng,
+                       1 + 3 * l, a["ctx"].data_ptr(), a["lse"].data_ptr(),
+                       L.ptr(a["keep"]) if need_backward else None, s)
             self.dense_dropout_residual_layernorm(
                 M, H, a["ctx"].data_ptr(), w(pre + "attention.output.dense.weight"),
                 w(pre + "attention.output.dense.bias"), x.data_ptr(), p_h, 2 + 3 * l,
@@ -649,19 +696,24 @@ class _Engine:
                 w(pre + "output.LayerNorm.bias"), a["z2"].data_ptr(), a["x2"].data_ptr(), a["mean2"].data_ptr(),
                 a["rstd2"].data_ptr())
             x = a["x2"]
-        L.call("b2_head_fwd", x.data_ptr(), B, S, H, w("bert.pooler.dense.weight"), w("bert.pooler.dense.bias"),
-               w("classifier.weight"), w("classifier.bias"), self.C, p_c, rng, 1 + 3 * self.nl,
-               ws["pooled"].data_ptr(), ws["logits"].data_ptr(), s)
+        head_w = (w("bert.pooler.dense.weight"), w("bert.pooler.dense.bias"), w("classifier.weight"),
+                  w("classifier.bias"))
+        if packed is None:
+            L.call("b2_head_fwd", x.data_ptr(), B, S, H, *head_w, self.C, p_c, rng, 1 + 3 * self.nl,
+                   ws["pooled"].data_ptr(), ws["logits"].data_ptr(), s)
+        else:
+            L.call("b2_head_fwd_packed", x.data_ptr(), cls_rows.data_ptr(), Bo, H, *head_w, self.C, p_c, rng,
+                   1 + 3 * self.nl, ws["pooled"].data_ptr(), ws["logits"].data_ptr(), s)
         loss = None
         if labels is not None:
             lab = labels.contiguous().view(-1)
-            if lab.numel() != B:
+            if lab.numel() != Bo:
                 raise ValueError("labels must be [batch]")
-            L.call("b2_ce_fwd_bwd", ws["logits"].data_ptr(), lab.data_ptr(), B, self.C, ws["loss"].data_ptr(),
+            L.call("b2_ce_fwd_bwd", ws["logits"].data_ptr(), lab.data_ptr(), Bo, self.C, ws["loss"].data_ptr(),
                    ws["dloss_logits"].data_ptr() if need_backward else None, s)
             loss = ws["loss"]
         if need_backward:
-            self._saved = (B, S, mask, p_h, p_a, p_c)
+            self._saved = (B, S, mask, p_h, p_a, p_c, None if packed is None else (segs, cls_rows))
         return ws["logits"], loss
 
     # ---- backward ---------------------------------------------------------------------------------------------------------
@@ -669,28 +721,23 @@ class _Engine:
         """d_logits: fp32 [B, C] gradient wrt the returned logits; d_loss: optional scalar gradient wrt HF's loss."""
         if self._saved is None:
             raise RuntimeError("backward called without a training forward")
-        B, S, mask, p_h, p_a, p_c = self._saved
+        B, S, mask, p_h, p_a, p_c, packed = self._saved
         self._saved = None
-        cfg, H, I, M = self.cfg, self.H, self.I, B * S
-        ws = self.workspace(B, S)
-        s = self.stream()
-        rng = self.rng.data_ptr()
-        w, g = self.w, self.g
-        KM, MN = L.MAJOR_K, L.MAJOR_MN
-        scratch, scratch_bytes = self.partials.data_ptr(), self.partials.numel()
-
+        Bo = B if packed is None else packed[1].numel()
+        ws = self.workspace(B, S, Bo)
         dl = ws["dlogits"]
         if d_logits is not None:
-            dl.copy_(d_logits.to(torch.float32).reshape(B, self.C))
+            dl.copy_(d_logits.to(torch.float32).reshape(Bo, self.C))
         else:
             dl.zero_()
         if d_loss is not None:
             dl.add_(ws["dloss_logits"] * d_loss.to(torch.float32))
-        return self._backward_from_dlogits(dl, B, S, mask, p_h, p_a, p_c)
+        return self._backward_from_dlogits(dl, B, S, mask, p_h, p_a, p_c, packed)
 
-    def _backward_from_dlogits(self, dl, B, S, mask, p_h, p_a, p_c):
+    def _backward_from_dlogits(self, dl, B, S, mask, p_h, p_a, p_c, packed=None):
         cfg, H, I, M = self.cfg, self.H, self.I, B * S
-        ws = self.workspace(B, S)
+        Bo = B if packed is None else packed[1].numel()
+        ws = self.workspace(B, S, Bo)
         s = self.stream()
         rng = self.rng.data_ptr()
         w, g = self.w, self.g
@@ -704,10 +751,16 @@ class _Engine:
         L.call("b2_zero", self.grads.data_ptr() + 2 * eb, 2 * (ee - eb), s)
 
         x_last = ws["layers"][-1]["x2"] if self.nl > 0 else ws["emb_out"]
-        L.call("b2_head_bwd", dl.data_ptr(), x_last.data_ptr(), ws["pooled"].data_ptr(), B, S, H,
-               w("bert.pooler.dense.weight"), w("classifier.weight"), self.C, p_c, rng, 1 + 3 * self.nl,
-               g("bert.pooler.dense.weight"), g("bert.pooler.dense.bias"), g("classifier.weight"),
-               g("classifier.bias"), ws["dxA"].data_ptr(), 1, ws["head_scratch"].data_ptr(), s)
+        head_g = (g("bert.pooler.dense.weight"), g("bert.pooler.dense.bias"), g("classifier.weight"),
+                  g("classifier.bias"))
+        if packed is None:
+            L.call("b2_head_bwd", dl.data_ptr(), x_last.data_ptr(), ws["pooled"].data_ptr(), B, S, H,
+                   w("bert.pooler.dense.weight"), w("classifier.weight"), self.C, p_c, rng, 1 + 3 * self.nl,
+                   *head_g, ws["dxA"].data_ptr(), 1, ws["head_scratch"].data_ptr(), s)
+        else:
+            L.call("b2_head_bwd_packed", dl.data_ptr(), x_last.data_ptr(), ws["pooled"].data_ptr(),
+                   packed[1].data_ptr(), M, Bo, H, w("bert.pooler.dense.weight"), w("classifier.weight"), self.C, p_c,
+                   rng, 1 + 3 * self.nl, *head_g, ws["dxA"].data_ptr(), 1, ws["head_scratch"].data_ptr(), s)
         dx, dx_other = ws["dxA"], ws["dxB"]
         # Weight gradients are off the critical path (only the optimizer consumes them): they run on a second stream,
         # overlapping the dgrad / LayerNorm / attention chain of the main stream.  Their A operands (dzd, dU, dz1d,
@@ -738,9 +791,7 @@ class _Engine:
             """bucket `idx` holds its final gradients once the main stream reaches this point (and `wg_event`,
             the weight-gradient stream's marker for the layer, has fired)"""
             if hooks is not None:
-                if wg_event is not None:
-                    main.wait_event(wg_event)
-                hooks._bucket_ready(idx)
+                hooks._bucket_ready(idx, wg_event)
             elif overlap_opt:
                 # single GPU: the HBM-bound AdamW of this bucket runs on its own stream under the rest of backward
                 ev = torch.cuda.Event()
@@ -753,7 +804,8 @@ class _Engine:
                                  self.opt_stream.cuda_stream)
                 opt._pending.add(idx)
 
-        bucket_ready(len(self.lay.buckets) - 1)
+        if not self.lay.head_in_last_layer:
+            bucket_ready(len(self.lay.buckets) - 1)     # (a model without encoder layers: the head is its own bucket)
         for l in reversed(range(self.nl)):
             a = ws["layers"][l]
             x_in = ws["layers"][l - 1]["x2"] if l > 0 else ws["emb_out"]
@@ -804,9 +856,14 @@ class _Engine:
             self.gemm(M, H, H, dz1d.data_ptr(), H, KM, w(pre + "attention.output.dense.weight"), H, MN,
                       ws["dctx"].data_ptr(), H)
             # --- BertSelfAttention
-            L.call("b2_attention_bwd", a["qkv"].data_ptr(), L.ptr(mask), a["ctx"].data_ptr(), ws["dctx"].data_ptr(),
-                   a["lse"].data_ptr(), B, S, self.heads, 64, p_a, rng, 1 + 3 * l, dqkv.data_ptr(),
-                   L.ptr(ws["dq_accum"]), acc_l if S == 128 else None, L.ptr(a["keep"]), s)
+            if packed is None:
+                L.call("b2_attention_bwd", a["qkv"].data_ptr(), L.ptr(mask), a["ctx"].data_ptr(),
+                       ws["dctx"].data_ptr(), a["lse"].data_ptr(), B, S, self.heads, 64, p_a, rng, 1 + 3 * l,
+                       dqkv.data_ptr(), L.ptr(ws["dq_accum"]), acc_l if S == 128 else None, L.ptr(a["keep"]), s)
+            else:
+                L.call("b2_attention_bwd_packed", a["qkv"].data_ptr(), packed[0].data_ptr(), a["ctx"].data_ptr(),
+                       ws["dctx"].data_ptr(), a["lse"].data_ptr(), B, self.heads, 64, p_a, rng, 1 + 3 * l,
+                       dqkv.data_ptr(), acc_l, L.ptr(a["keep"]), s)
             if S != 128:   # long-sequence parity configs: separate column-sum pass into the same accumulator slot
                 L.call("b2_colsum", dqkv.data_ptr(), M, 3 * H, 3 * H, g(pre + "attention.self.query.bias"),
                        scratch, scratch_bytes, s)
@@ -841,15 +898,24 @@ class _Engine:
             L.call("b2_accum_finish", self.bias_acc.data_ptr(), self.grads.data_ptr(),
                    self.bias_segs.data_ptr() + 24 * seg0, spl * (l + 1) - seg0, max(3 * H, I), s)
             bucket_ready(1 + l, done.get(l))   # complete only with this layer's weight gradients
-        L.call("b2_embed_bwd", dx.data_ptr(), 1, ws["emb_pre"].data_ptr(), ws["emb_mean"].data_ptr(),
-               ws["emb_rstd"].data_ptr(), w("bert.embeddings.LayerNorm.weight"), ws["ids32"].data_ptr(),
-               ws["tt32"].data_ptr(), B, S, H, cfg.vocab_size, cfg.type_vocab_size,
-               -1 if getattr(cfg, "pad_token_id", None) is None else int(cfg.pad_token_id), p_h, rng, 0,
-               g("bert.embeddings.word_embeddings.weight"), g("bert.embeddings.position_embeddings.weight"),
-               g("bert.embeddings.token_type_embeddings.weight"), g("bert.embeddings.LayerNorm.weight"),
-               g("bert.embeddings.LayerNorm.bias"), ws["emb_dx"].data_ptr(), scratch, scratch_bytes,
-               self.owner.data_ptr(), s)
-        if side is not main and hooks is None:
+        emb_in = (dx.data_ptr(), 1, ws["emb_pre"].data_ptr(), ws["emb_mean"].data_ptr(), ws["emb_rstd"].data_ptr(),
+                  w("bert.embeddings.LayerNorm.weight"), ws["ids32"].data_ptr(), ws["tt32"].data_ptr())
+        emb_tail = (B, S, H, cfg.vocab_size, cfg.type_vocab_size,
+                    -1 if getattr(cfg, "pad_token_id", None) is None else int(cfg.pad_token_id), p_h, rng, 0,
+                    g("bert.embeddings.word_embeddings.weight"), g("bert.embeddings.position_embeddings.weight"),
+                    g("bert.embeddings.token_type_embeddings.weight"), g("bert.embeddings.LayerNorm.weight"),
+                    g("bert.embeddings.LayerNorm.bias"), ws["emb_dx"].data_ptr(), scratch, scratch_bytes,
+                    self.owner.data_ptr(), s)
+        if packed is None:
+            L.call("b2_embed_bwd", *emb_in, *emb_tail)
+        else:
+            L.call("b2_embed_bwd_packed", *emb_in, ws["pos32"].data_ptr(), *emb_tail)
+        # Whoever consumes the gradients next on the main stream (optimizer.step, grad_dict) must see the weight-gradient
+        # stream's work.  Under an armed DDP exchange the side stream has taken those dependencies bucket by bucket
+        # (ddp._bucket_ready) and optimizer.step() joins the side stream; in every other case join here.
+        ddp_overlap = (hooks is not None and hooks.world > 1 and hooks.overlap and opt is not None and
+                       getattr(opt, "_armed", False))
+        if side is not main and not ddp_overlap:
             for l in sorted(done)[:2]:       # the last two layers processed (0 and 1) may still be in flight
                 main.wait_event(done[l])
         bucket_ready(0)

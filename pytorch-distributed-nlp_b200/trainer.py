@@ -9,6 +9,7 @@ Same methods, same argument meaning: ``on_step`` [:126-137], ``loss_reduce`` [:1
   * ``loss_reduce`` / ``output_reduce`` go through the peer-memory kernels when the model is the b200 DDP wrapper;
   * ``train`` uses :class:`FusedTrainStep` (the whole step captured in one CUDA graph) when ``args.fused`` is set.
 """
+import os
 import time
 
 import numpy as np
@@ -35,6 +36,8 @@ class Args:
     dev = False
     use_amp = False       # the -amp scripts' flag (multi-gpu-distributed-mp-amp-cls.py:160): GradScaler loop on the eager path
     fused = True          # capture fwd + bwd + exchange + AdamW in one CUDA graph
+    pack = False          # pack the valid prefixes of the padded [B, 128] batches into 128-token bins (packing.py): the
+                          # reference pads every row to max_seq_len although real rows average 18 tokens [:76]
     log_every = 1         # the reference prints every step (forces a D2H sync per step)
     total_step = 0
 
@@ -66,6 +69,12 @@ class _StagedGraphStep:
         self.graph = None
         self._warm = 0
         self._h2d_done = None
+        # B2_STEP_PRIORITY=1 (A/B switch): the step body -- the critical chain of forward / dgrad kernels -- is issued
+        # (and captured) on a HIGH-priority stream, so that when an SM frees up the block scheduler hands it to the
+        # critical path before the weight-gradient / optimizer streams (default, i.e. lowest, priority)
+        self._prio_stream = None
+        if os.environ.get("B2_STEP_PRIORITY", "0") == "1":
+            self._prio_stream = torch.cuda.Stream(device=dev, priority=-1)
 
     def _unstage(self):
         n = self.B * self.S
@@ -97,21 +106,31 @@ class _StagedGraphStep:
         self._h2d_done = torch.cuda.Event()
         self._h2d_done.record(torch.cuda.current_stream(self.eng.dev))
 
+    def _run_body(self):
+        if self._prio_stream is None:
+            self._body()
+            return
+        cur = torch.cuda.current_stream(self.eng.dev)
+        self._prio_stream.wait_stream(cur)
+        with torch.cuda.stream(self._prio_stream):
+            self._body()
+        cur.wait_stream(self._prio_stream)
+
     def run_device(self):
         """The step with inputs already staged on the device (bench `value` path)."""
         if not self.use_graph:
-            self._body()
+            self._run_body()
             return
         if self.graph is None:
             if self._warm < 2:
                 # eager warm-up: first launches set kernel attributes, DDP arms its overlap path
-                self._body()
+                self._run_body()
                 self._warm += 1
                 return
             torch.cuda.synchronize(self.eng.dev)
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
-                self._body()
+                self._run_body()
             self.graph = g
             self.graph.replay()
             return
@@ -142,10 +161,10 @@ class FusedTrainStep(_StagedGraphStep):
         self._unstage()
         logits, loss = eng.forward(self.d_ids, self.d_tt, self.d_mask, self.d_lab, training=True, need_backward=True)
         ws = eng.workspace(self.B, self.S)
-        B, S, mask, p_h, p_a, p_c = eng._saved
+        B, S, mask, p_h, p_a, p_c, packed = eng._saved
         eng._saved = None
         # d(loss)/d(logits) was produced by the CE kernel: the reference's criterion(logits, label) [:169]
-        eng._backward_from_dlogits(ws["dloss_logits"], B, S, mask, p_h, p_a, p_c)
+        eng._backward_from_dlogits(ws["dloss_logits"], B, S, mask, p_h, p_a, p_c, packed)
         self.opt.step()
         self.loss_out.copy_(loss)
 
@@ -153,6 +172,69 @@ class FusedTrainStep(_StagedGraphStep):
         """batch_data: the dict the reference Collate yields (host int64 tensors).  Returns the device loss scalar
         (local rank's mean CE, like `loss` at [:169])."""
         self.stage(batch_data)
+        self.run_device()
+        return self.loss_out
+
+
+class PackedTrainStep(_StagedGraphStep):
+    """FusedTrainStep for PACKED batches (packing.pack_batch): `bins` 128-token bins carrying `batch` sequences.  One
+    instance (staging buffers + CUDA graph) per bin count; the Trainer keeps a small cache of them, since the number of
+    bins a batch packs into varies with its lengths."""
+
+    def __init__(self, model, optimizer, bins, batch, use_graph=True):
+        super().__init__(model, bins, 128, use_graph)
+        dev = self.eng.dev
+        self.bins, self.batch = bins, batch
+        n = bins * 128
+        # pinned staging: ids | token types | positions | segments (as int64) | cls rows | labels
+        self.h_stage = torch.empty(4 * n + 2 * batch, dtype=torch.int64).pin_memory()
+        self.d_stage = torch.empty_like(self.h_stage, device=dev)
+        z = lambda *sh: torch.zeros(*sh, dtype=torch.int64, device=dev)
+        self.d_pos, self.d_cls, self.d_lab = z(bins, 128), z(batch), z(batch)
+        self.d_seg = torch.zeros(bins, 128, dtype=torch.int32, device=dev)
+        self.opt = optimizer
+        optimizer._armed = True
+
+    def _unstage(self):
+        n, st = self.bins * 128, self.d_stage
+        self.d_ids.copy_(st[0:n].view(self.bins, 128))
+        self.d_tt.copy_(st[n:2 * n].view(self.bins, 128))
+        self.d_pos.copy_(st[2 * n:3 * n].view(self.bins, 128))
+        self.d_seg.copy_(st[3 * n:4 * n].view(self.bins, 128))          # int64 -> int32
+        self.d_cls.copy_(st[4 * n:4 * n + self.batch])
+        self.d_lab.copy_(st[4 * n + self.batch:4 * n + 2 * self.batch])
+
+    def stage(self, packed, label):
+        n, hs = self.bins * 128, self.h_stage
+        if packed["bins"] != self.bins or label.numel() != self.batch:
+            raise ValueError("PackedTrainStep was built for %d bins / %d sequences" % (self.bins, self.batch))
+        if self._h2d_done is not None:
+            self._h2d_done.synchronize()
+        hs[0:n].copy_(packed["input_ids"].reshape(-1))
+        hs[n:2 * n].copy_(packed["token_type_ids"].reshape(-1))
+        hs[2 * n:3 * n].copy_(packed["position_ids"].reshape(-1))
+        hs[3 * n:4 * n].copy_(packed["segments"].reshape(-1))
+        hs[4 * n:4 * n + self.batch].copy_(packed["cls_index"])
+        hs[4 * n + self.batch:4 * n + 2 * self.batch].copy_(label.reshape(-1))
+        self.d_stage.copy_(hs, non_blocking=True)
+        self._h2d_done = torch.cuda.Event()
+        self._h2d_done.record(torch.cuda.current_stream(self.eng.dev))
+
+    def _body(self):
+        eng = self.eng
+        self._unstage()
+        packed = (self.d_pos, self.d_seg, self.d_cls)
+        logits, loss = eng.forward(self.d_ids, self.d_tt, None, self.d_lab, training=True, need_backward=True,
+                                   packed=packed)
+        ws = eng.workspace(self.bins, 128, self.batch)
+        B, S, mask, p_h, p_a, p_c, pk = eng._saved
+        eng._saved = None
+        eng._backward_from_dlogits(ws["dloss_logits"], B, S, mask, p_h, p_a, p_c, pk)
+        self.opt.step()
+        self.loss_out.copy_(loss)
+
+    def __call__(self, packed, label):
+        self.stage(packed, label)
         self.run_device()
         return self.loss_out
 
@@ -187,6 +269,7 @@ class Trainer:
         self.criterion = criterion
         self.optimizer = optimizer
         self._fused = None
+        self._packed = {}     # bins -> PackedTrainStep
         self._scaler = None
         self._fused_eval = {}
         self._pin = {}
@@ -244,7 +327,18 @@ class Trainer:
 
     def train_step(self, batch_data):
         """One step of the reference loop body [:166-176]; returns the rank-averaged loss (device scalar)."""
-        if getattr(self.args, "fused", True):
+        if getattr(self.args, "fused", True) and getattr(self.args, "pack", False) and \
+                batch_data["input_ids"].shape[1] == 128 and not batch_data["input_ids"].is_cuda:
+            from .packing import pack_batch
+            packed = pack_batch(batch_data["input_ids"], batch_data["token_type_ids"], batch_data["attention_mask"])
+            key = (packed["bins"], batch_data["input_ids"].shape[0])
+            if key not in self._packed:
+                if len(self._packed) >= 16:           # bound the graph cache: drop the oldest entry
+                    self._packed.pop(next(iter(self._packed)))
+                self._packed[key] = PackedTrainStep(self.model, self.optimizer, key[0], key[1])
+            self.model.train()
+            loss = self._packed[key](packed, batch_data["label"])
+        elif getattr(self.args, "fused", True):
             B, S = batch_data["input_ids"].shape
             if self._fused is None or (self._fused.B, self._fused.S) != (B, S):
                 self._fused = FusedTrainStep(self.model, self.optimizer, B, S)

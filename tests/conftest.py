@@ -11,6 +11,14 @@ if ROOT not in sys.path:
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a B200 (run with -m gpu on the GPU box)")
     # the C-ABI library is built in-tree; build it if a checkout has none yet (nvcc cross-compiles without a GPU)
+    # CPU oracle runs: a container that shows 100+ CPUs but is throttled to a few thrashes when torch spawns one thread
+    # per visible CPU -- use the affinity mask capped by the cgroup quota (oracle/cpu_step.usable_cores)
+    try:
+        import torch
+        from oracle import cpu_step
+        torch.set_num_threads(cpu_step.usable_cores())
+    except Exception:
+        pass
     lib = os.path.join(ROOT, "pytorch-distributed-nlp_b200", "libb2ddpbert.so")
     if not os.path.exists(lib):
         import __graft_entry__

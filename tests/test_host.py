@@ -50,7 +50,7 @@ def test_parameter_names_order_and_count_match_hf():
     n_params = sum(int(torch.tensor(s).prod()) for _, s in lay.entries.values())
     assert n_params == 102_272_262
     assert lay.total % 8 == 0 and all(off % 8 == 0 for off, _ in lay.entries.values())
-    assert len(lay.buckets) == 14                       # embeddings | 12 layers | head
+    assert len(lay.buckets) == 13                       # embeddings | layers 0..10 | layer 11 + head
     assert lay.buckets[0][0] == 0 and lay.buckets[-1][1] == lay.total
     for (b0, e0, _), (b1, _e1, _) in zip(lay.buckets, lay.buckets[1:]):
         assert e0 == b1

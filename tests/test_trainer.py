@@ -104,7 +104,7 @@ def test_full_size_gradients_per_tensor_vs_oracle(cuda_dev):
                 labels=d["label"])
     F.cross_entropy(out[1], d["label"]).backward()
     torch.cuda.synchronize()
-    torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
+    torch.set_num_threads(cpu_step.usable_cores())   # affinity capped by the cgroup CPU quota
     _, _, ref = bert_ref.loss_and_grads(state, cfg, batch)
     got = model.grad_dict()
     # the comparison stack: HF's own module, bf16 autocast (fp32 parameters and gradients, bf16 matmuls, fp32 softmax)
@@ -185,7 +185,7 @@ def test_config_a_loss_trajectory_vs_oracle(cuda_dev, dropout, steps):
             auto.append(float(hl))
         del hf, hopt
 
-    torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
+    torch.set_num_threads(cpu_step.usable_cores())   # affinity capped by the cgroup CPU quota
     params = {k: v.clone() for k, v in state.items()}
     ropt = adamw_ref.HFAdamW(params, lr=3e-5, weight_decay=0.01)
     ref = []
