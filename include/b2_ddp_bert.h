@@ -28,7 +28,7 @@ extern "C" {
 /* ------------------------------------------------------------------------------------------------------ */
 const char* b2_last_error(void);
 int32_t b2_abi_version(void);             /* bumped when a struct below changes */
-#define B2_ABI_VERSION 15
+#define B2_ABI_VERSION 16
 int64_t b2_launch_count(void);            /* kernels launched by this library so far (process-wide) */
 
 /* ------------------------------------------------------------------------------------------------------ */
@@ -89,14 +89,16 @@ int32_t b2_gemm_bf16_grouped(const b2_gemm_args_t* args, int32_t count, void* st
 
 /* BertSelfOutput.forward / BertOutput.forward in ONE launch (SP/transformers/models/bert/modeling_bert.py:294-298,
  * :352-356): y = LayerNorm(dropout(x W^T + b) + residual).  `args` as for b2_gemm_bf16 with epilogue
- * B2_EPI_BIAS_DROPOUT_RESIDUAL, NT layouts, N = hidden in {768, 1024}: D receives the pre-LayerNorm sum (bf16, kept
- * for the backward), y the normalised output, mean / rstd (fp32 [M]) the row statistics.  A row's N columns are
- * spread over a cluster of 4 CTA pairs; the row statistics travel through distributed shared memory.  Same arithmetic
- * as b2_gemm_bf16 followed by b2_layernorm_fwd, up to the summation order of the statistics.
+ * B2_EPI_BIAS_DROPOUT_RESIDUAL, NT layouts, N = hidden in {768, 1024} -- EXCEPT that args->aux_in is the residual as
+ * FP32 [M, N] (ld_aux_in in elements): the residual stream stays in fp32 end to end.  D receives the pre-LayerNorm sum
+ * rounded to bf16 (kept for the backward), y the normalised output as bf16 (the next GEMM's operand), y_f32 (optional)
+ * the same as fp32 (the next block's residual), mean / rstd (fp32 [M]) the row statistics -- computed from the
+ * UNROUNDED fp32 sum.  A row's N columns are spread over a cluster of N / 256 CTA pairs; the row statistics travel
+ * through distributed shared memory.
  * b2_gemm_ln_max_clusters(hidden): how many such clusters the device can hold at once (0 = shape / device not
- * supported: issue the two separate kernels instead).                                                          */
+ * supported: issue b2_gemm_bf16 + b2_layernorm_fwd instead).                                                    */
 int32_t b2_gemm_ln_fwd(const b2_gemm_args_t* args, const void* gamma, const void* beta, float eps, void* y,
-                       int64_t ldy, float* mean, float* rstd, void* stream);
+                       int64_t ldy, float* y_f32, int64_t ldyf, float* mean, float* rstd, void* stream);
 int32_t b2_gemm_ln_max_clusters(int64_t hidden);
 
 /* ------------------------------------------------------------------------------------------------------ */
@@ -110,7 +112,7 @@ int32_t b2_gemm_ln_max_clusters(int64_t hidden);
 int32_t b2_embed_fwd(const int64_t* input_ids, const int64_t* token_type_ids, int64_t batch, int64_t seq,
                      const void* word_emb, const void* pos_emb, const void* type_emb, const void* gamma,
                      const void* beta, int64_t hidden, int64_t vocab, int64_t type_vocab, float eps, float dropout_p,
-                     const void* rng_state, uint32_t rng_site, void* y, void* pre_ln, float* mean, float* rstd,
+                     const void* rng_state, uint32_t rng_site, void* y, float* y_f32 /* optional fp32 copy of y: first residual of the fp32 stream */, void* pre_ln, float* mean, float* rstd,
                      int32_t* ids32, int32_t* tt32, void* stream);
 
 /* arms the owner table used by b2_embed_bwd (int32[vocab] = INT_MAX); call once after allocation */
@@ -216,8 +218,8 @@ int32_t b2_embed_fwd_packed(const int64_t* input_ids, const int64_t* token_type_
                             int64_t max_positions, int64_t bins, int64_t seq, const void* word_emb,
                             const void* pos_emb, const void* type_emb, const void* gamma, const void* beta,
                             int64_t hidden, int64_t vocab, int64_t type_vocab, float eps, float dropout_p,
-                            const void* rng_state, uint32_t rng_site, void* y, void* pre_ln, float* mean, float* rstd,
-                            int32_t* ids32, int32_t* tt32, int32_t* pos32, void* stream);
+                            const void* rng_state, uint32_t rng_site, void* y, float* y_f32, void* pre_ln, float* mean,
+                            float* rstd, int32_t* ids32, int32_t* tt32, int32_t* pos32, void* stream);
 int32_t b2_embed_bwd_packed(const void* dy, int32_t dy_fp32, const void* pre_ln, const float* mean, const float* rstd,
                             const void* gamma, const int32_t* ids32, const int32_t* tt32, const int32_t* pos32,
                             int64_t bins, int64_t seq, int64_t hidden, int64_t vocab, int64_t type_vocab,

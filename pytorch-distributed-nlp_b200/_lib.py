@@ -8,7 +8,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libb2ddpbert.so")
-ABI_VERSION = 15
+ABI_VERSION = 16
 
 MAJOR_K, MAJOR_MN = 0, 1
 EPI_NONE, EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_DROPOUT_RESIDUAL, EPI_RESIDUAL, EPI_GELU_BWD = 0, 1, 2, 3, 4, 5
@@ -47,9 +47,9 @@ _SIGNATURES = {
     "b2_gemm_bf16_grouped": [C.POINTER(GemmArgs), i32, vp],
     "b2_gemm_bf16_grouped_adamw": [C.POINTER(GemmArgs), C.POINTER(FusedAdamWTarget), i32, C.POINTER(AdamWHParams), vp,
                                    vp],
-    "b2_gemm_ln_fwd": [C.POINTER(GemmArgs), vp, vp, f32, vp, i64, vp, vp, vp],
+    "b2_gemm_ln_fwd": [C.POINTER(GemmArgs), vp, vp, f32, vp, i64, vp, i64, vp, vp, vp],
     "b2_embed_fwd": [vp, vp, i64, i64, vp, vp, vp, vp, vp, i64, i64, i64, f32, f32, vp, u32, vp, vp, vp, vp, vp, vp,
-                     vp],
+                     vp, vp],
     "b2_embed_owner_init": [vp, i64, vp],
     "b2_embed_bwd": [vp, i32, vp, vp, vp, vp, vp, vp, i64, i64, i64, i64, i64, i64, f32, vp, u32, vp, vp, vp, vp, vp, vp, vp,
                      i64, vp, vp],
@@ -66,7 +66,7 @@ _SIGNATURES = {
     "b2_head_bwd": [vp, vp, vp, i64, i64, i64, vp, vp, i64, f32, vp, u32, vp, vp, vp, vp, vp, i32, vp, vp],
     # packed-bin variants (include/b2_ddp_bert.h, "packed bins")
     "b2_embed_fwd_packed": [vp, vp, vp, i64, i64, i64, vp, vp, vp, vp, vp, i64, i64, i64, f32, f32, vp, u32, vp, vp, vp,
-                            vp, vp, vp, vp, vp],
+                            vp, vp, vp, vp, vp, vp],
     "b2_embed_bwd_packed": [vp, i32, vp, vp, vp, vp, vp, vp, vp, i64, i64, i64, i64, i64, i64, f32, vp, u32, vp, vp, vp,
                             vp, vp, vp, vp, i64, vp, vp],
     "b2_attention_fwd_packed": [vp, vp, i64, i64, i64, f32, vp, u32, vp, vp, vp, vp],

@@ -24,6 +24,7 @@ __global__ void __launch_bounds__(128) embed_fwd_kernel(
     const __nv_bfloat16* __restrict__ type, const __nv_bfloat16* __restrict__ gamma,
     const __nv_bfloat16* __restrict__ beta, int vocab, int type_vocab, float eps, float dropout_p,
     const unsigned long long* rng, unsigned rng_site, __nv_bfloat16* __restrict__ y,
+    float* __restrict__ y_f32 /* optional: the same output unrounded, the first residual of the fp32 stream */,
     __nv_bfloat16* __restrict__ pre_ln, float* __restrict__ mean_out, float* __restrict__ rstd_out,
     int* __restrict__ ids32, int* __restrict__ tt32) {
   pdl_wait();               // PDL: predecessors complete + visible before any global access
@@ -64,6 +65,7 @@ __global__ void __launch_bounds__(128) embed_fwd_kernel(
     }
   }
   store_row<VPL>(y + (size_t)t * H, lane, v);
+  if (y_f32 != nullptr) store_row_f32<VPL>(y_f32 + (size_t)t * H, lane, v);
   if (lane == 0) {
     mean_out[t] = mean;
     rstd_out[t] = rstd;
@@ -248,8 +250,8 @@ static int32_t embed_fwd_impl(const int64_t* input_ids, const int64_t* token_typ
                               int64_t max_pos, int32_t* pos32, int64_t batch, int64_t seq, const void* word_emb,
                               const void* pos_emb, const void* type_emb, const void* gamma, const void* beta,
                               int64_t hidden, int64_t vocab, int64_t type_vocab, float eps, float dropout_p,
-                              const void* rng_state, uint32_t rng_site, void* y, void* pre_ln, float* mean,
-                              float* rstd, int32_t* ids32, int32_t* tt32, void* stream_) {
+                              const void* rng_state, uint32_t rng_site, void* y, float* y_f32, void* pre_ln,
+                              float* mean, float* rstd, int32_t* ids32, int32_t* tt32, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   B2_REQUIRE(input_ids && word_emb && pos_emb && type_emb && gamma && beta && y && pre_ln && mean && rstd && ids32 &&
                  tt32,
@@ -267,7 +269,8 @@ static int32_t embed_fwd_impl(const int64_t* input_ids, const int64_t* token_typ
         (int)max_pos, pos32, tokens, (int)seq,                                                                    \
         (const __nv_bfloat16*)word_emb, (const __nv_bfloat16*)pos_emb, (const __nv_bfloat16*)type_emb,            \
         (const __nv_bfloat16*)gamma, (const __nv_bfloat16*)beta, (int)vocab, (int)type_vocab, eps, dropout_p,     \
-        (const unsigned long long*)rng_state, rng_site, (__nv_bfloat16*)y, (__nv_bfloat16*)pre_ln, mean, rstd,    \
+        (const unsigned long long*)rng_state, rng_site, (__nv_bfloat16*)y, y_f32, (__nv_bfloat16*)pre_ln, mean,   \
+        rstd,                                                                                                     \
         ids32, tt32);                                                                                             \
     break;
   switch ((int)(hidden / 256)) { B2_EMB(1) B2_EMB(2) B2_EMB(3) B2_EMB(4) }
@@ -280,11 +283,11 @@ static int32_t embed_fwd_impl(const int64_t* input_ids, const int64_t* token_typ
 extern "C" int32_t b2_embed_fwd(const int64_t* input_ids, const int64_t* token_type_ids, int64_t batch, int64_t seq,
                                 const void* word_emb, const void* pos_emb, const void* type_emb, const void* gamma,
                                 const void* beta, int64_t hidden, int64_t vocab, int64_t type_vocab, float eps,
-                                float dropout_p, const void* rng_state, uint32_t rng_site, void* y, void* pre_ln,
-                                float* mean, float* rstd, int32_t* ids32, int32_t* tt32, void* stream_) {
+                                float dropout_p, const void* rng_state, uint32_t rng_site, void* y, float* y_f32,
+                                void* pre_ln, float* mean, float* rstd, int32_t* ids32, int32_t* tt32, void* stream_) {
   return embed_fwd_impl(input_ids, token_type_ids, nullptr, 0, nullptr, batch, seq, word_emb, pos_emb, type_emb, gamma,
-                        beta, hidden, vocab, type_vocab, eps, dropout_p, rng_state, rng_site, y, pre_ln, mean, rstd,
-                        ids32, tt32, stream_);
+                        beta, hidden, vocab, type_vocab, eps, dropout_p, rng_state, rng_site, y, y_f32, pre_ln, mean,
+                        rstd, ids32, tt32, stream_);
 }
 
 extern "C" int32_t b2_embed_fwd_packed(const int64_t* input_ids, const int64_t* token_type_ids,
@@ -292,12 +295,12 @@ extern "C" int32_t b2_embed_fwd_packed(const int64_t* input_ids, const int64_t* 
                                        const void* word_emb, const void* pos_emb, const void* type_emb,
                                        const void* gamma, const void* beta, int64_t hidden, int64_t vocab,
                                        int64_t type_vocab, float eps, float dropout_p, const void* rng_state,
-                                       uint32_t rng_site, void* y, void* pre_ln, float* mean, float* rstd,
-                                       int32_t* ids32, int32_t* tt32, int32_t* pos32, void* stream_) {
+                                       uint32_t rng_site, void* y, float* y_f32, void* pre_ln, float* mean,
+                                       float* rstd, int32_t* ids32, int32_t* tt32, int32_t* pos32, void* stream_) {
   B2_REQUIRE(position_ids && pos32 && max_positions > 0, "embed_fwd_packed: position ids / pos32 / max_positions");
   return embed_fwd_impl(input_ids, token_type_ids, position_ids, max_positions, pos32, bins, seq, word_emb, pos_emb,
                         type_emb, gamma, beta, hidden, vocab, type_vocab, eps, dropout_p, rng_state, rng_site, y,
-                        pre_ln, mean, rstd, ids32, tt32, stream_);
+                        y_f32, pre_ln, mean, rstd, ids32, tt32, stream_);
 }
 
 static int32_t embed_bwd_impl(const void* dy, int32_t dy_fp32, const void* pre_ln, const float* mean,

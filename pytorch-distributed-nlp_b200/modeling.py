@@ -532,6 +532,9 @@ class _Engine:
 
         ws = {
             "emb_out": e(M, H), "emb_pre": e(M, H), "emb_mean": e(M, dtype=f32), "emb_rstd": e(M, dtype=f32),
+            # fp32 residual stream of the forward (fused dense + LayerNorm path): the LayerNorm outputs are kept
+            # unrounded for the NEXT block's residual add; the bf16 copies above / below feed the GEMMs
+            "emb_out_f": e(M, H, dtype=f32) if self.fused_ln else None,
             "ids32": e(M, dtype=torch.int32), "tt32": e(M, dtype=torch.int32), "pos32": e(M, dtype=torch.int32),
             "layers": [
                 {"qkv": e(M, 3 * H), "ctx": e(M, H), "lse": e(B * self.heads * S, dtype=f32),
@@ -540,8 +543,10 @@ class _Engine:
                           if (S == 128 and self.attn_keep_bits) else None),
                  "z1": e(M, H),
                  "x1": e(M, H), "mean1": e(M, dtype=f32), "rstd1": e(M, dtype=f32), "u": e(M, I), "h": e(M, I),
-                 "z2": e(M, H), "x2": e(M, H), "mean2": e(M, dtype=f32), "rstd2": e(M, dtype=f32)}
-                for _ in range(nl)],
+                 "z2": e(M, H), "x2": e(M, H), "mean2": e(M, dtype=f32), "rstd2": e(M, dtype=f32),
+                 "x1f": e(M, H, dtype=f32) if self.fused_ln else None,
+                 "x2f": e(M, H, dtype=f32) if (self.fused_ln and li < nl - 1) else None}
+                for li in range(nl)],
             "pooled": e(Bo, H), "logits": e(Bo, self.C, dtype=f32), "loss": e((), dtype=f32),
             "dlogits": e(Bo, self.C, dtype=f32), "dloss_logits": e(Bo, self.C, dtype=f32),
             # gradient of the residual stream: fp32 (12 layers of residual adds would otherwise each round it to bf16);
@@ -587,9 +592,11 @@ class _Engine:
             return
         L.call("b2_gemm_bf16", a, stream if stream is not None else self.stream())
 
-    def dense_dropout_residual_layernorm(self, M, K, A, W, bias, resid, p, site, gamma, beta, z, y, mean, rstd):
+    def dense_dropout_residual_layernorm(self, M, K, A, W, bias, resid, resid_f, p, site, gamma, beta, z, y, y_f, mean,
+                                         rstd):
         """y = LayerNorm(dropout(A W^T + bias) + resid) with z = the pre-LN sum kept for the backward
-        (BertSelfOutput / BertOutput, modeling_bert.py:294-298, :352-356)"""
+        (BertSelfOutput / BertOutput, modeling_bert.py:294-298, :352-356).  Fused path: ONE cluster kernel, the
+        residual comes in as fp32 (resid_f), the output leaves as bf16 (y) and fp32 (y_f, may be None)."""
         H = self.H
         s = self.stream()
         eps = float(self.cfg.layer_norm_eps)
@@ -599,12 +606,12 @@ class _Engine:
             a.A, a.lda, a.a_major = A, K, L.MAJOR_K
             a.B, a.ldb, a.b_major = W, K, L.MAJOR_K
             a.D, a.ldd, a.epilogue = z, H, L.EPI_BIAS_DROPOUT_RESIDUAL
-            a.bias, a.aux_in, a.ld_aux_in, a.aux_out, a.ld_aux_out = bias, resid, H, None, 0
+            a.bias, a.aux_in, a.ld_aux_in, a.aux_out, a.ld_aux_out = bias, resid_f, H, None, 0
             a.dropout_p, a.rng_state, a.rng_site = p, self.rng.data_ptr(), site
             a.workspace, a.workspace_bytes = None, 0
             a.force_bn = a.force_splits = a.force_kernel = 0
             a.debug_timing, a.colsum_out = None, None
-            L.call("b2_gemm_ln_fwd", a, gamma, beta, eps, y, H, mean, rstd, s)
+            L.call("b2_gemm_ln_fwd", a, gamma, beta, eps, y, H, y_f, H if y_f else 0, mean, rstd, s)
             return
         self.gemm(M, H, K, A, K, L.MAJOR_K, W, K, L.MAJOR_K, z, H, L.EPI_BIAS_DROPOUT_RESIDUAL, bias=bias,
                   aux_in=resid, ld_aux_in=H, p=p, site=site)
@@ -660,8 +667,8 @@ class _Engine:
         emb_w = (w("bert.embeddings.word_embeddings.weight"), w("bert.embeddings.position_embeddings.weight"),
                  w("bert.embeddings.token_type_embeddings.weight"), w("bert.embeddings.LayerNorm.weight"),
                  w("bert.embeddings.LayerNorm.bias"))
-        emb_out = (L.ptr(ws["emb_out"]), L.ptr(ws["emb_pre"]), L.ptr(ws["emb_mean"]), L.ptr(ws["emb_rstd"]),
-                   L.ptr(ws["ids32"]), L.ptr(ws["tt32"]))
+        emb_out = (L.ptr(ws["emb_out"]), L.ptr(ws["emb_out_f"]), L.ptr(ws["emb_pre"]), L.ptr(ws["emb_mean"]),
+                   L.ptr(ws["emb_rstd"]), L.ptr(ws["ids32"]), L.ptr(ws["tt32"]))
         if packed is None:
             L.call("b2_embed_fwd", ids.data_ptr(), tt.data_ptr(), B, S, *emb_w, H, cfg.vocab_size, cfg.type_vocab_size,
                    float(cfg.layer_norm_eps), p_h, rng, 0, *emb_out, s)
@@ -669,7 +676,7 @@ class _Engine:
             L.call("b2_embed_fwd_packed", ids.data_ptr(), tt.data_ptr(), pos_ids.data_ptr(),
                    cfg.max_position_embeddings, B, S, *emb_w, H, cfg.vocab_size, cfg.type_vocab_size,
                    float(cfg.layer_norm_eps), p_h, rng, 0, *emb_out, L.ptr(ws["pos32"]), s)
-        x = ws["emb_out"]
+        x, xf = ws["emb_out"], ws["emb_out_f"]
         for l in range(self.nl):
             a = ws["layers"][l]
             pre = "bert.encoder.layer.%d." % l
@@ -684,18 +691,18 @@ class _Engine:
                        L.ptr(a["keep"]) if need_backward else None, s)
             self.dense_dropout_residual_layernorm(
                 M, H, a["ctx"].data_ptr(), w(pre + "attention.output.dense.weight"),
-                w(pre + "attention.output.dense.bias"), x.data_ptr(), p_h, 2 + 3 * l,
+                w(pre + "attention.output.dense.bias"), x.data_ptr(), L.ptr(xf), p_h, 2 + 3 * l,
                 w(pre + "attention.output.LayerNorm.weight"), w(pre + "attention.output.LayerNorm.bias"),
-                a["z1"].data_ptr(), a["x1"].data_ptr(), a["mean1"].data_ptr(), a["rstd1"].data_ptr())
+                a["z1"].data_ptr(), a["x1"].data_ptr(), L.ptr(a["x1f"]), a["mean1"].data_ptr(), a["rstd1"].data_ptr())
             self.gemm(M, I, H, a["x1"].data_ptr(), H, KM, w(pre + "intermediate.dense.weight"), H, KM,
                       a["h"].data_ptr(), I, L.EPI_BIAS_GELU, bias=w(pre + "intermediate.dense.bias"),
                       aux_out=a["u"].data_ptr(), ld_aux_out=I)
             self.dense_dropout_residual_layernorm(
                 M, I, a["h"].data_ptr(), w(pre + "output.dense.weight"), w(pre + "output.dense.bias"),
-                a["x1"].data_ptr(), p_h, 3 + 3 * l, w(pre + "output.LayerNorm.weight"),
-                w(pre + "output.LayerNorm.bias"), a["z2"].data_ptr(), a["x2"].data_ptr(), a["mean2"].data_ptr(),
-                a["rstd2"].data_ptr())
-            x = a["x2"]
+                a["x1"].data_ptr(), L.ptr(a["x1f"]), p_h, 3 + 3 * l, w(pre + "output.LayerNorm.weight"),
+                w(pre + "output.LayerNorm.bias"), a["z2"].data_ptr(), a["x2"].data_ptr(), L.ptr(a["x2f"]),
+                a["mean2"].data_ptr(), a["rstd2"].data_ptr())
+            x, xf = a["x2"], a["x2f"]
         head_w = (w("bert.pooler.dense.weight"), w("bert.pooler.dense.bias"), w("classifier.weight"),
                   w("classifier.bias"))
         if packed is None:

@@ -128,11 +128,13 @@ def test_embed_fwd_bwd(cuda_dev, p):
     rs = rng_state(dev)
     M = B * Sq
     y, pre = torch.empty(M, H, dtype=bf, device=dev), torch.empty(M, H, dtype=bf, device=dev)
+    yf = torch.empty(M, H, dtype=torch.float32, device=dev)
     mean, rstd = torch.empty(M, device=dev), torch.empty(M, device=dev)
     ids32, tt32 = torch.empty(M, dtype=torch.int32, device=dev), torch.empty(M, dtype=torch.int32, device=dev)
     L.call("b2_embed_fwd", ids.data_ptr(), tt.data_ptr(), B, Sq, word.data_ptr(), pos.data_ptr(), typ.data_ptr(),
-           gam.data_ptr(), bet.data_ptr(), H, V, T, 1e-12, p, rs.data_ptr(), 0, y.data_ptr(), pre.data_ptr(),
-           mean.data_ptr(), rstd.data_ptr(), ids32.data_ptr(), tt32.data_ptr(), S())
+           gam.data_ptr(), bet.data_ptr(), H, V, T, 1e-12, p, rs.data_ptr(), 0, y.data_ptr(), yf.data_ptr(),
+           pre.data_ptr(), mean.data_ptr(), rstd.data_ptr(), ids32.data_ptr(), tt32.data_ptr(), S())
+    assert torch.equal(yf.to(bf), y)          # the fp32 copy (first residual of the fp32 stream) rounds to the bf16 output
     wr, pr, tr = (t.float().requires_grad_(True) for t in (word, pos, typ))
     gr, br = gam.float().requires_grad_(True), bet.float().requires_grad_(True)
     e = F.embedding(ids, wr, padding_idx=0) + pr[:Sq][None] + tr[tt]

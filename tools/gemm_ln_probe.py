@@ -49,6 +49,7 @@ def probe(M, N, K, p=0.1):
     for _ in range(nset):
         sets.append(dict(A=torch.randn(M, K, device=dev).to(bf), B=(torch.randn(N, K, device=dev) * 0.05).to(bf),
                          bias=torch.randn(N, device=dev).to(bf), X=torch.randn(M, N, device=dev).to(bf),
+                         Xf=torch.randn(M, N, device=dev), Yf=torch.empty(M, N, device=dev),
                          Z=torch.empty(M, N, dtype=bf, device=dev), Y=torch.empty(M, N, dtype=bf, device=dev),
                          mean=torch.empty(M, device=dev), rstd=torch.empty(M, device=dev)))
     gamma, beta = torch.ones(N, device=dev).to(bf), torch.zeros(N, device=dev).to(bf)
@@ -56,8 +57,9 @@ def probe(M, N, K, p=0.1):
     st = lambda: torch.cuda.current_stream().cuda_stream
 
     def fused(s):
-        L.call("b2_gemm_ln_fwd", args(M, N, K, s["A"], s["B"], s["Z"], s["bias"], s["X"], rng, p), gamma.data_ptr(),
-               beta.data_ptr(), 1e-12, s["Y"].data_ptr(), N, s["mean"].data_ptr(), s["rstd"].data_ptr(), st())
+        L.call("b2_gemm_ln_fwd", args(M, N, K, s["A"], s["B"], s["Z"], s["bias"], s["Xf"], rng, p), gamma.data_ptr(),
+               beta.data_ptr(), 1e-12, s["Y"].data_ptr(), N, s["Yf"].data_ptr(), N, s["mean"].data_ptr(),
+               s["rstd"].data_ptr(), st())
 
     def gemm_only(s):
         L.call("b2_gemm_bf16", args(M, N, K, s["A"], s["B"], s["Z"], s["bias"], s["X"], rng, p), st())
