@@ -7,7 +7,7 @@ from .modeling import (BertConfig, BertForSequenceClassification, SequenceClassi
                        bert_large_config, chinese_bert_wwm_ext_config)
 from .optim import AdamW, build_optimizer
 from .ddp import DistributedDataParallel
-from .synthetic import synthetic_batch
+from .synthetic import REFERENCE_LENGTH_HISTOGRAM, reference_length_batch, synthetic_batch
 from .packing import pack_batch
 from .trainer import Args, FusedEvalStep, FusedTrainStep, PackedTrainStep, Trainer
 
@@ -25,5 +25,5 @@ def set_seed(seed=123):
 
 
 __all__ = ["BertConfig", "BertForSequenceClassification", "SequenceClassifierOutput", "AdamW", "build_optimizer",
-           "DistributedDataParallel", "Args", "Trainer", "FusedTrainStep", "FusedEvalStep", "PackedTrainStep", "pack_batch", "synthetic_batch", "set_seed", "bert_base_config",
+           "DistributedDataParallel", "Args", "Trainer", "FusedTrainStep", "FusedEvalStep", "PackedTrainStep", "pack_batch", "synthetic_batch", "reference_length_batch", "REFERENCE_LENGTH_HISTOGRAM", "set_seed", "bert_base_config",
            "bert_large_config", "chinese_bert_wwm_ext_config"]

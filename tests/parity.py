@@ -24,11 +24,13 @@ TOL_LOSS = 2e-3          # |loss - loss_ref|
 TOL_LOGITS = 1e-2        # max |logit - logit_ref|
 TOL_GRAD_REL = 2e-2      # per-tensor ||g - g_ref|| / ||g_ref||  (tensors with a non-negligible reference norm)
 TOL_TRAJ = 1e-2          # per-step |loss - loss_ref| along a short trajectory
-# The attention query / key projection gradients are the one stated exception: their
-# gradient is P * (dP - delta) with dP - delta = dO . (V_j - O_i), and at random initialisation the value rows of a
-# sequence are nearly collinear in the upper layers, so the 2^-9 rounding of bf16 V / dO operands is amplified ~10x.
-# tests/test_trainer.py::test_full_size_gradients_per_tensor_vs_oracle measures the same tensors of stock HF BERT under
-# torch.autocast(bf16) on the same batch next to ours and asserts ours is no worse.
+# Query / key projection gradients are the most rounding-sensitive tensors of the model: their gradient is
+# P * (dP - delta) with dP - delta = dO . (V_j - O_i), and at random initialisation the value rows of a sequence are
+# nearly collinear in the upper layers, so every bf16 rounding upstream is amplified ~10x.  With the residual stream of
+# the forward kept in fp32 (csrc/gemm_ln.cu) they meet the general 2e-2 at the headline config A (measured worst 1.9e-2,
+# stock torch bf16 autocast on the same batch: 1.4e-2; tests/test_trainer.py measures both).  Stated exception
+# (BASELINE.md §4): the deeper / longer parity configs -- bert-large's 24 layers (config C, measured 3.4e-2) and the
+# seq-512 attention path (config B shapes, 1.9e-2) -- are held to 4e-2 on these tensors only.
 TOL_GRAD_REL_QK = 4e-2
 
 
@@ -36,8 +38,8 @@ def is_qk(name):
     return ".attention.self.query." in name or ".attention.self.key." in name
 
 
-def grad_tol(name):
-    return TOL_GRAD_REL_QK if is_qk(name) else TOL_GRAD_REL
+def grad_tol(name, qk_tol=TOL_GRAD_REL):
+    return qk_tol if is_qk(name) else TOL_GRAD_REL
 
 
 def report(tag, obj):
@@ -132,11 +134,11 @@ def grad_report(got, ref, floor_frac=1e-3):
     return worst, rows
 
 
-def assert_grads_within_tolerance(got, ref, floor_frac=1e-3):
-    """every tensor within its stated tolerance (TOL_GRAD_REL; TOL_GRAD_REL_QK for the query / key projections);
+def assert_grads_within_tolerance(got, ref, floor_frac=1e-3, qk_tol=TOL_GRAD_REL):
+    """every tensor within the stated tolerance TOL_GRAD_REL (query / key projections: `qk_tol`, see TOL_GRAD_REL_QK);
     returns (worst q/k, worst other)"""
     _, rows = grad_report(got, ref, floor_frac)
-    bad = [(k, rel) for (k, rel, _rn) in rows if rel > grad_tol(k)]
+    bad = [(k, rel) for (k, rel, _rn) in rows if rel > grad_tol(k, qk_tol)]
     assert not bad, sorted(bad, key=lambda r: -r[1])[:5]
     qk = max([rel for (k, rel, _rn) in rows if is_qk(k)] or [0.0])
     other = max([rel for (k, rel, _rn) in rows if not is_qk(k)] or [0.0])

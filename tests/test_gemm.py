@@ -322,9 +322,11 @@ def test_gemm_layernorm_cluster_kernel(cuda_dev, shape, p):
         keep = torch.from_numpy(philox_keep_mask(M * N, 77, 3, 5, p).reshape(M, N)).to(dev)
         lin = lin * keep / (1 - p)
     z = lin + X
-    # D: bf16(z) up to the accumulation-order noise of the fp32 GEMM (one bf16 ulp at |z| < 8 is 2^-5)
+    # D: bf16(z) up to the accumulation-order noise of the fp32 GEMM: within one bf16 rounding (2^-8 relative) everywhere,
+    # and identical to torch's rounding of its own fp32 z almost everywhere
     dz = (Z[:M].float() - z).abs()
-    assert float(dz.max()) <= 2.0 ** -5 and float((Z[:M].float() - z.to(torch.bfloat16).float()).abs().mean()) < 2e-4
+    assert bool((dz <= 2.0 ** -7 * (1.0 + z.abs())).all())
+    assert float((Z[:M] != z.to(torch.bfloat16)).float().mean()) < 2e-2
     mu = z.mean(1)
     var = z.var(1, unbiased=False)
     assert float((mean - mu).abs().max()) <= 2e-5 * (1 + float(mu.abs().max()))

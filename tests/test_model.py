@@ -5,7 +5,7 @@ import pytest
 import torch
 import torch.nn.functional as F
 
-from parity import (TOL_GRAD_REL, TOL_LOGITS, TOL_LOSS, TOL_TRAJ, adamw_ref, assert_grads_within_tolerance, b2, bert_ref,
+from parity import (TOL_GRAD_REL, TOL_GRAD_REL_QK, TOL_LOGITS, TOL_LOSS, TOL_TRAJ, adamw_ref, assert_grads_within_tolerance, b2, bert_ref,
                     full_config, grad_report, grad_tol, make_model, oracle_masks, report, state_from_hf_init,
                     tiny_config, to_dev)
 
@@ -66,7 +66,8 @@ def test_other_baseline_shapes_match_oracle(cuda_dev, name, cfg_kw, batch, seq, 
     rl, rz, rg = bert_ref.loss_and_grads(state, cfg, b, masks=masks)
     assert abs(float(loss) - float(rl)) <= TOL_LOSS
     assert float((out[1].detach().cpu() - rz).abs().max()) <= TOL_LOGITS
-    qk, other = assert_grads_within_tolerance(model.grad_dict(), rg)   # 2e-2; query / key projections 4e-2 (parity.py)
+    # 2e-2; query / key projections of the long-sequence / wide parity shapes 4e-2 (parity.TOL_GRAD_REL_QK)
+    qk, other = assert_grads_within_tolerance(model.grad_dict(), rg, qk_tol=TOL_GRAD_REL_QK)
     report("shape_grads", {"name": name, "dropout": dropout, "worst_qk": qk, "worst_other": other})
 
 
@@ -290,6 +291,7 @@ def test_full_depth_step0_matches_ddp_fixture(cuda_dev, name):
     assert abs(float(loss) - float(w1["loss"][0][0])) <= TOL_LOSS
     assert float((out[1].detach().cpu() - w1["logits"][0][0]).abs().max()) <= TOL_LOGITS
     g = model.grad_dict()
+    qk_tol = TOL_GRAD_REL if name == "A" else TOL_GRAD_REL_QK     # headline config: 2e-2 on every tensor
     gold = fx["step0_rank0"]
     scale = max(gold["grad_norms"].values())
     worst = {"qk": 0.0, "other": 0.0}
@@ -298,13 +300,13 @@ def test_full_depth_step0_matches_ddp_fixture(cuda_dev, name):
         rel = abs(got - n) / max(n, 1e-3 * scale)
         worst["qk" if ".query." in k or ".key." in k else "other"] = max(
             worst["qk" if ".query." in k or ".key." in k else "other"], rel)
-        assert rel <= grad_tol(k), (k, got, n)
+        assert rel <= grad_tol(k, qk_tol), (k, got, n)
     # strided 64-value samples guard layout / indexing (bf16 noise does not average out over 64 values: 3x tolerance)
     for k, ref in gold["grad_samples"].items():
         f = g[k].flatten()
         if f.numel() > ref.numel():
             f = f[(torch.arange(ref.numel(), dtype=torch.int64) * (f.numel() - 1) // (ref.numel() - 1)).to(f.device)]
-        assert float((f.cpu() - ref).norm()) <= 3 * grad_tol(k) * max(float(ref.norm()), 1e-3 * scale), k
+        assert float((f.cpu() - ref).norm()) <= 3 * grad_tol(k, qk_tol) * max(float(ref.norm()), 1e-3 * scale), k
     report("full_depth_step0", {"config": name, "dloss": abs(float(loss) - float(w1["loss"][0][0])),
                                 "dlogit": float((out[1].detach().cpu() - w1["logits"][0][0]).abs().max()),
                                 "worst_norm_rel": worst})

@@ -88,12 +88,11 @@ def test_trainer_train_dev_test(cuda_dev, tmp_path, capsys, fused):
 
 def test_full_size_gradients_per_tensor_vs_oracle(cuda_dev):
     """BASELINE config A, dropout off: every one of the 201 gradient tensors against the fp32 oracle (run here on the
-    host cores).  Stated tolerance: rel-L2 <= 2e-2, except the attention query/key projections:
-    <= 4e-2.  Their gradient is P * (dP - delta) with dP - delta = dO . (V_j - O_i): at initialisation the value rows of
-    a sequence are nearly collinear in the upper layers, so the bf16 rounding of the V / dO operands (2^-9 relative) is
-    amplified by |V| / |V_j - O_i| ~ 10.  That this is a property of bf16 Q/K/V activations and not of these kernels is
-    MEASURED here: stock HF BERT (eager attention, cuBLAS) under torch.autocast(bf16) on the same weights and batch is
-    compared with the same oracle, and ours must not be worse than it on the q/k tensors by more than 15 %."""
+    host cores).  Stated tolerance: rel-L2 <= 2e-2 for EVERY tensor.  The attention query / key
+    projections are the sensitive ones (P * (dP - delta) with dP - delta = dO . (V_j - O_i): nearly collinear value rows
+    at initialisation amplify every upstream rounding ~10x); they meet 2e-2 because the forward keeps the residual stream
+    in fp32 (with a bf16 stream they reached 3.1e-2 in layer 11).  For context the same tensors of stock HF BERT (eager
+    attention, cuBLAS) under torch.autocast(bf16) are measured against the same oracle on the same batch and reported."""
     from oracle import cpu_step
     cfg = full_config(hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0)
     state = state_from_hf_init(cfg)
@@ -130,11 +129,11 @@ def test_full_size_gradients_per_tensor_vs_oracle(cuda_dev):
         worst[grp] = max(worst[grp], rel)
         worst["auto_" + grp] = max(worst["auto_" + grp], rel_a)
         rows.append((k, round(rel, 5), round(rel_a, 5)))
-        assert rel <= grad_tol(k), (k, rel)
+        assert rel <= TOL_GRAD_REL, (k, rel)
     print("worst rel-L2 vs fp32 oracle: q/k %.4f (torch bf16 autocast: %.4f), others %.4f (autocast: %.4f)"
           % (worst["qk"], worst["auto_qk"], worst["other"], worst["auto_other"]))
     report("config_a_grads", {"worst": worst, "qk_rows": [r for r in rows if is_qk(r[0])]})
-    assert worst["qk"] <= 1.15 * worst["auto_qk"], worst
+    assert worst["other"] <= 1.25 * worst["auto_other"], worst      # and no worse than autocast where it is not amplified
 
 
 @pytest.mark.parametrize("dropout,steps", [(False, 20), (True, 8)])
