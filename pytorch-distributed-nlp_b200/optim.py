@@ -6,6 +6,8 @@ Reference surface: ``build_optimizer(model, args)`` (multi-gpu-distributed-cls.p
 weight, ``correct_bias=True``) — NOT ``torch.optim.AdamW``.  One kernel updates the whole flat parameter space
 (or, under DDP, this rank's slice of every bucket, fused with the gradient mean over peers).
 """
+import os
+
 import torch
 
 from . import _lib as L
@@ -148,6 +150,8 @@ class AdamW(torch.optim.Optimizer):
 
     def update_range(self, begin, end, world, rank, peer_grads, peer_shadow, stream):
         """Fused (mean over peers +) HF-AdamW on flat elements [begin, end)."""
+        if os.environ.get("B2_DEBUG_SKIP_ADAMW") == "1":
+            return      # MEASUREMENT ONLY (how much of the optimizer is exposed in the step): weights are not updated
         st = self._state()
         hp = self.hparams()
         model = self._model

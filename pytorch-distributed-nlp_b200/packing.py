@@ -10,6 +10,7 @@ fewer rows, and the pooler reads each sequence's first token through `cls_index`
 exactly that of the padded batch (a padded key contributes exp(-3.4e38 - m) = 0 to its softmax row, like a key of
 another sequence here).
 """
+import numpy as np
 import torch
 
 BIN = 128
@@ -28,46 +29,52 @@ def pack_batch(input_ids, token_type_ids, attention_mask, bin_len=BIN):
     if input_ids.dim() != 2:
         raise ValueError("input_ids must be [batch, seq]")
     B, S = input_ids.shape
-    if attention_mask is None:
-        attention_mask = torch.ones_like(input_ids)
-    if token_type_ids is None:
-        token_type_ids = torch.zeros_like(input_ids)
-    mask = attention_mask.to(torch.int64)
-    lengths = mask.sum(1)
-    # valid tokens must form a prefix (right padding): cumulative product of the mask == the mask
-    if not torch.equal(torch.cumprod(mask, 1), mask):
+    ids_np = input_ids.numpy()
+    mask_np = (attention_mask.numpy() != 0) if attention_mask is not None else np.ones((B, S), dtype=bool)
+    lens = mask_np.sum(1).astype(np.int64)
+    # valid tokens must form a prefix (right padding): row i is exactly `lens[i]` ones followed by zeros
+    if not np.array_equal(mask_np, np.arange(S)[None, :] < lens[:, None]):
         raise ValueError("pack_batch: attention_mask is not a right-padded prefix mask")
-    if int(lengths.min()) < 1:
+    if int(lens.min()) < 1:
         raise ValueError("pack_batch: empty sequence (no valid token)")
-    if int(lengths.max()) > bin_len:
+    if int(lens.max()) > bin_len:
         raise ValueError("pack_batch: a sequence has %d valid tokens, more than the %d-token bin"
-                         % (int(lengths.max()), bin_len))
-    order = sorted(range(B), key=lambda i: (-int(lengths[i]), i))     # longest first; ties in batch order
-    free, where = [], [None] * B                                         # free[k]: tokens left in bin k
+                         % (int(lens.max()), bin_len))
+    # first-fit, longest first (ties in batch order): a few dozen integers -- plain Python
+    ll = lens.tolist()
+    order = sorted(range(B), key=lambda i: (-ll[i], i))
+    free, bin_of, lo_of = [], [0] * B, [0] * B
     for i in order:
-        n = int(lengths[i])
+        n = ll[i]
         for k in range(len(free)):
             if free[k] >= n:
-                where[i] = (k, bin_len - free[k])
+                bin_of[i], lo_of[i] = k, bin_len - free[k]
                 free[k] -= n
                 break
         else:
             free.append(bin_len - n)
-            where[i] = (len(free) - 1, 0)
+            bin_of[i], lo_of[i] = len(free) - 1, 0
     NB = len(free)
-    ids = torch.zeros(NB, bin_len, dtype=torch.int64)
-    tts = torch.zeros(NB, bin_len, dtype=torch.int64)
-    pos = torch.zeros(NB, bin_len, dtype=torch.int64)
-    ar = torch.arange(bin_len, dtype=torch.int32)
-    seg = (ar | ((ar + 1) << 16)).repeat(NB, 1).contiguous()             # unused rows: a segment of their own
-    cls_index = torch.zeros(B, dtype=torch.int64)
-    for i in range(B):
-        k, lo = where[i]
-        n = int(lengths[i])
-        ids[k, lo:lo + n] = input_ids[i, :n]
-        tts[k, lo:lo + n] = token_type_ids[i, :n]
-        pos[k, lo:lo + n] = torch.arange(n)
-        seg[k, lo:lo + n] = lo | ((lo + n) << 16)
-        cls_index[i] = k * bin_len + lo
-    return {"input_ids": ids, "token_type_ids": tts, "position_ids": pos, "segments": seg, "cls_index": cls_index,
-            "lengths": lengths, "bins": NB}
+    # one vectorised gather / scatter for all tokens
+    lo = np.asarray(lo_of, dtype=np.int64)
+    first = np.asarray(bin_of, dtype=np.int64) * bin_len + lo          # flat destination row of every sequence's [CLS]
+    total = int(lens.sum())
+    seq_of_tok = np.repeat(np.arange(B, dtype=np.int64), lens)
+    starts = np.cumsum(lens) - lens
+    within = np.arange(total, dtype=np.int64) - np.repeat(starts, lens)
+    src = seq_of_tok * S + within
+    dst = first[seq_of_tok] + within
+    ids = np.zeros(NB * bin_len, dtype=np.int64)
+    tts = np.zeros(NB * bin_len, dtype=np.int64)
+    pos = np.zeros(NB * bin_len, dtype=np.int64)
+    ar = np.arange(bin_len, dtype=np.int32)
+    seg = np.tile(ar | ((ar + 1) << 16), NB)                             # unused rows: a segment of their own
+    ids[dst] = ids_np.reshape(-1)[src]
+    if token_type_ids is not None:
+        tts[dst] = token_type_ids.numpy().reshape(-1)[src]
+    pos[dst] = within
+    seg[dst] = (lo[seq_of_tok] | ((lo[seq_of_tok] + lens[seq_of_tok]) << 16)).astype(np.int32)
+    t = torch.from_numpy
+    return {"input_ids": t(ids).view(NB, bin_len), "token_type_ids": t(tts).view(NB, bin_len),
+            "position_ids": t(pos).view(NB, bin_len), "segments": t(seg).view(NB, bin_len), "cls_index": t(first),
+            "lengths": t(lens), "bins": NB}
