@@ -28,7 +28,7 @@ extern "C" {
 /* ------------------------------------------------------------------------------------------------------ */
 const char* b2_last_error(void);
 int32_t b2_abi_version(void);             /* bumped when a struct below changes */
-#define B2_ABI_VERSION 16
+#define B2_ABI_VERSION 17
 int64_t b2_launch_count(void);            /* kernels launched by this library so far (process-wide) */
 
 /* ------------------------------------------------------------------------------------------------------ */
@@ -292,6 +292,17 @@ int32_t b2_bucket_reduce_adamw(const void* const* peer_grads, void* const* peer_
                                int32_t rank, float* master, float* exp_avg, float* exp_avg_sq,
                                const uint8_t* decay_flags, int64_t begin, int64_t end,
                                const b2_adamw_hparams_t* hp, const int64_t* step_counter, void* stream);
+
+/* Single-GPU background form of the same update (world == 1, no GradScaler state): blocks of 128 threads x 32
+ * registers and no shared memory, i.e. shaped to become resident BESIDE a 640-thread GEMM CTA instead of waiting for the
+ * gaps between GEMM kernels; launched per bucket on the optimizer stream while the backward pass is still running.
+ * `step_size` = the bias-corrected step of this update, a device float written by b2_adamw_prepare (lr * sqrt(1 - b2^t)
+ * / (1 - b1^t), t = *step_counter + 1, in double like the host would); call b2_adamw_prepare once per step, after
+ * b2_step_advance.  Same arithmetic as b2_bucket_reduce_adamw.                                                  */
+int32_t b2_adamw_prepare(const b2_adamw_hparams_t* hp, const int64_t* step_counter, float* step_size, void* stream);
+int32_t b2_adamw_background(const void* grads, void* shadow, float* master, float* exp_avg, float* exp_avg_sq,
+                            const uint8_t* decay_flags, int64_t begin, int64_t end, const b2_adamw_hparams_t* hp,
+                            const float* step_size, void* stream);
 
 /* ++step (AdamW t) and ++rng step (dropout stream) on the device: keeps CUDA-graph replays stateful.
  * found_inf (optional device fp32, see b2_adamw_hparams_t): non-zero leaves the AdamW step count untouched.   */

@@ -93,6 +93,79 @@ __global__ void __launch_bounds__(256) reduce_adamw_kernel(const ReduceAdamWPara
   }
 }
 
+// ---- single-GPU background form ------------------------------------------------------------------------------------
+// Measured (B2_DEBUG_SKIP_ADAMW): on one GPU the 0.49 ms of optimizer kernels are exposed almost in full, although they
+// run on their own stream under the backward pass -- a 256-thread x 64-register block cannot become resident on an SM
+// whose 64 K registers are held by a 640-thread x 96-register GEMM CTA (61 440), so the update only ever runs in the
+// gaps between GEMM kernels.  This variant is shaped to fit BESIDE such a CTA: 128 threads x 32 registers = the 4 096
+// registers that are left, no shared memory, and the same shared-memory carve-out preference as the GEMM kernels
+// (an SM is not re-partitioned while it has resident CTAs).  Blocks are short-lived (8 vectors of 4 elements per
+// thread) so they never hold an SM back from a kernel that needs all of it (the attention kernels).  Same arithmetic,
+// statement for statement, as reduce_adamw_kernel with world == 1; the bias-corrected step size is computed once per
+// step by adamw_prepare_kernel (double pow, as the host would) instead of in every block.
+struct SlimParams {
+  const __nv_bfloat16* grads; __nv_bfloat16* shadow;
+  float* master; float* m; float* v;
+  const uint8_t* decay;
+  long long begin, nvec4;
+  float beta1, beta2, one_minus_beta1, one_minus_beta2, eps, lr_wd;
+  int has_wd;
+  const float* step_size;
+};
+constexpr int kSlimThreads = 128, kSlimIters = 8;
+template <int DUMMY>
+__global__ void __launch_bounds__(DUMMY > 0 ? kSlimThreads : 0) __maxnreg__(DUMMY > 0 ? 32 : 24)
+adamw_slim_kernel(const SlimParams p) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const float step_size = *p.step_size;
+  long long i = (long long)blockIdx.x * (kSlimThreads * kSlimIters) + threadIdx.x;
+#pragma unroll 1
+  for (int it = 0; it < kSlimIters; ++it, i += kSlimThreads) {
+    if (i >= p.nvec4) break;
+    const long long e = p.begin + (i << 2);
+    const uint2 q = *reinterpret_cast<const uint2*>(p.grads + e);
+    float4 w = *reinterpret_cast<const float4*>(p.master + e);
+    float4 mm = *reinterpret_cast<const float4*>(p.m + e);
+    float4 vv = *reinterpret_cast<const float4*>(p.v + e);
+    const bool decay = p.has_wd && p.decay[e >> 3];
+    const float g0 = bf16_lo(q.x), g1 = bf16_hi(q.x), g2 = bf16_lo(q.y), g3 = bf16_hi(q.y);
+    mm.x = mm.x * p.beta1 + g0 * p.one_minus_beta1; vv.x = vv.x * p.beta2 + g0 * g0 * p.one_minus_beta2;
+    mm.y = mm.y * p.beta1 + g1 * p.one_minus_beta1; vv.y = vv.y * p.beta2 + g1 * g1 * p.one_minus_beta2;
+    mm.z = mm.z * p.beta1 + g2 * p.one_minus_beta1; vv.z = vv.z * p.beta2 + g2 * g2 * p.one_minus_beta2;
+    mm.w = mm.w * p.beta1 + g3 * p.one_minus_beta1; vv.w = vv.w * p.beta2 + g3 * g3 * p.one_minus_beta2;
+    w.x = w.x - step_size * (mm.x / (sqrtf(vv.x) + p.eps));
+    w.y = w.y - step_size * (mm.y / (sqrtf(vv.y) + p.eps));
+    w.z = w.z - step_size * (mm.z / (sqrtf(vv.z) + p.eps));
+    w.w = w.w - step_size * (mm.w / (sqrtf(vv.w) + p.eps));
+    if (decay) {
+      w.x = w.x - p.lr_wd * w.x; w.y = w.y - p.lr_wd * w.y; w.z = w.z - p.lr_wd * w.z; w.w = w.w - p.lr_wd * w.w;
+    }
+    *reinterpret_cast<float4*>(p.master + e) = w;
+    *reinterpret_cast<float4*>(p.m + e) = mm;
+    *reinterpret_cast<float4*>(p.v + e) = vv;
+    uint2 o;
+    o.x = pack_bf16(w.x, w.y);
+    o.y = pack_bf16(w.z, w.w);
+    *reinterpret_cast<uint2*>(p.shadow + e) = o;
+  }
+}
+
+// HF AdamW bias correction for the NEXT update: step_size = lr * sqrt(1 - b2^t) / (1 - b1^t), t = *step + 1
+__global__ void adamw_prepare_kernel(double lr, double beta1, double beta2, int correct_bias, const long long* step,
+                                     float* step_size) {
+  pdl_wait();
+  pdl_launch_dependents();
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    double ss = lr;
+    if (correct_bias) {
+      const long long t = *step + 1;
+      ss = lr * sqrt(1.0 - pow(beta2, (double)t)) / (1.0 - pow(beta1, (double)t));
+    }
+    *step_size = (float)ss;
+  }
+}
+
 __global__ void step_advance_kernel(long long* step, unsigned long long* rng, const float* found_inf) {
   pdl_wait();               // PDL: predecessors complete + visible before any global access
   pdl_launch_dependents();  // let the next kernel in the stream begin launching
@@ -192,6 +265,49 @@ extern "C" int32_t b2_bucket_reduce_adamw(const void* const* peer_grads, void* c
   const long long cap = 148 * 8;
   if (blocks > cap) blocks = cap;
   B2_LAUNCH(reduce_adamw_kernel, (unsigned)blocks, 256, 0, (cudaStream_t)stream_, p);
+  B2_CUDA(cudaGetLastError());
+  count_launches(1);
+  return 0;
+}
+
+extern "C" int32_t b2_adamw_prepare(const b2_adamw_hparams_t* hp, const int64_t* step_counter, float* step_size,
+                                    void* stream_) {
+  B2_REQUIRE(hp && step_counter && step_size, "adamw_prepare: null pointer");
+  B2_LAUNCH(adamw_prepare_kernel, 1, 32, 0, (cudaStream_t)stream_, hp->lr, hp->beta1, hp->beta2, hp->correct_bias,
+            (const long long*)step_counter, step_size);
+  B2_CUDA(cudaGetLastError());
+  count_launches(1);
+  return 0;
+}
+
+extern "C" int32_t b2_adamw_background(const void* grads, void* shadow, float* master, float* exp_avg,
+                                       float* exp_avg_sq, const uint8_t* decay_flags, int64_t begin, int64_t end,
+                                       const b2_adamw_hparams_t* hp, const float* step_size, void* stream_) {
+  B2_REQUIRE(grads && shadow && master && exp_avg && exp_avg_sq && decay_flags && hp && step_size,
+             "adamw_background: null pointer");
+  B2_REQUIRE(begin >= 0 && end >= begin && begin % 8 == 0 && end % 8 == 0,
+             "adamw_background: slice [%lld,%lld) must be 8-element aligned", (long long)begin, (long long)end);
+  B2_REQUIRE(hp->grad_scale == nullptr && hp->found_inf == nullptr && hp->skip_flags == nullptr,
+             "adamw_background: GradScaler state / skip flags are handled by b2_bucket_reduce_adamw");
+  if (end == begin) return 0;
+  static bool attr = false;
+  if (!attr) {   // same shared-memory carve-out as the GEMM CTAs it is meant to run beside
+    B2_CUDA(cudaFuncSetAttribute(adamw_slim_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                 cudaSharedmemCarveoutMaxShared));
+    attr = true;
+  }
+  SlimParams p;
+  p.grads = (const __nv_bfloat16*)grads; p.shadow = (__nv_bfloat16*)shadow;
+  p.master = master; p.m = exp_avg; p.v = exp_avg_sq; p.decay = decay_flags;
+  p.begin = begin; p.nvec4 = (end - begin) >> 2;
+  p.beta1 = (float)hp->beta1; p.beta2 = (float)hp->beta2;
+  p.one_minus_beta1 = (float)(1.0 - hp->beta1); p.one_minus_beta2 = (float)(1.0 - hp->beta2);
+  p.eps = (float)hp->eps; p.lr_wd = (float)(hp->lr * hp->weight_decay);
+  p.has_wd = hp->weight_decay > 0.0 ? 1 : 0;
+  p.step_size = step_size;
+  const long long per_block = (long long)kSlimThreads * kSlimIters;
+  const long long blocks = (p.nvec4 + per_block - 1) / per_block;
+  B2_LAUNCH(adamw_slim_kernel<1>, (unsigned)blocks, kSlimThreads, 0, (cudaStream_t)stream_, p);
   B2_CUDA(cudaGetLastError());
   count_launches(1);
   return 0;

@@ -65,6 +65,7 @@ class AdamW(torch.optim.Optimizer):
         self._dev_state = None
         self._armed = False      # set by FusedTrainStep: per-bucket updates may start during backward
         self._pending = set()    # buckets already updated (on the engine's optimizer stream) in this step
+        self._background = os.environ.get("B2_ADAMW_BACKGROUND", "1") != "0"   # one-GPU update shaped to co-reside
         self._amp_seen = False   # a GradScaler drives this optimizer: the scale is only known inside step(), so
                                  # per-bucket updates must not start during backward
         self._model._optimizer = self
@@ -81,10 +82,17 @@ class AdamW(torch.optim.Optimizer):
                 "exp_avg": torch.zeros(n, dtype=torch.float32, device=eng.dev),
                 "exp_avg_sq": torch.zeros(n, dtype=torch.float32, device=eng.dev),
                 "step": torch.zeros(1, dtype=torch.int64, device=eng.dev),
+                "step_size": torch.zeros(1, dtype=torch.float32, device=eng.dev),   # see b2_adamw_prepare
                 "decay": self._decay_flags_cpu.to(eng.dev),
                 "skip": self._fused_skip_flags().to(eng.dev),
             }
+            self._prepare(eng.stream())
         return self._dev_state
+
+    def _prepare(self, stream):
+        """bias-corrected step size of the NEXT update -> device float (read by the background kernel)"""
+        st = self._dev_state
+        L.call("b2_adamw_prepare", self.hparams(), L.ptr(st["step"]), L.ptr(st["step_size"]), stream)
 
     def _fused_skip_flags(self):
         """uint8 per 8-element vector: 1 for the encoder weight matrices, which the single-GPU fused step updates in the
@@ -129,7 +137,9 @@ class AdamW(torch.optim.Optimizer):
             raise TypeError("grad_scale must be a CUDA fp32 scalar (torch.cuda.amp.GradScaler's)")
         hp.found_inf = self._found_inf_ptr()
         eng = self._model._engine
-        hp.skip_flags = self._state()["skip"].data_ptr() if getattr(eng, "fused_adamw_active", False) else None
+        st = self._dev_state
+        hp.skip_flags = (st["skip"].data_ptr() if (st is not None and getattr(eng, "fused_adamw_active", False))
+                         else None)
         return hp
 
     def _found_inf_ptr(self):
@@ -155,6 +165,12 @@ class AdamW(torch.optim.Optimizer):
         st = self._state()
         hp = self.hparams()
         model = self._model
+        if (world == 1 and self._background and hp.grad_scale is None and hp.found_inf is None and
+                hp.skip_flags is None):
+            # one GPU: the form that fits beside the GEMM CTAs (csrc/optim.cu, adamw_slim_kernel)
+            L.call("b2_adamw_background", peer_grads[0], peer_shadow[0], L.ptr(model._flat), L.ptr(st["exp_avg"]),
+                   L.ptr(st["exp_avg_sq"]), L.ptr(st["decay"]), begin, end, hp, L.ptr(st["step_size"]), stream)
+            return
         L.call("b2_bucket_reduce_adamw", L.ptr_array(peer_grads), L.ptr_array(peer_shadow), world, rank,
                L.ptr(model._flat), L.ptr(st["exp_avg"]), L.ptr(st["exp_avg_sq"]), L.ptr(st["decay"]), begin, end,
                hp, L.ptr(st["step"]), stream)
@@ -162,6 +178,7 @@ class AdamW(torch.optim.Optimizer):
     def advance(self, stream):
         st = self._state()
         L.call("b2_step_advance", L.ptr(st["step"]), L.ptr(self._model._engine.rng), self._found_inf_ptr(), stream)
+        self._prepare(stream)
 
     @torch.no_grad()
     def step(self, closure=None):

@@ -296,6 +296,47 @@ def test_head_and_ce(cuda_dev, p):
     assert float(dh[:, 1:].float().abs().max()) == 0.0
 
 
+def test_adamw_background_form_matches_hf_restatement(cuda_dev):
+    """b2_adamw_background (the one-GPU form shaped to run beside the GEMM CTAs: 128 threads x 32 registers) +
+    b2_adamw_prepare (bias-corrected step size on the device) vs oracle/adamw_ref.HFAdamW, and bit-identical to
+    b2_bucket_reduce_adamw on the same inputs."""
+    from oracle import adamw_ref
+    dev = cuda_dev
+    n = 8 * 5003
+    torch.manual_seed(4)
+    master = torch.randn(n, device=dev)
+    ref_p = {"w.weight": master[: n // 2].clone().cpu(), "w.bias": master[n // 2:].clone().cpu()}
+    opt = adamw_ref.HFAdamW(ref_p, lr=3e-5, weight_decay=0.01)
+    m, v = torch.zeros(n, device=dev), torch.zeros(n, device=dev)
+    shadow = torch.empty(n, dtype=bf, device=dev)
+    master2, m2, v2, shadow2 = master.clone(), m.clone(), v.clone(), shadow.clone()
+    decay = torch.zeros(n // 8, dtype=torch.uint8, device=dev)
+    decay[: n // 16] = 1
+    step = torch.zeros(1, dtype=torch.int64, device=dev)
+    step_size = torch.zeros(1, device=dev)
+    rs = rng_state(dev, 1, 0)
+    hp = L.AdamWHParams()
+    hp.lr, hp.beta1, hp.beta2, hp.eps, hp.weight_decay, hp.correct_bias = 3e-5, 0.9, 0.999, 1e-6, 0.01, 1
+    L.call("b2_adamw_prepare", hp, step.data_ptr(), step_size.data_ptr(), S())
+    for it in range(4):
+        g = (torch.randn(n, device=dev) * 0.01).to(bf)
+        L.call("b2_adamw_background", g.data_ptr(), shadow.data_ptr(), master.data_ptr(), m.data_ptr(), v.data_ptr(),
+               decay.data_ptr(), 0, n, hp, step_size.data_ptr(), S())
+        L.call("b2_bucket_reduce_adamw", L.ptr_array([g.data_ptr()]), L.ptr_array([shadow2.data_ptr()]), 1, 0,
+               master2.data_ptr(), m2.data_ptr(), v2.data_ptr(), decay.data_ptr(), 0, n, hp, step.data_ptr(), S())
+        L.call("b2_step_advance", step.data_ptr(), rs.data_ptr(), None, S())
+        L.call("b2_adamw_prepare", hp, step.data_ptr(), step_size.data_ptr(), S())
+        gc = g.float().cpu()
+        opt.step({"w.weight": gc[: n // 2], "w.bias": gc[n // 2:]})
+    torch.cuda.synchronize()
+    ref = torch.cat([ref_p["w.weight"], ref_p["w.bias"]])
+    assert (master.cpu() - ref).abs().max().item() < 2e-7
+    assert torch.equal(master, master2) and torch.equal(m, m2) and torch.equal(v, v2) and torch.equal(shadow, shadow2)
+    with pytest.raises(RuntimeError, match="8-element aligned"):
+        L.call("b2_adamw_background", g.data_ptr(), shadow.data_ptr(), master.data_ptr(), m.data_ptr(), v.data_ptr(),
+               decay.data_ptr(), 4, n, hp, step_size.data_ptr(), S())
+
+
 def test_ce_ignore_index_matches_torch(cuda_dev):
     """torch.nn.CrossEntropyLoss defaults (multi-gpu-distributed-cls.py:343): label -100 is ignored and the mean runs
     over the remaining samples; all-ignored -> nan."""
