@@ -83,6 +83,25 @@ def main(local=None, world=None, init_method=None):
             lv, rv = float(loss), float(red)
             assert abs(lv - float(hist[s]["loss_per_rank"][rank])) <= TOL_TRAJ, (mode, s, rank, lv)
             assert abs(rv - float(hist[s]["loss_mean"])) <= TOL_TRAJ, (mode, s, rank, rv)
+        if mode == "amp":
+            # one rank's loss overflows: stock DDP all-reduces the gradients before GradScaler looks at them, so EVERY
+            # rank skips the step and backs its scale off.  Here the inf check sees the classifier.bias probe, made
+            # rank-consistent by a scalar peer exchange (ddp.consensus_probe): same outcome, no rank diverges.
+            before = model._flat.clone()
+            t_before = int(opt._state()["step"])
+            d = {k: v.to(dev) for k, v in batches[0][rank].items()}
+            with torch.autocast("cuda"):
+                out = ddp(input_ids=d["input_ids"], token_type_ids=d["token_type_ids"],
+                          attention_mask=d["attention_mask"], labels=d["label"])
+                loss = F.cross_entropy(out[1], d["label"]) * (float("inf") if rank == world - 1 else 1.0)
+            scaler.scale(loss).backward()
+            scaler.step(opt)
+            scaler.update()
+            torch.cuda.synchronize()
+            assert float(scaler.get_scale()) == 32768.0, (rank, float(scaler.get_scale()))
+            assert int(opt._state()["step"]) == t_before, rank
+            assert torch.equal(model._flat, before), (rank, "a skipped step changed the weights")
+            assert bool(torch.isfinite(model._engine.shadow.float()).all())
         # the reference's checkpoint idiom: ONLY rank 0 calls state_dict() (`if local_rank == 0: torch.save(
         # self.model.state_dict(), ...)`, multi-gpu-distributed-cls.py:190-197) -- it must not need the other ranks
         # (fp32 slices owned by peers are pulled one-sidedly out of their HBM)

@@ -200,6 +200,26 @@ def test_amp_script_loop_with_gradscaler(cuda_dev):
         assert torch.equal(before[k], after[k]), k
 
 
+def test_second_backward_without_step_raises(cuda_dev):
+    """gradients live in the bf16 bucket space and are OVERWRITTEN by every backward (zero_grad is a no-op): with an
+    optimizer attached, a second backward before optimizer.step() must raise instead of silently dropping the first
+    one's gradients (torch would have accumulated them)"""
+    cfg = tiny_config(hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0)
+    model = make_model(cfg, state_from_hf_init(cfg), cuda_dev).train()
+
+    class A:
+        weight_decay, learning_rate = 0.01, 3e-5
+
+    opt = b2.build_optimizer(model, A)
+    b = bert_ref.synthetic_batch(cfg, 4, 128, 3)
+    _fwd_bwd(model, b, cuda_dev)
+    with pytest.raises(RuntimeError, match="accumulation"):
+        _fwd_bwd(model, b, cuda_dev)
+    opt.step()
+    _fwd_bwd(model, b, cuda_dev)          # fine again after the step
+    opt.step()
+
+
 def test_state_dict_round_trip_and_hf_loadable(cuda_dev):
     cfg = tiny_config()
     state = state_from_hf_init(cfg)
