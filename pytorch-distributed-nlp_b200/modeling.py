@@ -808,7 +808,7 @@ class _Engine:
                     self.opt_stream.wait_event(wg_event)
                 b0, e0, _lbl = self.lay.buckets[idx]
                 opt.update_range(b0, e0, 1, 0, [self.grads.data_ptr()], [self.shadow.data_ptr()],
-                                 self.opt_stream.cuda_stream)
+                                 self.opt_stream.cuda_stream, background=(idx != 0))
                 opt._pending.add(idx)
 
         if not self.lay.head_in_last_layer:

@@ -158,14 +158,17 @@ class AdamW(torch.optim.Optimizer):
         self._model._params_by_name["classifier.bias"].grad = None
         return None
 
-    def update_range(self, begin, end, world, rank, peer_grads, peer_shadow, stream):
-        """Fused (mean over peers +) HF-AdamW on flat elements [begin, end)."""
+    def update_range(self, begin, end, world, rank, peer_grads, peer_shadow, stream, background=False):
+        """Fused (mean over peers +) HF-AdamW on flat elements [begin, end).  background=True (one GPU, the update of
+        a bucket launched while the backward pass is still running): the form shaped to run beside the GEMM CTAs;
+        with nothing left to hide behind (the last bucket, or a plain optimizer.step()) the 256-thread kernel is the
+        faster one (5.2 vs 3.6 TB/s alone)."""
         if os.environ.get("B2_DEBUG_SKIP_ADAMW") == "1":
             return      # MEASUREMENT ONLY (how much of the optimizer is exposed in the step): weights are not updated
         st = self._state()
         hp = self.hparams()
         model = self._model
-        if (world == 1 and self._background and hp.grad_scale is None and hp.found_inf is None and
+        if (background and world == 1 and self._background and hp.grad_scale is None and hp.found_inf is None and
                 hp.skip_flags is None):
             # one GPU: the form that fits beside the GEMM CTAs (csrc/optim.cu, adamw_slim_kernel)
             L.call("b2_adamw_background", peer_grads[0], peer_shadow[0], L.ptr(model._flat), L.ptr(st["exp_avg"]),
