@@ -28,7 +28,7 @@ extern "C" {
 /* ------------------------------------------------------------------------------------------------------ */
 const char* b2_last_error(void);
 int32_t b2_abi_version(void);             /* bumped when a struct below changes */
-#define B2_ABI_VERSION 17
+#define B2_ABI_VERSION 18
 int64_t b2_launch_count(void);            /* kernels launched by this library so far (process-wide) */
 
 /* ------------------------------------------------------------------------------------------------------ */
@@ -242,6 +242,17 @@ int32_t b2_head_bwd_packed(const float* dlogits, const void* hidden_states, cons
                            const void* pool_w, const void* cls_w, int64_t num_labels, float dropout_p,
                            const void* rng_state, uint32_t rng_site, void* d_pool_w, void* d_pool_b, void* d_cls_w,
                            void* d_cls_b, void* d_hidden, int32_t d_hidden_fp32, float* scratch, void* stream);
+
+/* b2_head_bwd / b2_head_bwd_packed (cls_rows NULL: row of sequence b = b * seq) with the two parameter-gradient
+ * kernels launched on `weight_stream` (ordered behind the data-gradient part by an event; the same stream when NULL): they
+ * are off the critical path of the backward.  Whatever reads the four head gradients must be ordered behind
+ * `weight_stream`.                                                                                               */
+int32_t b2_head_bwd_split(const float* dlogits, const void* hidden_states, const void* pooled,
+                          const int64_t* cls_rows, int64_t tokens, int64_t batch, int64_t seq, int64_t hidden,
+                          const void* pool_w, const void* cls_w, int64_t num_labels, float dropout_p,
+                          const void* rng_state, uint32_t rng_site, void* d_pool_w, void* d_pool_b, void* d_cls_w,
+                          void* d_cls_b, void* d_hidden, int32_t d_hidden_fp32, float* scratch, void* stream,
+                          void* weight_stream);
 
 /* ------------------------------------------------------------------------------------------------------ */
 /* optimizer + gradient exchange                                                                          */

@@ -14,8 +14,11 @@ class is third-party code pinned at transformers==4.28.1 (README.md:6) and is AB
 
 Defaults: lr as passed (3e-5 in the reference Args :252), betas (0.9, 0.999), eps 1e-6, correct_bias True.
 Parity for this piece is "unpinned" in the brief's sense (no executable upstream, no upstream vectors); it is anchored
-on (a) the formula above, (b) a hand-computed scalar case in tests/test_oracle.py, and (c) its documented difference
-from torch.optim.AdamW (eps placement, decay ordering), which the tests assert.
+on (a) the formula above, (b) a hand-computed scalar case in tests/test_oracle.py, (c) two limits in which the
+algorithm coincides with optimizers that CAN be executed here (tests/test_oracle.py::
+test_hf_adamw_restatement_vs_executable_upstreams): eps = 0, no decay == torch.optim.Adam(eps=0) over several steps
+(moment recursions + bias correction), and eps = 0 with decay differs from torch.optim.AdamW by exactly lr * wd * update
+(decay applied after the update); only the placement of eps rests on the formula and the hand case alone.
 """
 import math
 

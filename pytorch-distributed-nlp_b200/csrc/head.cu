@@ -307,7 +307,7 @@ static int32_t head_bwd_impl(const float* dlogits, const void* hidden_states, co
                                int64_t seq, int64_t hidden, const void* pool_w, const void* cls_w, int64_t num_labels,
                                float dropout_p, const void* rng_state, uint32_t rng_site, void* d_pool_w,
                                void* d_pool_b, void* d_cls_w, void* d_cls_b, void* d_hidden, int32_t d_hidden_fp32,
-                               float* scratch, void* stream_) {
+                               float* scratch, void* stream_, void* weight_stream_ = nullptr) {
   cudaStream_t stream = (cudaStream_t)stream_;
   B2_REQUIRE(dlogits && hidden_states && pooled && pool_w && cls_w && d_pool_w && d_pool_b && d_cls_w && d_cls_b &&
                  d_hidden && scratch,
@@ -328,11 +328,22 @@ static int32_t head_bwd_impl(const float* dlogits, const void* hidden_states, co
             d_hidden_fp32 ? 1 : 0);
   B2_CUDA(cudaGetLastError());
   count_launches(1);
-  B2_LAUNCH(head_bwd_k1b, dim3((unsigned)((hidden + 255) / 256), (unsigned)num_labels), 256, 0, stream, dlogits, pm,
+  // The two parameter-gradient kernels are off the critical path (only the optimizer / exchange consumes them): on
+  // request they go to the caller's weight-gradient stream, ordered behind k1 (which fills `scratch` / `pm`) by an
+  // event, so the main stream continues with the encoder's backward right after k3
+  cudaStream_t wstream = stream;
+  if (weight_stream_ != nullptr && (cudaStream_t)weight_stream_ != stream) {
+    static thread_local cudaEvent_t ev = nullptr;
+    if (ev == nullptr) B2_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    B2_CUDA(cudaEventRecord(ev, stream));
+    wstream = (cudaStream_t)weight_stream_;
+    B2_CUDA(cudaStreamWaitEvent(wstream, ev, 0));
+  }
+  B2_LAUNCH(head_bwd_k1b, dim3((unsigned)((hidden + 255) / 256), (unsigned)num_labels), 256, 0, wstream, dlogits, pm,
             (int)batch, (int)hidden, (int)num_labels, (__nv_bfloat16*)d_cls_w, (__nv_bfloat16*)d_cls_b);
   B2_CUDA(cudaGetLastError());
   count_launches(1);
-  B2_LAUNCH(head_bwd_k2, (unsigned)hidden, (unsigned)(hidden / 8), 0, stream, 
+  B2_LAUNCH(head_bwd_k2, (unsigned)hidden, (unsigned)(hidden / 8), 0, wstream, 
       scratch, (const __nv_bfloat16*)hidden_states, (const long long*)cls_rows, (int)batch, (int)seq, (int)hidden,
       (__nv_bfloat16*)d_pool_w, (__nv_bfloat16*)d_pool_b);
   B2_CUDA(cudaGetLastError());
@@ -360,4 +371,19 @@ extern "C" int32_t b2_head_bwd_packed(const float* dlogits, const void* hidden_s
   return head_bwd_impl(dlogits, hidden_states, pooled, cls_rows, tokens, batch, 1, hidden, pool_w, cls_w, num_labels,
                        dropout_p, rng_state, rng_site, d_pool_w, d_pool_b, d_cls_w, d_cls_b, d_hidden, d_hidden_fp32,
                        scratch, stream_);
+}
+
+// b2_head_bwd / b2_head_bwd_packed with the two parameter-gradient kernels on a second stream (cls_rows may be NULL:
+// row of sequence b = b * seq).  The caller must order whatever consumes d_pool_w / d_pool_b / d_cls_w / d_cls_b
+// behind `weight_stream`.
+extern "C" int32_t b2_head_bwd_split(const float* dlogits, const void* hidden_states, const void* pooled,
+                                     const int64_t* cls_rows, int64_t tokens, int64_t batch, int64_t seq,
+                                     int64_t hidden, const void* pool_w, const void* cls_w, int64_t num_labels,
+                                     float dropout_p, const void* rng_state, uint32_t rng_site, void* d_pool_w,
+                                     void* d_pool_b, void* d_cls_w, void* d_cls_b, void* d_hidden,
+                                     int32_t d_hidden_fp32, float* scratch, void* stream_, void* weight_stream_) {
+  B2_REQUIRE(tokens > 0 && (cls_rows != nullptr || tokens == batch * seq), "head_bwd_split: tokens / seq mismatch");
+  return head_bwd_impl(dlogits, hidden_states, pooled, cls_rows, tokens, batch, cls_rows ? 1 : seq, hidden, pool_w,
+                       cls_w, num_labels, dropout_p, rng_state, rng_site, d_pool_w, d_pool_b, d_cls_w, d_cls_b,
+                       d_hidden, d_hidden_fp32, scratch, stream_, weight_stream_);
 }

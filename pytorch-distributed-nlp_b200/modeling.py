@@ -760,14 +760,18 @@ class _Engine:
         x_last = ws["layers"][-1]["x2"] if self.nl > 0 else ws["emb_out"]
         head_g = (g("bert.pooler.dense.weight"), g("bert.pooler.dense.bias"), g("classifier.weight"),
                   g("classifier.bias"))
-        if packed is None:
-            L.call("b2_head_bwd", dl.data_ptr(), x_last.data_ptr(), ws["pooled"].data_ptr(), B, S, H,
-                   w("bert.pooler.dense.weight"), w("classifier.weight"), self.C, p_c, rng, 1 + 3 * self.nl,
-                   *head_g, ws["dxA"].data_ptr(), 1, ws["head_scratch"].data_ptr(), s)
-        else:
-            L.call("b2_head_bwd_packed", dl.data_ptr(), x_last.data_ptr(), ws["pooled"].data_ptr(),
-                   packed[1].data_ptr(), M, Bo, H, w("bert.pooler.dense.weight"), w("classifier.weight"), self.C, p_c,
-                   rng, 1 + 3 * self.nl, *head_g, ws["dxA"].data_ptr(), 1, ws["head_scratch"].data_ptr(), s)
+        # data gradient (d_hidden) on the main stream; the four head parameter gradients on the weight-gradient stream
+        # (they belong to the last layer's bucket, whose readiness waits for that stream's marker of the layer anyway).
+        # A model without encoder layers announces its head bucket right away: keep everything on one stream there.
+        main0 = torch.cuda.current_stream(self.dev)
+        head_side = self.wgrad_stream if (self.use_wgrad_stream and self.nl > 0) else main0
+        if head_side is not main0:
+            # the side stream may still be busy with the previous step's tail; it must also not overtake this step
+            head_side.wait_stream(main0)
+        L.call("b2_head_bwd_split", dl.data_ptr(), x_last.data_ptr(), ws["pooled"].data_ptr(),
+               None if packed is None else packed[1].data_ptr(), M, Bo, S, H, w("bert.pooler.dense.weight"),
+               w("classifier.weight"), self.C, p_c, rng, 1 + 3 * self.nl, *head_g, ws["dxA"].data_ptr(), 1,
+               ws["head_scratch"].data_ptr(), s, None if head_side is main0 else head_side.cuda_stream)
         dx, dx_other = ws["dxA"], ws["dxB"]
         # Weight gradients are off the critical path (only the optimizer consumes them): they run on a second stream,
         # overlapping the dgrad / LayerNorm / attention chain of the main stream.  Their A operands (dzd, dU, dz1d,

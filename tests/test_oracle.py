@@ -168,6 +168,40 @@ def _gloo_worker(rank, world, port, out_path):
     dist.destroy_process_group()
 
 
+def test_hf_adamw_restatement_vs_executable_upstreams():
+    """HF's AdamW class cannot be executed here (removed from the installed transformers), but two limits of its
+    published algorithm coincide with optimizers that CAN: (1) with eps = 0 and weight_decay = 0 it is exactly
+    torch.optim.Adam with eps = 0 (lr * sqrt(bc2) / bc1 * m / sqrt(v) either way): pins the moment recursions and the
+    bias correction over several steps; (2) its weight decay is torch.optim.AdamW's decoupled decay applied AFTER the Adam
+    update instead of before it, so with eps = 0 the two differ by exactly lr * wd * (the Adam update): pins the decay
+    ordering.  What stays anchored on the formula + hand case alone is the placement of eps."""
+    torch.manual_seed(0)
+    p0 = torch.randn(64, dtype=torch.float64)
+    grads = [torch.randn(64, dtype=torch.float64) * 0.1 for _ in range(6)]
+    # (1) vs torch.optim.Adam
+    tp = torch.nn.Parameter(p0.clone())
+    to = torch.optim.Adam([tp], lr=3e-3, betas=(0.9, 0.999), eps=0.0)
+    hp = {"w.weight": p0.clone()}
+    ho = adamw_ref.HFAdamW(hp, lr=3e-3, eps=0.0, weight_decay=0.0)
+    for g in grads:
+        tp.grad = g.clone()
+        to.step()
+        ho.step({"w.weight": g})
+        assert float((tp.data - hp["w.weight"]).abs().max()) < 1e-14
+    # (2) vs torch.optim.AdamW: one step from identical state, eps = 0
+    lr, wd = 3e-3, 0.1
+    tp = torch.nn.Parameter(p0.clone())
+    to = torch.optim.AdamW([tp], lr=lr, betas=(0.9, 0.999), eps=0.0, weight_decay=wd)
+    hp = {"w.weight": p0.clone()}
+    ho = adamw_ref.HFAdamW(hp, lr=lr, eps=0.0, weight_decay=wd)
+    tp.grad = grads[0].clone()
+    to.step()
+    ho.step({"w.weight": grads[0]})
+    u = lr * torch.sign(grads[0])            # first Adam update with eps = 0: lr * m_hat / sqrt(v_hat) = lr * sign(g)
+    # torch: p0 (1 - lr wd) - u ;  HF: (p0 - u) (1 - lr wd)  ->  HF - torch = lr wd u
+    assert float(((hp["w.weight"] - tp.data) - lr * wd * u).abs().max()) < 1e-14
+
+
 def test_ddp_mean_semantics_on_gloo_world2(tmp_path):
     """ddp_ref.mean_grads == what real torch DDP leaves in .grad (gloo, world 2, rank-0 weights broadcast)."""
     ctx = mp.get_context("spawn")
