@@ -378,6 +378,8 @@ class BertForSequenceClassification(nn.Module):
         return torch.nn.modules.module._IncompatibleKeys(missing, unexpected)
 
     def state_dict(self, *args, **kwargs):
+        if self._optimizer is not None:
+            self._optimizer.flush_pending()      # a pipelined train step may still owe its update
         if self._ddp is not None:
             self._ddp._gather_master()
         return super().state_dict(*args, **kwargs)
@@ -392,6 +394,8 @@ class BertForSequenceClassification(nn.Module):
                                "there is no CPU path.")
         if input_ids is None:
             raise ValueError("input_ids is required")
+        if self._optimizer is not None:
+            self._optimizer.flush_pending()      # a pipelined train step may still owe its update
         packed = None
         if segments is not None or cls_index is not None:
             if position_ids is None or segments is None or cls_index is None:
@@ -618,9 +622,12 @@ class _Engine:
         L.call("b2_layernorm_fwd", z, gamma, beta, M, H, eps, y, mean, rstd, s)
 
     # ---- forward --------------------------------------------------------------------------------------------------------
-    def forward(self, input_ids, token_type_ids, attention_mask, labels, training, need_backward, packed=None):
+    def forward(self, input_ids, token_type_ids, attention_mask, labels, training, need_backward, packed=None,
+                weight_events=None):
         """packed: None, or (position_ids int64 [bins, 128], segments int32 [bins, 128], cls_index int64 [batch]) --
-        the rows of `input_ids` are then 128-token bins produced by packing.pack_batch, not sequences."""
+        the rows of `input_ids` are then 128-token bins produced by packing.pack_batch, not sequences.
+        weight_events: None, or one event per bucket (forward order) after which that bucket's bf16 weights are
+        current (pipelined optimizer, optim.AdamW.apply_pending): each is awaited right before its first use."""
         cfg, H, I = self.cfg, self.H, self.I
         if input_ids.dim() != 2:
             raise ValueError("input_ids must be [batch, seq]")
@@ -664,6 +671,9 @@ class _Engine:
         w = self.w
         KM, MN = L.MAJOR_K, L.MAJOR_MN
 
+        cur = torch.cuda.current_stream(self.dev)
+        if weight_events is not None:
+            cur.wait_event(weight_events[0])
         emb_w = (w("bert.embeddings.word_embeddings.weight"), w("bert.embeddings.position_embeddings.weight"),
                  w("bert.embeddings.token_type_embeddings.weight"), w("bert.embeddings.LayerNorm.weight"),
                  w("bert.embeddings.LayerNorm.bias"))
@@ -680,6 +690,8 @@ class _Engine:
         for l in range(self.nl):
             a = ws["layers"][l]
             pre = "bert.encoder.layer.%d." % l
+            if weight_events is not None:
+                cur.wait_event(weight_events[1 + l])
             self.gemm(M, 3 * H, H, x.data_ptr(), H, KM, w(pre + "attention.self.query.weight"), H, KM,
                       a["qkv"].data_ptr(), 3 * H, L.EPI_BIAS, bias=w(pre + "attention.self.query.bias"))
             if packed is None:
@@ -703,6 +715,8 @@ class _Engine:
                 w(pre + "output.LayerNorm.bias"), a["z2"].data_ptr(), a["x2"].data_ptr(), L.ptr(a["x2f"]),
                 a["mean2"].data_ptr(), a["rstd2"].data_ptr())
             x, xf = a["x2"], a["x2f"]
+        if weight_events is not None:
+            cur.wait_event(weight_events[-1])         # the head's bucket (the last layer's, or its own)
         head_w = (w("bert.pooler.dense.weight"), w("bert.pooler.dense.bias"), w("classifier.weight"),
                   w("classifier.bias"))
         if packed is None:

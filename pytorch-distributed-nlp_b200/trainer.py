@@ -137,6 +137,24 @@ class _StagedGraphStep:
             return
         self.graph.replay()
 
+    def _train_body(self, forward):
+        """forward(weight_events) -> (logits, loss): the common part of the captured train steps"""
+        eng, opt = self.eng, self.opt
+        events = opt.apply_pending(in_step=True) if opt._pipelined else None     # step i-1's update, see optim.py
+        logits, loss = forward(events)
+        B, S, mask, p_h, p_a, p_c, packed = eng._saved
+        eng._saved = None
+        Bo = B if packed is None else packed[1].numel()
+        ws = eng.workspace(B, S, Bo)
+        # d(loss)/d(logits) was produced by the CE kernel: the reference's criterion(logits, label) [:169]
+        eng._backward_from_dlogits(ws["dloss_logits"], B, S, mask, p_h, p_a, p_c, packed)
+        if opt._pipelined:
+            opt.mark_grads_pending()
+            torch.cuda.current_stream(eng.dev).wait_stream(eng.opt_stream)   # (step counter bump of the applied update)
+        else:
+            opt.step()
+        self.loss_out.copy_(loss)
+
     def loss_to_host(self):
         self.h_loss.copy_(self.loss_out, non_blocking=True)
         torch.cuda.current_stream(self.eng.dev).synchronize()
@@ -154,20 +172,14 @@ class FusedTrainStep(_StagedGraphStep):
         # the fused step owns backward + optimizer: per-bucket AdamW (and, under DDP, the peer exchange) may start
         # while backward is still running
         optimizer._armed = True
+        optimizer.enable_pipelining()     # one GPU: the update moves under the NEXT step's forward (optim.py)
         self.kernel_launches = None
 
     # the step body, expressed only with stream-ordered work (capturable)
     def _body(self):
-        eng = self.eng
         self._unstage()
-        logits, loss = eng.forward(self.d_ids, self.d_tt, self.d_mask, self.d_lab, training=True, need_backward=True)
-        ws = eng.workspace(self.B, self.S)
-        B, S, mask, p_h, p_a, p_c, packed = eng._saved
-        eng._saved = None
-        # d(loss)/d(logits) was produced by the CE kernel: the reference's criterion(logits, label) [:169]
-        eng._backward_from_dlogits(ws["dloss_logits"], B, S, mask, p_h, p_a, p_c, packed)
-        self.opt.step()
-        self.loss_out.copy_(loss)
+        self._train_body(lambda ev: self.eng.forward(self.d_ids, self.d_tt, self.d_mask, self.d_lab, training=True,
+                                                     need_backward=True, weight_events=ev))
 
     def __call__(self, batch_data):
         """batch_data: the dict the reference Collate yields (host int64 tensors).  Returns the device loss scalar
@@ -195,6 +207,7 @@ class PackedTrainStep(_StagedGraphStep):
         self.d_seg = torch.zeros(bins, 128, dtype=torch.int32, device=dev)
         self.opt = optimizer
         optimizer._armed = True
+        optimizer.enable_pipelining()
 
     def _unstage(self):
         n, st = self.bins * 128, self.d_stage
@@ -222,17 +235,10 @@ class PackedTrainStep(_StagedGraphStep):
         self._h2d_done.record(torch.cuda.current_stream(self.eng.dev))
 
     def _body(self):
-        eng = self.eng
         self._unstage()
         packed = (self.d_pos, self.d_seg, self.d_cls)
-        logits, loss = eng.forward(self.d_ids, self.d_tt, None, self.d_lab, training=True, need_backward=True,
-                                   packed=packed)
-        ws = eng.workspace(self.bins, 128, self.batch)
-        B, S, mask, p_h, p_a, p_c, pk = eng._saved
-        eng._saved = None
-        eng._backward_from_dlogits(ws["dloss_logits"], B, S, mask, p_h, p_a, p_c, pk)
-        self.opt.step()
-        self.loss_out.copy_(loss)
+        self._train_body(lambda ev: self.eng.forward(self.d_ids, self.d_tt, None, self.d_lab, training=True,
+                                                     need_backward=True, packed=packed, weight_events=ev))
 
     def __call__(self, packed, label):
         self.stage(packed, label)
@@ -257,6 +263,8 @@ class FusedEvalStep(_StagedGraphStep):
         self.loss_out.copy_(loss)
 
     def __call__(self, batch_data):
+        if self.model._optimizer is not None:
+            self.model._optimizer.flush_pending()     # a pipelined train step may still owe its update
         self.stage(batch_data)
         self.run_device()
         return self.logits_out, self.d_lab, self.loss_out
