@@ -907,6 +907,14 @@ class _Engine:
                            L.ptr(opt._state()["step"]), ss)
                 else:
                     self.gemm_grouped(wgrads, ss)
+            # fp32 accumulators -> bf16 bias gradients of this layer (and re-arm them); for S != 128 the QKV segment's
+            # accumulator is unused (zero) and must not overwrite the colsum result: finish only the intermediate one.
+            # Every kernel that adds into this layer's accumulators is behind the fork() above, and only the optimizer /
+            # exchange reads the result: the launch rides the weight-gradient stream, off the critical path.
+            spl = self.segs_per_layer
+            seg0 = spl * l if S == 128 else spl * l + 1
+            L.call("b2_accum_finish", self.bias_acc.data_ptr(), self.grads.data_ptr(),
+                   self.bias_segs.data_ptr() + 24 * seg0, spl * (l + 1) - seg0, max(3 * H, I), ss)
             if side is not main:
                 done[l] = torch.cuda.Event()
                 done[l].record(side)
@@ -916,12 +924,6 @@ class _Engine:
             else:
                 self.gemm(M, H, 3 * H, dqkv.data_ptr(), 3 * H, KM, w(pre + "attention.self.query.weight"), H, MN,
                           dx.data_ptr(), H, L.EPI_RESIDUAL_F32, aux_in=ws["dz1"].data_ptr(), ld_aux_in=H)
-            # fp32 accumulators -> bf16 bias gradients of this layer (and re-arm them); for S != 128 the QKV segment's
-            # accumulator is unused (zero) and must not overwrite the colsum result: finish only the intermediate one
-            spl = self.segs_per_layer
-            seg0 = spl * l if S == 128 else spl * l + 1
-            L.call("b2_accum_finish", self.bias_acc.data_ptr(), self.grads.data_ptr(),
-                   self.bias_segs.data_ptr() + 24 * seg0, spl * (l + 1) - seg0, max(3 * H, I), s)
             bucket_ready(1 + l, done.get(l))   # complete only with this layer's weight gradients
         emb_in = (dx.data_ptr(), 1, ws["emb_pre"].data_ptr(), ws["emb_mean"].data_ptr(), ws["emb_rstd"].data_ptr(),
                   w("bert.embeddings.LayerNorm.weight"), ws["ids32"].data_ptr(), ws["tt32"].data_ptr())
