@@ -119,6 +119,12 @@ class _StagedGraphStep:
 
     def run_device(self):
         """The step with inputs already staged on the device (bench `value` path)."""
+        self._run_device()
+        opt = getattr(self, "opt", None)
+        if opt is not None and opt._pipelined:
+            opt._deferred_pending = True      # (a graph replay runs no Python: keep the host-side flag current)
+
+    def _run_device(self):
         if not self.use_graph:
             self._run_body()
             return
