@@ -461,9 +461,11 @@ class _Engine:
         # optimizer-state round trips (one 4 KB staging tile per warp) keep too few bytes in flight; see DESIGN.md 4.3
         self.fused_adamw = os.environ.get("B2_FUSED_ADAMW", "0") == "1"
         self.fused_adamw_active = False
-        # cache of the forward's attention-dropout decisions for the backward: measured neutral (3.96 vs 3.95 ms/step --
-        # the backward is latency-, not Philox-bound), so off by default; the kernels and tests keep the path alive
-        self.attn_keep_bits = os.environ.get("B2_ATTN_KEEP_BITS", "0") == "1"
+        # cache of the forward's attention-dropout decisions for the backward (1 bit per (b, h, q, k), bit-exact against
+        # the Philox replica): neutral in round 1 (3.96 vs 3.95 ms/step), +1.4 % now that the step body runs on a
+        # high-priority stream (8 232 vs 8 117 samples/s, two A/B pairs in one run) -> on by default, B2_ATTN_KEEP_BITS=0
+        # regenerates the masks in the backward instead
+        self.attn_keep_bits = os.environ.get("B2_ATTN_KEEP_BITS", "1") != "0"
         self.use_wgrad_stream = os.environ.get("B2_WGRAD_STREAM", "1") != "0"
         # dense + bias + dropout + residual + LayerNorm as ONE cluster kernel (b2_gemm_ln_fwd) for the two N = hidden
         # GEMMs of a layer, when the hidden size has a row-cluster tiling (768, 1024) and the device can co-schedule
