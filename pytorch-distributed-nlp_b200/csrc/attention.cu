@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_fwd_kernel(const __grid
                                                                    const __grid_constant__ CUtensorMap tmap_ctx,
                                                                    const AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_align_1024(smem_raw);
   uint8_t* sQ = smem;
   uint8_t* sK = smem + TILE_BYTES;
   uint8_t* sV = smem + 2 * TILE_BYTES;
@@ -300,7 +300,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 4) attention_fwd128_kernel(const 
                                                                          const __grid_constant__ CUtensorMap tmap_ctx,
                                                                          const AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_align_1024(smem_raw);
   uint8_t* sQ = smem;                      // later: keys 0-63 of P
   uint8_t* sK = smem + TILE_BYTES;         // later: keys 64-127 of P
   uint8_t* sV = smem + 2 * TILE_BYTES;     // later: the context tile on its way out
@@ -502,7 +502,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_
   // kOneQ has no room for alignment slack: the dynamic window of a kernel without static shared memory starts
   // 1024-aligned (checked below, loudly)
   uint8_t* smem = kOneQ ? smem_raw
-                        : reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+                        : smem_align_1024(smem_raw);
   constexpr int kTiles = kOneQ ? 7 : 8;
   constexpr uint32_t kTmemCols = kOneQ ? 256 : 512;
   uint8_t* sK = smem;

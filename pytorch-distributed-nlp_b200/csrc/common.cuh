@@ -68,6 +68,13 @@ inline void launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
+// First 1024-byte boundary inside a dynamic shared-memory window (TMA / UMMA 128-byte-swizzle tiles).  Written as
+// `base + offset` -- NOT as a round trip through uintptr_t -- so that every pointer derived from the result is still
+// known to the compiler to be SHARED: the cast form degraded each staging-tile access of the epilogues to a generic
+// LD.E / ST.E (address-space check, L1 tag stage, and a memory barrier that must wait for them) instead of LDS / STS.
+__device__ __forceinline__ uint8_t* smem_align_1024(uint8_t* smem_raw) {
+  return smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+}
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }
 
 __device__ __forceinline__ float warp_sum(float v) {

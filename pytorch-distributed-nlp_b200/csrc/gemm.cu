@@ -58,7 +58,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                  const GemmKernelParams p) {
   using Cfg = GemmCfg<BN, EW>;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_align_1024(smem_raw);
   uint8_t* epi_stage = smem + Cfg::kPipeBytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_stage + EW * kEpiStageBytes);
   uint64_t* empty_bar = full_bar + Cfg::kStages;
@@ -214,7 +214,7 @@ gemm2_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                   const GemmKernelParams p) {
   using Cfg = Gemm2Cfg<BN, EW>;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_align_1024(smem_raw);
   uint8_t* epi_stage = smem + Cfg::kPipeBytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_stage + EW * kEpiStageBytes);
   uint64_t* empty_bar = full_bar + Cfg::kStages;
@@ -511,7 +511,7 @@ gemm2_grouped_tn_kernel(const __grid_constant__ GroupedMaps maps, const GroupedP
   constexpr int BN = 256;
   using Cfg = Gemm2Cfg<BN, EW>;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_align_1024(smem_raw);
   uint8_t* epi_stage = smem + Cfg::kPipeBytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_stage + EW * kEpiStageBytes);
   uint64_t* empty_bar = full_bar + Cfg::kStages;

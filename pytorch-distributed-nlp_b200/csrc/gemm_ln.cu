@@ -21,6 +21,8 @@
 //   warp 0   TMA producer (this CTA's 128 A rows + its half of the pair's B tile; completion credited to the pair
 //            leader's mbarrier)          warp 1   MMA issuer (pair leader only)         warp 2   TMEM allocator
 //   warps 4-19  epilogue, warp -> (TMEM lane quarter, column group of 64), thread -> one row:
+//     under the mainloop: the warp's fp32 residual tile arrives by TMA, and every thread draws the Philox keep bits of
+//             its 64 elements (they do not depend on the accumulator: ~850 instructions per thread off the tail)
 //     pass 1  z = (acc + bias -> dropout) + residual in fp32, kept in shared memory (the residual tile is overwritten
 //             in place); bf16(z) stored to D for the backward; per-row partial statistics over the warp's 64 columns
 //             (mean, M2 = sum (z - mean)^2) written into the `stats` pad of every CTA that holds the same rows --
@@ -29,6 +31,11 @@
 //     pass 2  every thread merges the 4 PAIRS partials of its row (Chan's parallel-variance formula: exact two-pass
 //             statistics, no E[x^2] - mean^2 cancellation), normalises its staged z in place, stores y as bf16 and fp32;
 //             mean / rstd (fp32, what the LayerNorm backward reads) are written by the first pair's first column group
+//   Every tile that crosses the SM boundary in the epilogue (fp32 residual in; bf16 z, bf16 y, fp32 y out) is one TMA
+//   box of 32 rows x 128 bytes issued by one lane, in the 128-byte swizzle stage_ptr<8> already uses (an fp32 [M, N]
+//   tensor is described to TMA as bf16 [M, 2N]).  The per-lane cp.async / ld.shared + st.global copies they replace
+//   were ~1 700 of the ~4 200 instructions an epilogue warp issued (ncu, profiles/r02_gemm_ln_epilogue.md), on a
+//   kernel whose tail is issue-bound: four epilogue warps per scheduler.
 #include "common.cuh"
 #include "gemm_epilogue.cuh"
 #include "pair.cuh"
@@ -54,7 +61,7 @@ struct GemmLnCfg {
   static constexpr int kTmemCols = 256;
   static constexpr int kPipeBytes = kStages * kStageBytes;     // 128 KB: after the last MMA, 8 KB of epilogue scratch per warp
   static constexpr int kStatsBytes = 4 * PAIRS * kLnBM * 8;    // [pair][column group][row] float2
-  static constexpr int kSmemBytes = kPipeBytes + kLnEW * kEpiStageBytes + kStatsBytes + 1024 /*align*/ + 256;
+  static constexpr int kSmemBytes = kPipeBytes + kLnEW * kEpiStageBytes + kStatsBytes + 1024 /*align*/ + 512;
   static_assert(kPipeBytes >= kLnEW * 2 * kEpiStageBytes, "epilogue scratch lives in the drained operand ring");
 };
 
@@ -68,32 +75,42 @@ struct GemmLnParams {
   __nv_bfloat16* Y; long long ldy;                 // LayerNorm output, bf16 [M, N]: the next GEMM's operand
   float* Yf; long long ldyf;                       // LayerNorm output, fp32 [M, N]: the next block's residual (or null)
   float* mean; float* rstd;                        // fp32 [M]
+  long long* timing;                               // optional [gridDim.x][8] clock64 stamps of the first epilogue warp
 };
+__device__ __forceinline__ void ln_stamp(const GemmLnParams& p, int slot) {
+  if (p.timing != nullptr) p.timing[(size_t)blockIdx.x * 8 + slot] = clock64();
+}
 
 __device__ __forceinline__ void unpack8(const uint4& t, float (&f)[8]) {
   f[0] = bf16_lo(t.x); f[1] = bf16_hi(t.x); f[2] = bf16_lo(t.y); f[3] = bf16_hi(t.y);
   f[4] = bf16_lo(t.z); f[5] = bf16_hi(t.z); f[6] = bf16_lo(t.w); f[7] = bf16_hi(t.w);
 }
-__device__ __forceinline__ void cp_async_wait_1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
 
 template <int PAIRS>
 __global__ void __cluster_dims__(2 * PAIRS, 1, 1) __launch_bounds__(gemm_ln_threads<PAIRS>())
     __maxnreg__(PAIRS > 0 ? 96 : 64)
 gemm_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+               const __grid_constant__ CUtensorMap tmap_r /* fp32 residual */,
+               const __grid_constant__ CUtensorMap tmap_d /* bf16 z */,
+               const __grid_constant__ CUtensorMap tmap_y /* bf16 y */,
+               const __grid_constant__ CUtensorMap tmap_yf /* fp32 y (unused when p.Yf is null) */,
                const GemmLnParams p) {
   using Cfg = GemmLnCfg<PAIRS>;
   constexpr int BN = kLnBN;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_align_1024(smem_raw);
   uint8_t* epi_stage = smem + Cfg::kPipeBytes;
   float2* stats = reinterpret_cast<float2*>(epi_stage + kLnEW * kEpiStageBytes);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(stats) + Cfg::kStatsBytes);
   uint64_t* empty_bar = full_bar + Cfg::kStages;
   uint64_t* tmem_full = empty_bar + Cfg::kStages;
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tmem_full + 1);
+  uint64_t* res_bar = tmem_full + 1;                  // [epilogue warp][residual half]: TMA completion
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(res_bar + 2 * kLnEW);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const bool stamper = warp == 4 && lane == 0;        // profiling aid (tools/gemm_ln_probe.py --timeline)
+  if (stamper) ln_stamp(p, 0);                        // 0: kernel entry
   const uint32_t rank = cluster_ctarank();            // 0 .. 2 PAIRS - 1
   const uint32_t parity = rank & 1u;                  // which 128 of the pair's 256 rows
   const uint32_t lead_rank = rank & ~1u;              // the pair's leader CTA
@@ -106,6 +123,10 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
+    tma_prefetch_desc(&tmap_r);
+    tma_prefetch_desc(&tmap_d);
+    tma_prefetch_desc(&tmap_y);
+    tma_prefetch_desc(&tmap_yf);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < Cfg::kStages; ++s) {
@@ -113,6 +134,7 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       mbar_init(&empty_bar[s], 1);
     }
     mbar_init(tmem_full, 1);
+    for (int i = 0; i < 2 * kLnEW; ++i) mbar_init(&res_bar[i], 1);
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc_2sm(tmem_holder, Cfg::kTmemCols);
@@ -123,6 +145,7 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   // PDL: nothing above touches global data
   pdl_wait();
   pdl_launch_dependents();
+  if (stamper) ln_stamp(p, 1);                        // 1: barriers + TMEM set up, cluster running, predecessor done
 
   if (warp == 0) {
     // ------------------------------ TMA producer (every CTA) ------------------------------
@@ -137,6 +160,22 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         uint8_t* sb = sa + Cfg::kABytes;
         tma_load_2d_2sm(sa, &tmap_a, bar, kb * kLnBK, m0);     // box {64 k, 128 rows}
         tma_load_2d_2sm(sb, &tmap_b, bar, kb * kLnBK, nb);     // box {64 k, 128 rows}
+        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
+      }
+      // The two ring stages the MMAs release first (those of k-blocks kblocks-4 and kblocks-3) take the second
+      // residual halves of the 16 epilogue warps while the last MMAs still run: issued by the epilogue warps
+      // themselves once the accumulator is complete, these 64 KB of TMA traffic sat in front of pass 1.
+      for (int t = 0; t < 2; ++t) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        for (int e = 8 * t; e < 8 * t + 8; ++e) {      // epilogue warp e: rows q = e & 3, column group e >> 2
+          const int erow0 = m0 + (e & 3) * 32;
+          if (erow0 < p.M) {
+            uint64_t* rb = &res_bar[2 * e + 1];
+            mbar_expect_tx(rb, kEpiStageBytes);
+            tma_load_2d(smem + stage * Cfg::kStageBytes + (e & 7) * kEpiStageBytes, &tmap_r, rb,
+                        2 * (n_tile + (e >> 2) * (BN / 4) + 32), erow0);
+          }
+        }
         if (++stage == Cfg::kStages) { stage = 0; phase ^= 1; }
       }
     }
@@ -166,12 +205,14 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     //   zA, zB  fp32, columns [0, 32) / [32, 64) of the warp's block: residual in -> z (fp32, unrounded) -> y (fp32)
     //   hb      bf16, all 64 columns: z on its way to D, then y on its way to Y
     // zA is the warp's dedicated staging tile (its residual arrives under the mainloop); zB and hb live in the operand
+    // ring: zB in the two stages released first (filled by the producer warp, above), hb in the two released last;
     // ring, which is dead once the accumulator barrier has fired (all MMAs complete, every TMA write consumed).
     constexpr int CW = BN / 4;          // 64 columns per warp
     const DropCtx drop = make_drop_ctx(p.rng, p.rng_site, p.dropout_p);
     uint8_t* zA = epi_stage + (warp - 4) * kEpiStageBytes;
-    uint8_t* zB = smem + (warp - 4) * (2 * kEpiStageBytes);
-    uint8_t* hb = zB + kEpiStageBytes;
+    const int ew = warp - 4;
+    uint8_t* zB = smem + ((p.kblocks + (ew >> 3)) % Cfg::kStages) * Cfg::kStageBytes + (ew & 7) * kEpiStageBytes;
+    uint8_t* hb = smem + ((p.kblocks + 2 + (ew >> 3)) % Cfg::kStages) * Cfg::kStageBytes + (ew & 7) * kEpiStageBytes;
     const int q = warp & 3, cg = (warp - 4) >> 2;
     const int row_l = q * 32 + lane;                  // row inside this CTA's 128
     const int row0 = m0 + q * 32;
@@ -179,32 +220,45 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const int m = row0 + lane;
     const int nw = n_tile + cg * CW;
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cg * CW);
-    const float* rsrc = p.resid + (size_t)row0 * p.ld_resid + nw;
+    const bool active = rows_valid > 0;               // warp-uniform; an inactive warp computes on stale tiles, stores nothing
+    uint64_t* rbarA = &res_bar[2 * (warp - 4)];
+    uint64_t* rbarB = rbarA + 1;
 
-    tile_g2s_async<8>(zA, reinterpret_cast<const uint8_t*>(rsrc), p.ld_resid * 4, lane, rows_valid);
+    if (lane == 0 && active) {                        // residual columns [nw, nw + 32): rows past M arrive as zeros
+      mbar_expect_tx(rbarA, kEpiStageBytes);
+      tma_load_2d(zA, &tmap_r, rbarA, 2 * nw, row0);
+    }
+    // dropout decisions of this thread's 64 elements, drawn while the mainloop runs: bit 8 k + i of keep_lo (k < 4) /
+    // keep_hi (k >= 4) <=> element nw + 8 k + i of row m is kept
+    uint32_t keep_lo = 0, keep_hi = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      keep_lo |= dropout_keep8(drop, (unsigned long long)m * p.N + nw + 8 * k) << (8 * k);
+      keep_hi |= dropout_keep8(drop, (unsigned long long)m * p.N + nw + 32 + 8 * k) << (8 * k);
+    }
     mbar_wait(tmem_full, 0);
     tc_fence_after();
-    tile_g2s_async<8>(zB, reinterpret_cast<const uint8_t*>(rsrc + 32), p.ld_resid * 4, lane, rows_valid);
+    if (stamper) ln_stamp(p, 2);                      // 2: accumulator complete
     float sum = 0.f;
-#pragma unroll 1
+    uint32_t vv[2][16];                 // accumulator columns of step j / j + 1: the next load flies under the math
+    tmem_ld16(taddr, vv[0]);
+#pragma unroll
     for (int j = 0; j < CW / 16; ++j) {
-      uint32_t v[16];
-      tmem_ld16(taddr + j * 16, v);
       tmem_ld_wait();
-      if (j == 0) {
-        cp_async_wait_1();      // the first residual half has landed
-        __syncwarp();
-      } else if (j == 2) {
-        tile_async_wait();      // ... and the second
-        __syncwarp();
+      if (j + 1 < CW / 16) tmem_ld16(taddr + (j + 1) * 16, vv[(j + 1) & 1]);
+      const uint32_t (&v)[16] = vv[j & 1];
+      if (active) {
+        if (j == 0) mbar_wait(rbarA, 0);        // the first residual half has landed
+        else if (j == 2) mbar_wait(rbarB, 0);   // ... and the second
       }
       uint8_t* zt = j < 2 ? zA : zB;
+      const uint32_t keep_j = (j < 2 ? keep_lo : keep_hi) >> ((j & 1) * 16);
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         const int col = nw + j * 16 + c * 8;
         float f[8], b8[8];
         unpack8(ldg16(p.bias + col), b8);
-        const uint32_t keep = dropout_keep8(drop, (unsigned long long)m * p.N + col);
+        const uint32_t keep = keep_j >> (c * 8);
         uint4* r0 = stage_ptr<8>(zt, lane, ((j & 1) * 2 + c) * 2);         // 4 fp32 columns per 16-byte chunk
         uint4* r1 = stage_ptr<8>(zt, lane, ((j & 1) * 2 + c) * 2 + 1);
         const uint4 ra = *r0, rb = *r1;
@@ -238,11 +292,16 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 #pragma unroll
       for (int dp = 0; dp < PAIRS; ++dp) st_cluster_f32x2(mapa_u32(slot, (uint32_t)(2 * dp) + parity), mean_l, m2_l);
     }
+    fence_proxy_async_smem();          // this lane's staged bf16 z -> visible to the TMA engine
     __syncwarp();
-    tile_s2g<8>(hb, reinterpret_cast<uint8_t*>(p.D + (size_t)row0 * p.ldd + nw), p.ldd * 2, lane, rows_valid);
-    __syncwarp();
+    if (lane == 0 && active) {
+      tma_store_2d(&tmap_d, hb, nw, row0);             // rows past M are clipped by the hardware
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+    if (stamper) ln_stamp(p, 3);                      // 3: pass 1 done, partial statistics posted
     cluster_arrive_release();
     cluster_wait_acquire();
+    if (stamper) ln_stamp(p, 4);                      // 4: every partial of this row block has arrived
     // merge the 4 PAIRS partials of this row (equal counts CW): mean = avg(mean_i), M2 = sum M2_i + CW sum (mean_i - mean)^2
     float mean = 0.f;
 #pragma unroll
@@ -256,8 +315,18 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       m2 += t.y + (float)CW * d * d;
     }
     const float rstd = rsqrtf(m2 / (float)p.N + p.eps);
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // hb has been read out (z -> D)
+    __syncwarp();
 #pragma unroll 1
     for (int c = 0; c < 8; ++c) {          // 8 columns per step: two fp32 chunks, one bf16 chunk
+      if (c == 4) {                        // first fp32 half finished: on its way while the second is normalised
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0 && active && p.Yf != nullptr) {
+          tma_store_2d(&tmap_yf, zA, 2 * nw, row0);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+      }
       const int col = nw + c * 8;
       uint8_t* zt = c < 4 ? zA : zB;
       float g[8], b[8];
@@ -276,17 +345,23 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       o.x = pack_bf16(f[0], f[1]); o.y = pack_bf16(f[2], f[3]); o.z = pack_bf16(f[4], f[5]); o.w = pack_bf16(f[6], f[7]);
       *stage_ptr<8>(hb, lane, c) = o;
     }
+    fence_proxy_async_smem();
     __syncwarp();
-    tile_s2g<8>(hb, reinterpret_cast<uint8_t*>(p.Y + (size_t)row0 * p.ldy + nw), p.ldy * 2, lane, rows_valid);
-    if (p.Yf != nullptr) {
-      float* ydst = p.Yf + (size_t)row0 * p.ldyf + nw;
-      tile_s2g<8>(zA, reinterpret_cast<uint8_t*>(ydst), p.ldyf * 4, lane, rows_valid);
-      tile_s2g<8>(zB, reinterpret_cast<uint8_t*>(ydst + 32), p.ldyf * 4, lane, rows_valid);
-    }
+    if (stamper) ln_stamp(p, 5);                      // 5: pass 2 done
     if (pair == 0 && cg == 0 && lane < rows_valid) {
       p.mean[m] = mean;
       p.rstd[m] = rstd;
     }
+    if (lane == 0 && active) {
+      tma_store_2d(&tmap_y, hb, nw, row0);
+      if (p.Yf != nullptr) tma_store_2d(&tmap_yf, zB, 2 * (nw + 32), row0);
+      // the tiles stay put until the engine has read them; the writes themselves complete with the grid (what the next
+      // kernel's griddepcontrol.wait / stream order observes), as with plain st.global
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    }
+    __syncwarp();
+    if (stamper) ln_stamp(p, 6);                      // 6: output tiles written
   }
   if (warp < 4) {
     // the statistics barrier counts every thread of the cluster
@@ -299,6 +374,7 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   tc_fence_before();
   __syncwarp();
   cluster_sync_all();
+  if (stamper) ln_stamp(p, 7);                        // 7: whole cluster drained
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc_2sm(tmem_base, Cfg::kTmemCols);
@@ -355,6 +431,20 @@ static int32_t launch_gemm_ln(const b2_gemm_args_t& a, const void* gamma, const 
   if (st) return st;
   st = get_tensor_map_2d(&tb, a.B, (uint64_t)a.N, (uint64_t)a.K, (uint64_t)a.ldb * 2, kLnBN / 2, 64);
   if (st) return st;
+  // epilogue tiles: boxes of 32 rows x 128 bytes (64 bf16 / 32 fp32 columns; fp32 tensors as bf16 [M, 2 N])
+  CUtensorMap tr, td, ty, tyf;
+  st = get_tensor_map_2d(&tr, a.aux_in, (uint64_t)a.M, (uint64_t)a.N * 2, (uint64_t)a.ld_aux_in * 4, 32, 64);
+  if (st) return st;
+  st = get_tensor_map_2d(&td, a.D, (uint64_t)a.M, (uint64_t)a.N, (uint64_t)a.ldd * 2, 32, 64);
+  if (st) return st;
+  st = get_tensor_map_2d(&ty, y, (uint64_t)a.M, (uint64_t)a.N, (uint64_t)ldy * 2, 32, 64);
+  if (st) return st;
+  if (y_f32 != nullptr) {
+    st = get_tensor_map_2d(&tyf, y_f32, (uint64_t)a.M, (uint64_t)a.N * 2, (uint64_t)ldyf * 4, 32, 64);
+    if (st) return st;
+  } else {
+    tyf = tr;
+  }
   GemmLnParams p;
   p.M = (int)a.M; p.N = (int)a.N; p.kblocks = (int)((a.K + kLnBK - 1) / kLnBK);
   p.D = (__nv_bfloat16*)a.D; p.ldd = a.ldd;
@@ -363,8 +453,9 @@ static int32_t launch_gemm_ln(const b2_gemm_args_t& a, const void* gamma, const 
   p.dropout_p = a.dropout_p; p.rng = (const unsigned long long*)a.rng_state; p.rng_site = a.rng_site;
   p.gamma = (const __nv_bfloat16*)gamma; p.beta = (const __nv_bfloat16*)beta; p.eps = eps;
   p.Y = (__nv_bfloat16*)y; p.ldy = ldy; p.Yf = y_f32; p.ldyf = ldyf; p.mean = mean; p.rstd = rstd;
+  p.timing = (long long*)a.debug_timing;
   const int row_blocks = (int)((a.M + 2 * kLnBM - 1) / (2 * kLnBM));
-  B2_LAUNCH(gemm_ln_kernel<PAIRS>, Cfg::kCluster * row_blocks, kLnThreads, Cfg::kSmemBytes, stream, ta, tb, p);
+  B2_LAUNCH(gemm_ln_kernel<PAIRS>, Cfg::kCluster * row_blocks, kLnThreads, Cfg::kSmemBytes, stream, ta, tb, tr, td, ty, tyf, p);
   B2_CUDA(cudaGetLastError());
   count_launches(1);
   return 0;

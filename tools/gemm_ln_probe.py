@@ -75,6 +75,43 @@ def probe(M, N, K, p=0.1):
           % (M, N, K, (M + 255) // 256, tf, fl / tf / 1e6, tg, tp, fl / tp / 1e6), flush=True)
 
 
+def timeline(M, N, K, p=0.1):
+    """clock64 stamps of the first epilogue warp of every CTA (b2_gemm_args_t.debug_timing), as phase durations"""
+    A, B = torch.randn(M, K, device=dev).to(bf), (torch.randn(N, K, device=dev) * 0.05).to(bf)
+    bias, Xf = torch.randn(N, device=dev).to(bf), torch.randn(M, N, device=dev)
+    Z, Y = torch.empty(M, N, dtype=bf, device=dev), torch.empty(M, N, dtype=bf, device=dev)
+    Yf, mean, rstd = torch.empty(M, N, device=dev), torch.empty(M, device=dev), torch.empty(M, device=dev)
+    gamma, beta = torch.ones(N, device=dev).to(bf), torch.zeros(N, device=dev).to(bf)
+    rng = torch.tensor([77, 3], dtype=torch.int64, device=dev)
+    ctas = ((M + 255) // 256) * 2 * (N // 256)
+    stamps = torch.zeros(ctas, 8, dtype=torch.int64, device=dev)
+    a = args(M, N, K, A, B, Z, bias, Xf, rng, p)
+    for it in range(3):
+        a.debug_timing = stamps.data_ptr() if it == 2 else None
+        L.call("b2_gemm_ln_fwd", a, gamma.data_ptr(), beta.data_ptr(), 1e-12, Y.data_ptr(), N, Yf.data_ptr(), N,
+               mean.data_ptr(), rstd.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+    t = stamps.cpu().double()
+    d = t[:, 1:] - t[:, :-1]
+    names = ["entry -> set up", "-> accumulator complete", "-> pass 1 done", "-> cluster barrier", "-> pass 2 done",
+             "-> tiles written", "-> cluster drained"]
+    print("M %d N %d K %d: %d CTAs, SM cycles (mean / max over CTAs)" % (M, N, K, ctas))
+    for i, n in enumerate(names):
+        print("   %-26s %8.0f %8.0f" % (n, float(d[:, i].mean()), float(d[:, i].max())))
+    print("   %-26s %8.0f %8.0f" % ("entry -> drained", float((t[:, 7] - t[:, 0]).mean()), float((t[:, 7] - t[:, 0]).max())),
+          flush=True)
+
+
+if len(sys.argv) > 1 and sys.argv[1] == "--timeline":
+    for spec in sys.argv[2:]:
+        M, N, K = (int(v) for v in spec.split("x"))
+        timeline(M, N, K)
+    sys.exit(0)
+if len(sys.argv) > 1:          # explicit shapes: MxNxK ...
+    for spec in sys.argv[1:]:
+        M, N, K = (int(v) for v in spec.split("x"))
+        probe(M, N, K)
+    sys.exit(0)
 for K in (768, 3072):
     for M in (256, 512, 1024, 2048, 3072, 3584, 4096, 4352, 8192):
         probe(M, 768, K)
