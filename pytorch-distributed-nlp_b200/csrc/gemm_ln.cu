@@ -27,7 +27,7 @@
 //             in place); bf16(z) stored to D for the backward; per-row partial statistics over the warp's 64 columns
 //             (mean, M2 = sum (z - mean)^2) written into the `stats` pad of every CTA that holds the same rows --
 //             distributed shared memory
-//     cluster barrier (arrive.release / wait.acquire)
+//     wait on the CTA's statistics barrier (st.async transaction bytes of all 4 PAIRS partials of its 128 rows)
 //     pass 2  every thread merges the 4 PAIRS partials of its row (Chan's parallel-variance formula: exact two-pass
 //             statistics, no E[x^2] - mean^2 cancellation), normalises its staged z in place, stores y as bf16 and fp32;
 //             mean / rstd (fp32, what the LayerNorm backward reads) are written by the first pair's first column group
@@ -105,7 +105,8 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   uint64_t* empty_bar = full_bar + Cfg::kStages;
   uint64_t* tmem_full = empty_bar + Cfg::kStages;
   uint64_t* res_bar = tmem_full + 1;                  // [epilogue warp][residual half]: TMA completion
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(res_bar + 2 * kLnEW);
+  uint64_t* stats_bar = res_bar + 2 * kLnEW;          // transaction barrier: all 4 PAIRS partials of every row are in
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(stats_bar + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -135,7 +136,10 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     }
     mbar_init(tmem_full, 1);
     for (int i = 0; i < 2 * kLnEW; ++i) mbar_init(&res_bar[i], 1);
+    mbar_init(stats_bar, 1);
     fence_mbar_init();
+    // armed before the opening cluster barrier, i.e. before any CTA of the cluster can post a partial
+    mbar_expect_tx(stats_bar, (uint32_t)Cfg::kStatsBytes);
   }
   if (warp == 2) tmem_alloc_2sm(tmem_holder, Cfg::kTmemCols);
   tc_fence_before();
@@ -267,7 +271,7 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           f[i] = __uint_as_float(v[c * 8 + i]) + b8[i];
-          f[i] = (((keep >> i) & 1u) ? f[i] * drop.scale : 0.f) + r[i];
+          f[i] = ((keep >> i) & 1u) ? fmaf(f[i], drop.scale, r[i]) : r[i];
           sum += f[i];
         }
         *r0 = make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]), __float_as_uint(f[3]));
@@ -290,7 +294,17 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     {
       const uint32_t slot = smem_u32(&stats[(pair * 4 + cg) * kLnBM + row_l]);
 #pragma unroll
-      for (int dp = 0; dp < PAIRS; ++dp) st_cluster_f32x2(mapa_u32(slot, (uint32_t)(2 * dp) + parity), mean_l, m2_l);
+      const uint32_t sbar = smem_u32(stats_bar);
+      // st.async: the 8 bytes and their complete_tx on the receiver's barrier travel together -- no release fence (a
+      // MEMBAR.ALL.GPU under barrier.cluster.arrive.release) and no cluster-wide barrier in the middle of the epilogue
+#pragma unroll
+      for (int dp = 0; dp < PAIRS; ++dp) {
+        const uint32_t dst = (uint32_t)(2 * dp) + parity;
+        asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f32 [%0], {%1, %2}, [%3];" ::"r"(
+                         mapa_u32(slot, dst)),
+                     "f"(mean_l), "f"(m2_l), "r"(mapa_u32(sbar, dst))
+                     : "memory");
+      }
     }
     fence_proxy_async_smem();          // this lane's staged bf16 z -> visible to the TMA engine
     __syncwarp();
@@ -299,8 +313,7 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     }
     if (stamper) ln_stamp(p, 3);                      // 3: pass 1 done, partial statistics posted
-    cluster_arrive_release();
-    cluster_wait_acquire();
+    mbar_wait(stats_bar, 0);
     if (stamper) ln_stamp(p, 4);                      // 4: every partial of this row block has arrived
     // merge the 4 PAIRS partials of this row (equal counts CW): mean = avg(mean_i), M2 = sum M2_i + CW sum (mean_i - mean)^2
     float mean = 0.f;
@@ -315,6 +328,7 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       m2 += t.y + (float)CW * d * d;
     }
     const float rstd = rsqrtf(m2 / (float)p.N + p.eps);
+    const float nmr = -mean * rstd;
     if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // hb has been read out (z -> D)
     __syncwarp();
 #pragma unroll 1
@@ -338,7 +352,7 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       float f[8] = {__uint_as_float(ra.x), __uint_as_float(ra.y), __uint_as_float(ra.z), __uint_as_float(ra.w),
                     __uint_as_float(rb.x), __uint_as_float(rb.y), __uint_as_float(rb.z), __uint_as_float(rb.w)};
 #pragma unroll
-      for (int i = 0; i < 8; ++i) f[i] = (f[i] - mean) * rstd * g[i] + b[i];
+      for (int i = 0; i < 8; ++i) f[i] = fmaf(fmaf(f[i], rstd, nmr), g[i], b[i]);
       *r0 = make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]), __float_as_uint(f[3]));
       *r1 = make_uint4(__float_as_uint(f[4]), __float_as_uint(f[5]), __float_as_uint(f[6]), __float_as_uint(f[7]));
       uint4 o;
@@ -363,13 +377,6 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     __syncwarp();
     if (stamper) ln_stamp(p, 6);                      // 6: output tiles written
   }
-  if (warp < 4) {
-    // the statistics barrier counts every thread of the cluster
-    __syncwarp();
-    cluster_arrive_release();
-    cluster_wait_acquire();
-  }
-
   // no CTA may exit (or free TMEM) while a partner can still multicast-commit into it or write its stats pad
   tc_fence_before();
   __syncwarp();
