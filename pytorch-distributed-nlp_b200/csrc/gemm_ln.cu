@@ -61,7 +61,8 @@ struct GemmLnCfg {
   static constexpr int kTmemCols = 256;
   static constexpr int kPipeBytes = kStages * kStageBytes;     // 128 KB: after the last MMA, 8 KB of epilogue scratch per warp
   static constexpr int kStatsBytes = 4 * PAIRS * kLnBM * 8;    // [pair][column group][row] float2
-  static constexpr int kSmemBytes = kPipeBytes + kLnEW * kEpiStageBytes + kStatsBytes + 1024 /*align*/ + 512;
+  static constexpr int kParamBytes = kLnEW * 3 * 64 * 4;       // per epilogue warp: bias, gamma, beta of its 64 columns, fp32
+  static constexpr int kSmemBytes = kPipeBytes + kLnEW * kEpiStageBytes + kStatsBytes + kParamBytes + 1024 /*align*/ + 512;
   static_assert(kPipeBytes >= kLnEW * 2 * kEpiStageBytes, "epilogue scratch lives in the drained operand ring");
 };
 
@@ -101,7 +102,8 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   uint8_t* smem = smem_align_1024(smem_raw);
   uint8_t* epi_stage = smem + Cfg::kPipeBytes;
   float2* stats = reinterpret_cast<float2*>(epi_stage + kLnEW * kEpiStageBytes);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(stats) + Cfg::kStatsBytes);
+  float* ptab_all = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(stats) + Cfg::kStatsBytes);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(ptab_all) + Cfg::kParamBytes);
   uint64_t* empty_bar = full_bar + Cfg::kStages;
   uint64_t* tmem_full = empty_bar + Cfg::kStages;
   uint64_t* res_bar = tmem_full + 1;                  // [epilogue warp][residual half]: TMA completion
@@ -232,6 +234,18 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       mbar_expect_tx(rbarA, kEpiStageBytes);
       tma_load_2d(zA, &tmap_r, rbarA, 2 * nw, row0);
     }
+    // bias / gamma / beta of the warp's 64 columns, widened to fp32 once per warp (every lane needs the same values:
+    // 2 broadcast LDS.128 per 8 columns instead of an LDG and 8 unpacks, in the two passes that bound this kernel)
+    float* ptab = ptab_all + ew * (3 * 64);
+    {
+      const uint32_t tb = *reinterpret_cast<const uint32_t*>(p.bias + nw + 2 * lane);
+      const uint32_t tg = *reinterpret_cast<const uint32_t*>(p.gamma + nw + 2 * lane);
+      const uint32_t te = *reinterpret_cast<const uint32_t*>(p.beta + nw + 2 * lane);
+      *reinterpret_cast<float2*>(ptab + 2 * lane) = make_float2(bf16_lo(tb), bf16_hi(tb));
+      *reinterpret_cast<float2*>(ptab + 64 + 2 * lane) = make_float2(bf16_lo(tg), bf16_hi(tg));
+      *reinterpret_cast<float2*>(ptab + 128 + 2 * lane) = make_float2(bf16_lo(te), bf16_hi(te));
+    }
+    __syncwarp();
     // dropout decisions of this thread's 64 elements, drawn while the mainloop runs: bit 8 k + i of keep_lo (k < 4) /
     // keep_hi (k >= 4) <=> element nw + 8 k + i of row m is kept
     uint32_t keep_lo = 0, keep_hi = 0;
@@ -260,8 +274,10 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         const int col = nw + j * 16 + c * 8;
-        float f[8], b8[8];
-        unpack8(ldg16(p.bias + col), b8);
+        float f[8];
+        const float4 bl = *reinterpret_cast<const float4*>(ptab + j * 16 + c * 8);
+        const float4 bh = *reinterpret_cast<const float4*>(ptab + j * 16 + c * 8 + 4);
+        const float b8[8] = {bl.x, bl.y, bl.z, bl.w, bh.x, bh.y, bh.z, bh.w};
         const uint32_t keep = keep_j >> (c * 8);
         uint4* r0 = stage_ptr<8>(zt, lane, ((j & 1) * 2 + c) * 2);         // 4 fp32 columns per 16-byte chunk
         uint4* r1 = stage_ptr<8>(zt, lane, ((j & 1) * 2 + c) * 2 + 1);
@@ -343,9 +359,12 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       }
       const int col = nw + c * 8;
       uint8_t* zt = c < 4 ? zA : zB;
-      float g[8], b[8];
-      unpack8(ldg16(p.gamma + col), g);
-      unpack8(ldg16(p.beta + col), b);
+      const float4 gl = *reinterpret_cast<const float4*>(ptab + 64 + c * 8);
+      const float4 gh = *reinterpret_cast<const float4*>(ptab + 64 + c * 8 + 4);
+      const float4 el = *reinterpret_cast<const float4*>(ptab + 128 + c * 8);
+      const float4 eh = *reinterpret_cast<const float4*>(ptab + 128 + c * 8 + 4);
+      const float g[8] = {gl.x, gl.y, gl.z, gl.w, gh.x, gh.y, gh.z, gh.w};
+      const float b[8] = {el.x, el.y, el.z, el.w, eh.x, eh.y, eh.z, eh.w};
       uint4* r0 = stage_ptr<8>(zt, lane, (c & 3) * 2);
       uint4* r1 = stage_ptr<8>(zt, lane, (c & 3) * 2 + 1);
       const uint4 ra = *r0, rb = *r1;
@@ -372,15 +391,24 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       // the tiles stay put until the engine has read them; the writes themselves complete with the grid (what the next
       // kernel's griddepcontrol.wait / stream order observes), as with plain st.global
       asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     }
+    // closing cluster barrier, split around the TMA drain: it carries no data (every st.async this CTA is owed has
+    // landed before pass 2, every commit before that) -- it only keeps each CTA's shared memory and TMEM alive while a
+    // partner may still touch them, so the arrive needs no release fence and its latency overlaps the tile reads
+    tc_fence_before();
     __syncwarp();
-    if (stamper) ln_stamp(p, 6);                      // 6: output tiles written
+    asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
+    if (lane == 0 && active) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    __syncwarp();
+    if (stamper) ln_stamp(p, 6);                      // 6: output tiles read out of shared memory
+  }
+  if (warp < 4) {      // producer, MMA issuer, allocator, spare: straight to the closing barrier
+    tc_fence_before();
+    __syncwarp();
+    asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
   }
   // no CTA may exit (or free TMEM) while a partner can still multicast-commit into it or write its stats pad
-  tc_fence_before();
-  __syncwarp();
-  cluster_sync_all();
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
   if (stamper) ln_stamp(p, 7);                        // 7: whole cluster drained
   if (warp == 2) {
     tc_fence_after();
