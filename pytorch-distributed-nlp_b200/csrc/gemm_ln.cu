@@ -287,7 +287,9 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           f[i] = __uint_as_float(v[c * 8 + i]) + b8[i];
-          f[i] = ((keep >> i) & 1u) ? fmaf(f[i], drop.scale, r[i]) : r[i];
+          // (two roundings, as the unfused reference sequence dropout(...) + residual; an FFMA here moves the noisy
+          // query / key gradient norms of bert-large's last layers by more than a percent against the fixture)
+          f[i] = (((keep >> i) & 1u) ? f[i] * drop.scale : 0.f) + r[i];
           sum += f[i];
         }
         *r0 = make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]), __float_as_uint(f[3]));
@@ -344,7 +346,6 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       m2 += t.y + (float)CW * d * d;
     }
     const float rstd = rsqrtf(m2 / (float)p.N + p.eps);
-    const float nmr = -mean * rstd;
     if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // hb has been read out (z -> D)
     __syncwarp();
 #pragma unroll 1
@@ -371,7 +372,7 @@ gemm_ln_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       float f[8] = {__uint_as_float(ra.x), __uint_as_float(ra.y), __uint_as_float(ra.z), __uint_as_float(ra.w),
                     __uint_as_float(rb.x), __uint_as_float(rb.y), __uint_as_float(rb.z), __uint_as_float(rb.w)};
 #pragma unroll
-      for (int i = 0; i < 8; ++i) f[i] = fmaf(fmaf(f[i], rstd, nmr), g[i], b[i]);
+      for (int i = 0; i < 8; ++i) f[i] = (f[i] - mean) * rstd * g[i] + b[i];
       *r0 = make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]), __float_as_uint(f[3]));
       *r1 = make_uint4(__float_as_uint(f[4]), __float_as_uint(f[5]), __float_as_uint(f[6]), __float_as_uint(f[7]));
       uint4 o;
