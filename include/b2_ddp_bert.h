@@ -75,7 +75,7 @@ typedef struct b2_gemm_args {
   int32_t force_bn;       /* 0 = auto, else 128 / 192 / 256 (tests, tuning)                                  */
   int32_t force_splits;   /* 0 = auto, else >= 1                                                             */
   int32_t force_kernel;   /* 0 = auto, 1 = single-CTA 128xBN kernel, 2 = CTA-pair (cta_group::2) 256xBN kernel        */
-  void* debug_timing;     /* NULL, or device int64[grid][8]: clock64 stamps of the CTA-pair kernel's phases          */
+  void* debug_timing;     /* NULL, or device int64[grid][8]: clock64 phase stamps (CTA-pair GEMM, b2_gemm_ln_fwd)    */
   float* colsum_out;      /* NULL, or fp32 [N]: += column sums of the (bf16-rounded) output D, by atomic add        */
 } b2_gemm_args_t;
 

@@ -93,8 +93,8 @@ def timeline(M, N, K, p=0.1):
         torch.cuda.synchronize()
     t = stamps.cpu().double()
     d = t[:, 1:] - t[:, :-1]
-    names = ["entry -> set up", "-> accumulator complete", "-> pass 1 done", "-> cluster barrier", "-> pass 2 done",
-             "-> tiles written", "-> cluster drained"]
+    names = ["entry -> set up", "-> accumulator complete", "-> pass 1 done", "-> statistics complete", "-> pass 2 done",
+             "-> tiles read out", "-> cluster drained"]
     print("M %d N %d K %d: %d CTAs, SM cycles (mean / max over CTAs)" % (M, N, K, ctas))
     for i, n in enumerate(names):
         print("   %-26s %8.0f %8.0f" % (n, float(d[:, i].mean()), float(d[:, i].max())))
